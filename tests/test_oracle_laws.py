@@ -1,0 +1,106 @@
+"""Analytic anchors for what no reference test pins: tangent moduli vs finite
+differences, rigid-body null space, partition of unity, CSR pattern formula, PETSc-style COO->CSR."""
+import numpy as np
+import pytest
+from oracle import basis, fem, laws
+
+
+@pytest.mark.parametrize("law,iv", [
+    (laws.Poisson(2.5), ()),
+    (laws.LinearElastic(70e3, 0.3), ()),
+    (laws.NeoHookean(10.0, 0.3), ()),
+    (laws.NeoHookean(10.0, 0.3, clamp_J=True), (np.array([0.7, 1.3]),)),
+    (laws.SIMP(70e3, 70.0, 0.3), (np.array([0.4, 0.9]),)),
+])
+def test_tangent_matches_finite_difference(law, iv):
+    rng = np.random.default_rng(0)
+    ug = 0.1 * rng.standard_normal((2, 3, 3))
+    A = law.tangent(ug, *iv)
+    A_fd = laws.fd_tangent(law, ug, *iv, h=1e-6)
+    assert np.abs(A - A_fd).max() <= 1e-7 * max(1.0, np.abs(A).max())
+
+
+def test_dstress_dparam_fd():
+    rng = np.random.default_rng(1)
+    ug = 0.05 * rng.standard_normal((4, 3, 3))
+    th = np.array([0.3, 0.5, 0.7, 0.9])
+    for law in (laws.SIMP(70e3, 70.0, 0.3), laws.NeoHookean(10.0, 0.3, True)):
+        fd = (law.stress(ug, th + 1e-6) - law.stress(ug, th - 1e-6)) / 2e-6
+        assert np.abs(law.dstress_dparam(ug, th) - fd).max() <= 1e-6 * np.abs(fd).max()
+
+
+@pytest.mark.parametrize("ele", ["HEX8", "QUAD4", "HEX27"])
+def test_partition_of_unity_and_weights(ele):
+    vals, grads, w = basis.get_shape_vals_and_grads(ele)
+    assert np.allclose(vals.sum(1), 1.0, atol=1e-13)
+    assert np.allclose(grads.sum(1), 0.0, atol=1e-12)
+    assert abs(w.sum() - 1.0) < 1e-14
+    fv, fg, fw, fn, fi = basis.get_face_shape_vals_and_grads(ele)
+    assert np.allclose(fv.sum(2), 1.0, atol=1e-13) and np.allclose(fw.sum(1), 1.0)
+    assert {"HEX8": (8, 8), "QUAD4": (4, 4), "HEX27": (216, 27)}[ele] == vals.shape
+
+
+def test_hex27_nodes_are_vtk_triquadratic():
+    """After re_order the nodal points must be the VTK_TRIQUADRATIC_HEXAHEDRON lattice."""
+    _, _, degree, re = basis.get_elements("HEX27")
+    nodes = basis._lagrange_nodes(3, 2)[re]
+    vals, _ = basis.tabulate(3, 2, nodes)
+    assert np.allclose(vals[:, re], np.eye(27), atol=1e-13)          # nodal basis
+    vtk_corners = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    assert np.allclose(nodes[:8], vtk_corners)
+    edges = [(0, 1), (1, 2), (2, 3), (3, 0), (4, 5), (5, 6), (6, 7), (7, 4), (0, 4), (1, 5), (2, 6), (3, 7)]
+    for k, (a, b) in enumerate(edges):
+        assert np.allclose(nodes[8 + k], 0.5 * (vtk_corners[a] + vtk_corners[b]))
+    faces = [(0, 4, 7, 3), (1, 2, 6, 5), (0, 1, 5, 4), (3, 2, 6, 7), (0, 1, 2, 3), (4, 5, 6, 7)]
+    for k, f in enumerate(faces):
+        assert np.allclose(nodes[20 + k], vtk_corners[list(f)].mean(0))
+    assert np.allclose(nodes[26], 0.5)
+
+
+def test_rigid_body_null_space_and_symmetry():
+    mesh = fem.box_mesh(3, 2, 2, 1.0, 0.7, 0.9)
+    rng = np.random.default_rng(0)
+    mesh.points = mesh.points + 0.03 * rng.standard_normal(mesh.points.shape)      # non-affine cells
+    pb = fem.Problem(mesh, 3, 3, law=laws.LinearElastic(70e3, 0.3))
+    pb.newton_update(np.zeros((len(mesh.points), 3)))
+    A = fem.get_A(pb)
+    assert abs(A - A.T).max() < 1e-9 * abs(A).max()
+    x = mesh.points
+    modes = [np.tile(e, (len(x), 1)) for e in np.eye(3)] + \
+            [np.cross(e, x) for e in np.eye(3)]
+    for m in modes:
+        assert np.abs(A @ m.reshape(-1)).max() < 1e-9 * abs(A).max()
+
+
+def test_pattern_formula_and_coo_semantics():
+    N = 5
+    mesh = fem.box_mesh(N, N, N, 1, 1, 1)
+    pb = fem.Problem(mesh, 3, 3, dirichlet_bc_info=[[lambda p: np.isclose(p[0], 0.)], [1], [lambda p: 0.5]],
+                     law=laws.LinearElastic(1.0, 0.3))
+    pb.newton_update(np.zeros((len(mesh.points), 3)))
+    A = fem.get_A(pb)
+    assert A.nnz == 9 * (3 * (N + 1) - 2) ** 3
+    indptr, indices = fem.csr_pattern_from_cells(pb.cells, 3, pb.num_total_dofs_all_vars)
+    assert np.array_equal(indptr, A.indptr) and np.array_equal(indices, A.indices)
+    rows = pb.bc_rows()[0]
+    for r in rows[:7]:
+        row = A.getrow(r)
+        assert row.nnz == indptr[r + 1] - indptr[r]                   # pattern kept
+        assert row[0, r] == 1.0 and abs(row).sum() == 1.0             # zeroRows: unit diagonal
+
+
+def test_krylov_restatements_agree_with_direct_solve():
+    import scipy.sparse.linalg as spla
+    mesh = fem.box_mesh(4, 4, 4, 1, 1, 1)
+    bc = [[lambda p: np.isclose(p[0], 0.)] * 3, [0, 1, 2], [lambda p: 0.] * 3]
+    pb = fem.Problem(mesh, 3, 3, dirichlet_bc_info=bc, law=laws.LinearElastic(70e3, 0.3))
+    sol = np.zeros((len(mesh.points), 3))
+    res = fem.apply_bc_vec(pb.newton_update(sol).reshape(-1), sol.reshape(-1), pb)
+    A = fem.get_A(pb)
+    b = np.random.default_rng(0).standard_normal(A.shape[0])
+    b[np.concatenate(pb.bc_rows())] = 0.0
+    x_ref = spla.spsolve(A.tocsc(), b)
+    for method in ("bicgstab", "cg"):
+        x, k = fem.jax_solve(A, b, np.zeros_like(b), True, method, return_iters=True)
+        assert 0 < k < 500
+        assert np.abs(x - x_ref).max() <= 1e-8 * np.abs(x_ref).max()
