@@ -1,0 +1,136 @@
+/*
+ * fem_b200.h -- C ABI of the B200-native finite-element hot path (libfem_b200.so).
+ *
+ * Drop-in boundary for ONE path of deepmodeling/jax-fem (all citations relative to the reference
+ * tree): per-cell residual/tangent evaluation -> global sparse assembly -> Dirichlet row
+ * elimination -> Jacobi-preconditioned Krylov solve -> implicit adjoint.  The reference has no
+ * native FFI (it is pure Python on XLA/PETSc/SciPy); the entry points below are what a
+ * `jax.ffi` / ctypes binding for that path would bind, one per Python seam that is replaced.
+ * INTEGRATION.md shows the reference-side stubs.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; plain pointers and sizes
+ *     only, no library types.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - all functions are stream-ordered, allocate nothing, keep no global mutable state except the
+ *     thread-local error string, and return 0 on success or a negative FEM_E* code.
+ *   - float64 values, int32 indices (PETSc.IntType of the reference, jax_fem/solver.py:474-475).
+ *   - there is NO CPU fallback: every entry point fails with FEM_ENODEV when no CUDA device exists.
+ */
+#ifndef FEM_B200_H
+#define FEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FEM_OK 0
+#define FEM_EINVAL (-1)      /* bad argument / unregistered element-law combination            */
+#define FEM_ECUDA (-2)       /* CUDA runtime error (see fem_last_error)                         */
+#define FEM_ENODEV (-3)      /* no CUDA device: the product path never falls back to the CPU    */
+
+/* element types (jax_fem/basis.py:52-57, 58-65, 86-91) */
+#define FEM_ELE_HEX8 0
+#define FEM_ELE_QUAD4 1
+#define FEM_ELE_HEX27 2
+
+/* registered constitutive laws == the reference's get_tensor_map bodies          */
+#define FEM_LAW_POISSON 0         /* params: k                       ; optional per-quad scale   */
+#define FEM_LAW_LINEAR_ELASTIC 1  /* params: E, nu                                              */
+#define FEM_LAW_NEO_HOOKEAN 2     /* params: E, nu, clamp_J(0/1)     ; optional per-quad rho     */
+#define FEM_LAW_SIMP 3            /* params: Emax, Emin, nu, penal   ; REQUIRED per-quad theta   */
+
+const char* fem_last_error(void);
+int fem_version(void);
+/* number of CUDA devices visible, or FEM_ENODEV */
+int fem_device_count(void);
+
+/* ---- (1) element kernels: Problem.compute_residual_vars / compute_newton_vars
+ *      (jax_fem/problem.py:439-460) with the geometry of FiniteElement.get_shape_grads
+ *      (jax_fem/fe.py:112-141) recomputed in-kernel instead of materialised.
+ *
+ * ref_tables: [NQ*NN*DIM] reference shape gradients (q,n,d), then [NQ] quadrature weights
+ *             (jax_fem/basis.py:141-175), device memory.
+ * internal_var: (n_cells, NQ) per-quadrature-point parameter (problem.internal_vars[0],
+ *             jax_fem/problem.py:125,493-556) or NULL.
+ * Ke: (n_cells, ndof, ndof) row-major, row = test dof -- identical to the reference's
+ *     problem.V cell blocks (problem.py:265,453); NULL = residual only.
+ * Re: (n_cells, ndof) element residuals (weak_form_flat, problem.py:443).
+ */
+int fem_element_residual_jacobian(int ele_type, int vec, int law_id, const double* law_params_host,
+                                  const double* points, const int32_t* cells, int64_t n_cells,
+                                  const double* sol, const double* internal_var,
+                                  const double* ref_tables, double* Ke, double* Re, void* stream);
+
+/* ---- (2) global assembly: _PetscTangentCache.update / get_A (jax_fem/solver.py:469-553)
+ *      as a precomputed cell->CSR-slot permutation + deterministic segmented sum (no atomics).
+ *
+ * Node-block graph: brow_ptr (n_nodes+1), entries e in [brow_ptr[n], brow_ptr[n+1]) are the
+ * neighbour nodes of n in ascending order.  src_ptr (nnzb+1) / src: for block entry e the codes
+ * p = (c*NN + a)*NN + b of every (cell, local row node, local col node) contributing to it,
+ * ascending in p (fixed summation order => bit-reproducible).
+ * bc_flag (n_dofs) uint8: 1 on Dirichlet rows -> row zeroed, unit diagonal, pattern kept
+ * (Mat.zeroRows with KEEP_NONZERO_PATTERN, solver.py:477,527-528).
+ * data: CSR values for the scalar pattern (indptr[vec*n+i] = vec*vec*brow_ptr[n] + i*vec*len(n)).
+ */
+int fem_gather_csr(int vec, int nn, int64_t n_nodes, const int32_t* brow_ptr, const int32_t* bcol,
+                   const int32_t* src_ptr, const int32_t* src, const double* Ke,
+                   const uint8_t* bc_flag, double* data, void* stream);
+
+/* residual scatter-add of problem.py:426-437 as a per-node gather: nc_ptr (n_nodes+1) / nc codes
+ * c*NN + a ascending; res = sum Re + f_ext (f_ext may be NULL).                                  */
+int fem_gather_residual(int vec, int nn, int64_t n_nodes, const int32_t* nc_ptr, const int32_t* nc,
+                        const double* Re, const double* f_ext, double* res, void* stream);
+
+/* ---- (3) Dirichlet operations (jax_fem/solver.py:290-363) on merged (last-wins) row lists    */
+/* apply_bc_vec: res[row] = sol[row] - val*scale                                                  */
+int fem_apply_bc_vec(int64_t n_bc, const int32_t* bc_rows, const double* bc_vals, double scale,
+                     const double* sol, double* res, void* stream);
+/* x0 = assign_bc(0) - copy_bc(dofs): x0 = 0, x0[row] = val - dofs[row]   (solver.py:402-409)     */
+int fem_bc_initial_guess(int64_t n, int64_t n_bc, const int32_t* bc_rows, const double* bc_vals,
+                         const double* dofs, double* x0, void* stream);
+
+/* ---- (3) sparse kernels and Krylov solvers: jax_solve (jax_fem/solver.py:63-92)               */
+int fem_spmv(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
+             const double* x, double* y, void* stream);
+/* diag[i] = A[i,i] (jacobi = A.diagonal(), solver.py:68)                                          */
+int fem_csr_diagonal(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
+                     double* diag, void* stream);
+/* transpose of a structurally symmetric node-block CSR (A.transpose(A_T), solver.py:1407-1408):
+ * tperm (nnzb) maps block entry (n,m) -> entry (m,n).                                             */
+int fem_csr_transpose_values(int vec, int64_t n_nodes, const int32_t* brow_ptr, const int32_t* bcol,
+                             const int32_t* tperm, const double* data, double* data_t, void* stream);
+
+/* workspace (in doubles) for the solvers below */
+int64_t fem_krylov_workspace(int64_t n);
+
+/* Jacobi-preconditioned CG / BiCGSTAB, whole solve on the device, same recurrences and stopping
+ * rule as jax.scipy.sparse.linalg.cg / bicgstab: stop when ||r||^2 <= max(tol^2 ||b||^2, atol^2).
+ * x holds x0 on entry and the solution on exit.  diag = NULL means no preconditioner.
+ * info_host[0] = iterations (negative on breakdown as in JAX), info_host[1] = final ||r||^2,
+ * info_host[2] = ||A x - b|| (the reference's post-check, solver.py:87).
+ * check_every: iterations between host polls of the device-side convergence flag.               */
+int fem_pcg(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
+            const double* diag, const double* b, double* x, double tol, double atol, int maxiter,
+            int check_every, double* workspace, double* info_host, void* stream);
+int fem_pbicgstab(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
+                  const double* diag, const double* b, double* x, double tol, double atol, int maxiter,
+                  int check_every, double* workspace, double* info_host, void* stream);
+
+/* ---- (4) implicit adjoint: -lambda^T dc/dtheta per quadrature point
+ *      (jax_fem/solver.py:1386-1394,1414-1416) for per-quad parameters; lambda must already be
+ *      zero on Dirichlet rows (BC rows of c do not depend on theta).  grad: (n_cells, NQ).       */
+int fem_adjoint_param_grad(int ele_type, int vec, int law_id, const double* law_params_host,
+                           const double* points, const int32_t* cells, int64_t n_cells,
+                           const double* sol, const double* internal_var, const double* lam,
+                           const double* ref_tables, double* grad, void* stream);
+
+/* small helpers used by the Newton loop */
+int fem_dot(int64_t n, const double* x, const double* y, double* result_host, double* workspace, void* stream);
+int fem_axpy(int64_t n, double alpha, const double* x, double* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEM_B200_H */

@@ -1,0 +1,582 @@
+// Element kernels: per-cell residual and tangent for the registered constitutive laws.
+//
+// Replaces Problem.compute_residual_vars / compute_newton_vars (jax_fem/problem.py:439-460), i.e.
+// get_laplace_kernel (:189-214) + value_and_jacfwd (:262-266), with the geometry of
+// FiniteElement.get_shape_grads (jax_fem/fe.py:112-141) recomputed per cell instead of being
+// materialised as (C,Q,N,dim) arrays.
+//
+// Thread mapping: NN consecutive lanes own one cell (NN == NQ for HEX8 and QUAD4).
+//   phase 1: lane = quadrature point q.  J, det, J^-1, physical gradients g[n][:], JxW,
+//            grad u, stress and the law's tangent data -> shared-memory record of (cell, q).
+//   phase 2: lane = local node a.  r_a = sum_q S_q g_a(q);  K row block (a, :) accumulated in
+//            registers from broadcast shared-memory reads of g_b(q) (all NN lanes of a cell read
+//            the same address), closed-form tangents -- no AD, no per-cell (24x24) temporaries.
+#include "common.cuh"
+
+namespace femb200 {
+namespace {
+
+template <int DIM>
+__device__ __forceinline__ double det_inv(const double (&J)[DIM][DIM], double (&inv)[DIM][DIM]);
+
+template <>
+__device__ __forceinline__ double det_inv<2>(const double (&J)[2][2], double (&inv)[2][2]) {
+  const double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+  const double r = 1.0 / det;
+  inv[0][0] = J[1][1] * r;
+  inv[0][1] = -J[0][1] * r;
+  inv[1][0] = -J[1][0] * r;
+  inv[1][1] = J[0][0] * r;
+  return det;
+}
+
+template <>
+__device__ __forceinline__ double det_inv<3>(const double (&J)[3][3], double (&inv)[3][3]) {
+  const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+  const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+  const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+  const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+  const double r = 1.0 / det;
+  inv[0][0] = c00 * r;
+  inv[1][0] = c01 * r;
+  inv[2][0] = c02 * r;
+  inv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * r;
+  inv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * r;
+  inv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * r;
+  inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * r;
+  inv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * r;
+  inv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * r;
+  return det;
+}
+
+constexpr int pad_odd(int x) { return (x % 2) ? x : x + 1; }
+
+// Law-specific extra doubles in a (cell, q) record.
+template <int LAW, int NN, int DIM>
+struct LawExtra {
+  static constexpr int value = 1;   // Poisson: k_q * w ; isotropic elasticity: E_q * w
+};
+template <int NN, int DIM>
+struct LawExtra<FEM_LAW_NEO_HOOKEAN, NN, DIM> {
+  static constexpr int value = 2 * NN * DIM + 4;   // f_n = F g_n, h_n = F^-T g_n, c1..c4
+};
+
+template <int NN, int DIM, int VEC, int LAW>
+struct Layout {
+  static constexpr int NQ = NN;
+  static constexpr int ND = NN * VEC;
+  static constexpr int TAB_STRIDE = pad_odd(NN * DIM);      // per-q stride of the dN table (bank spread)
+  static constexpr int TAB_SIZE = NQ * TAB_STRIDE + NQ;     // + quadrature weights
+  static constexpr int OFF_G = 0;                           // g[NN][DIM]
+  static constexpr int OFF_W = NN * DIM;                    // JxW
+  static constexpr int OFF_S = OFF_W + 1;                   // S[VEC][DIM] = sigma * JxW
+  static constexpr int OFF_X = OFF_S + VEC * DIM;           // law extras
+  static constexpr int REC = pad_odd(OFF_X + LawExtra<LAW, NN, DIM>::value);
+  static constexpr int OFF_XN = 0;                          // X[NN][DIM] node coordinates
+  static constexpr int OFF_UN = NN * DIM;                   // U[NN][VEC] nodal solution
+  static constexpr int OFF_REC = NN * DIM + NN * VEC;
+  static constexpr int CELL_RAW = OFF_REC + NQ * REC;
+  // cell stride == 8 (mod 16) doubles: the two cells of a half-warp hit disjoint bank sets
+  static constexpr int CELL = CELL_RAW + ((8 - CELL_RAW % 16) + 16) % 16;
+};
+
+struct ElemArgs {
+  const double* points;
+  const int32_t* cells;
+  const double* sol;
+  const double* iv;      // (C, NQ) or nullptr
+  const double* lam;     // adjoint vector (nodes, vec) for the parameter-gradient kernel
+  const double* ref;     // [NQ*NN*DIM] dN, [NQ] w
+  double* Ke;
+  double* Re;
+  double* grad;          // (C, NQ)
+  int64_t C;
+  double p[8];
+};
+
+// ---- phase-1 building blocks -------------------------------------------------------------------
+template <int NN, int DIM>
+__device__ __forceinline__ double qp_geometry(const double* __restrict__ X, const double* __restrict__ tabq,
+                                              double wq, double (&g)[NN][DIM]) {
+  double J[DIM][DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d)
+#pragma unroll
+    for (int e = 0; e < DIM; ++e) J[d][e] = 0.0;
+#pragma unroll
+  for (int n = 0; n < NN; ++n)
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+#pragma unroll
+      for (int e = 0; e < DIM; ++e) J[d][e] = fma(X[n * DIM + d], tabq[n * DIM + e], J[d][e]);   // fe.py:132
+  double inv[DIM][DIM];
+  const double det = det_inv<DIM>(J, inv);                                                      // fe.py:134-135
+#pragma unroll
+  for (int n = 0; n < NN; ++n)
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      double s = 0.0;
+#pragma unroll
+      for (int e = 0; e < DIM; ++e) s = fma(tabq[n * DIM + e], inv[e][d], s);                   // fe.py:138-139
+      g[n][d] = s;
+    }
+  return det * wq;                                                                              // fe.py:140
+}
+
+template <int NN, int DIM, int VEC>
+__device__ __forceinline__ void qp_grad_u(const double* __restrict__ U, const double (&g)[NN][DIM],
+                                          double (&ug)[VEC][DIM]) {
+#pragma unroll
+  for (int i = 0; i < VEC; ++i)
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) ug[i][d] = 0.0;
+#pragma unroll
+  for (int n = 0; n < NN; ++n)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) ug[i][d] = fma(U[n * VEC + i], g[n][d], ug[i][d]);          // problem.py:204-205
+}
+
+// Young's modulus at a quadrature point for the isotropic laws, and its derivative wrt theta.
+template <int LAW>
+__device__ __forceinline__ double iso_modulus(const double* p, const double* ivq, bool derivative) {
+  if constexpr (LAW == FEM_LAW_SIMP) {
+    const double theta = *ivq;
+    if (derivative) return (p[0] - p[1]) * p[3] * pow(theta, p[3] - 1.0);
+    return p[1] + (p[0] - p[1]) * pow(theta, p[3]);
+  } else {
+    return p[0];
+  }
+}
+template <int LAW>
+__device__ __forceinline__ double iso_nu(const double* p) {
+  return LAW == FEM_LAW_SIMP ? p[2] : p[1];
+}
+
+template <int DIM>
+__device__ __forceinline__ void iso_stress(double lam, double mu, const double (&ug)[DIM][DIM], double (&sig)[DIM][DIM]) {
+  double tr = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) tr += ug[d][d];
+#pragma unroll
+  for (int i = 0; i < DIM; ++i)
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) sig[i][d] = mu * (ug[i][d] + ug[d][i]) + (i == d ? lam * tr : 0.0);
+}
+
+struct NHPoint {
+  double F[3][3], H[3][3];   // H = F^-T
+  double J, I1, m;           // m = mu J^-2/3
+};
+
+__device__ __forceinline__ void nh_kinematics(const double (&ug)[3][3], double mu, bool clamp, NHPoint& k) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) k.F[i][j] = ug[i][j] + (i == j ? 1.0 : 0.0);
+  double Finv[3][3];
+  double J = det_inv<3>(k.F, Finv);
+  if (clamp) J = fmax(J, 1e-14);
+  k.J = J;
+  k.I1 = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      k.H[i][j] = Finv[j][i];
+      k.I1 = fma(k.F[i][j], k.F[i][j], k.I1);
+    }
+  k.m = mu * pow(J, -2.0 / 3.0);
+}
+
+__device__ __forceinline__ void nh_stress(const NHPoint& k, double kappa, double (&P)[3][3]) {
+  const double a = k.I1 / 3.0, b = kappa * (k.J - 1.0) * k.J;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) P[i][j] = k.m * (k.F[i][j] - a * k.H[i][j]) + b * k.H[i][j];
+}
+
+// ---- the element kernel ----------------------------------------------------------------------------
+template <int NN, int DIM, int VEC, int LAW, int CPB, bool JAC>
+__global__ void __launch_bounds__(CPB* NN) element_kernel(const ElemArgs A) {
+  using L = Layout<NN, DIM, VEC, LAW>;
+  constexpr int NQ = L::NQ, ND = L::ND;
+  extern __shared__ double sm[];
+  double* tab = sm;
+  const int lc = threadIdx.x / NN, lane = threadIdx.x % NN;
+  double* cb = sm + L::TAB_SIZE + lc * L::CELL;
+  const int64_t c = (int64_t)blockIdx.x * CPB + lc;
+  const bool active = c < A.C;
+
+  for (int i = threadIdx.x; i < NQ * NN * DIM; i += CPB * NN)
+    tab[(i / (NN * DIM)) * L::TAB_STRIDE + i % (NN * DIM)] = A.ref[i];
+  if (threadIdx.x < NQ) tab[NQ * L::TAB_STRIDE + threadIdx.x] = A.ref[NQ * NN * DIM + threadIdx.x];
+  if (active) {
+    const int64_t node = A.cells[c * NN + lane];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) cb[L::OFF_XN + lane * DIM + d] = A.points[node * DIM + d];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) cb[L::OFF_UN + lane * VEC + i] = A.sol[node * VEC + i];
+  }
+  __syncthreads();
+
+  // ---------------- phase 1: lane = quadrature point ----------------
+  if (active) {
+    const int q = lane;
+    double g[NN][DIM];
+    const double w = qp_geometry<NN, DIM>(cb + L::OFF_XN, tab + q * L::TAB_STRIDE, tab[NQ * L::TAB_STRIDE + q], g);
+    double ug[VEC][DIM];
+    qp_grad_u<NN, DIM, VEC>(cb + L::OFF_UN, g, ug);
+    double* rec = cb + L::OFF_REC + q * L::REC;
+#pragma unroll
+    for (int n = 0; n < NN; ++n)
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) rec[L::OFF_G + n * DIM + d] = g[n][d];
+    rec[L::OFF_W] = w;
+    const double* ivq = A.iv ? A.iv + c * NQ + q : nullptr;
+
+    if constexpr (LAW == FEM_LAW_POISSON) {
+      const double kq = A.p[0] * (ivq ? *ivq : 1.0);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i)
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) rec[L::OFF_S + i * DIM + d] = kq * ug[i][d] * w;
+      rec[L::OFF_X] = kq * w;
+    } else if constexpr (LAW == FEM_LAW_LINEAR_ELASTIC || LAW == FEM_LAW_SIMP) {
+      static_assert(VEC == DIM, "elasticity needs vec == dim");
+      const double E = iso_modulus<LAW>(A.p, ivq, false), nu = iso_nu<LAW>(A.p);
+      const double mu = E / (2.0 * (1.0 + nu)), lam = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
+      double sig[DIM][DIM];
+      iso_stress<DIM>(lam, mu, ug, sig);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i)
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) rec[L::OFF_S + i * DIM + d] = sig[i][d] * w;
+      rec[L::OFF_X] = E * w;
+    } else {   // Neo-Hookean
+      static_assert(VEC == 3 && DIM == 3, "Neo-Hookean is 3-D");
+      const double E = A.p[0] * (ivq ? *ivq : 1.0), nu = A.p[1];
+      const double mu = E / (2.0 * (1.0 + nu)), kappa = E / (3.0 * (1.0 - 2.0 * nu));
+      NHPoint k;
+      nh_kinematics(ug, mu, A.p[2] != 0.0, k);
+      double P[3][3];
+      nh_stress(k, kappa, P);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) rec[L::OFF_S + i * 3 + d] = P[i][d] * w;
+      if constexpr (JAC) {
+        double* f = rec + L::OFF_X;
+        double* h = f + NN * 3;
+#pragma unroll
+        for (int n = 0; n < NN; ++n)
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            double sf = 0.0, sh = 0.0;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              sf = fma(k.F[i][j], g[n][j], sf);
+              sh = fma(k.H[i][j], g[n][j], sh);
+            }
+            f[n * 3 + i] = sf;
+            h[n * 3 + i] = sh;
+          }
+        double* cc = h + NN * 3;
+        cc[0] = k.m * w;                                                             // delta_ik (g_a . g_b)
+        cc[1] = -(2.0 / 3.0) * k.m * w;                                              // f_a h_b + h_a f_b
+        cc[2] = ((2.0 / 9.0) * k.m * k.I1 + kappa * (2.0 * k.J - 1.0) * k.J) * w;    // h_a h_b
+        cc[3] = (k.m * k.I1 / 3.0 - kappa * (k.J - 1.0) * k.J) * w;                  // h_b h_a (swapped)
+      }
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+
+  // ---------------- phase 2: lane = local node a ----------------
+  const int a = lane;
+  const double* recs = cb + L::OFF_REC;
+  {
+    double r[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) r[i] = 0.0;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const double* rec = recs + q * L::REC;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i)
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) r[i] = fma(rec[L::OFF_S + i * DIM + d], rec[L::OFF_G + a * DIM + d], r[i]);   // problem.py:210
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) A.Re[c * ND + a * VEC + i] = r[i];
+  }
+  if constexpr (!JAC) return;
+
+  double* Krow = A.Ke + c * (int64_t)(ND * ND) + (int64_t)a * VEC * ND;
+  if constexpr (LAW == FEM_LAW_POISSON) {
+    double G[NN];
+#pragma unroll
+    for (int b = 0; b < NN; ++b) G[b] = 0.0;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const double* rec = recs + q * L::REC;
+      double ga[DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) ga[d] = rec[L::OFF_G + a * DIM + d] * rec[L::OFF_X];
+#pragma unroll
+      for (int b = 0; b < NN; ++b)
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) G[b] = fma(ga[d], rec[L::OFF_G + b * DIM + d], G[b]);
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+#pragma unroll
+      for (int b = 0; b < NN; ++b)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) Krow[i * ND + b * VEC + k] = (i == k) ? G[b] : 0.0;
+  } else if constexpr (LAW == FEM_LAW_LINEAR_ELASTIC || LAW == FEM_LAW_SIMP) {
+    // K_ab[i][k] = lam' G[i][k] + mu' G[k][i] + mu' tr(G) delta_ik,  G = sum_q E_q w_q g_a (x) g_b
+    double G[NN][DIM][DIM];
+#pragma unroll
+    for (int b = 0; b < NN; ++b)
+#pragma unroll
+      for (int i = 0; i < DIM; ++i)
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) G[b][i][k] = 0.0;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const double* rec = recs + q * L::REC;
+      double ga[DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) ga[d] = rec[L::OFF_G + a * DIM + d] * rec[L::OFF_X];
+#pragma unroll
+      for (int b = 0; b < NN; ++b) {
+        double gb[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) gb[d] = rec[L::OFF_G + b * DIM + d];
+#pragma unroll
+        for (int i = 0; i < DIM; ++i)
+#pragma unroll
+          for (int k = 0; k < DIM; ++k) G[b][i][k] = fma(ga[i], gb[k], G[b][i][k]);
+      }
+    }
+    const double nu = iso_nu<LAW>(A.p);
+    const double mu1 = 1.0 / (2.0 * (1.0 + nu)), lam1 = nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
+#pragma unroll
+    for (int b = 0; b < NN; ++b) {
+      double tr = 0.0;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) tr += G[b][d][d];
+#pragma unroll
+      for (int i = 0; i < DIM; ++i)
+#pragma unroll
+        for (int k = 0; k < DIM; ++k)
+          Krow[i * ND + b * VEC + k] = lam1 * G[b][i][k] + mu1 * G[b][k][i] + (i == k ? mu1 * tr : 0.0);
+    }
+  } else {
+    // Neo-Hookean: K_ab[i][k] = c1 (g_a.g_b) d_ik + (c2 f_a + c3 h_a)_i h_b[k] + c2 h_a[i] f_b[k] + c4 h_b[i] h_a[k]
+    double K[NN][3][3];
+#pragma unroll
+    for (int b = 0; b < NN; ++b)
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) K[b][i][k] = 0.0;
+#pragma unroll 1
+    for (int q = 0; q < NQ; ++q) {
+      const double* rec = recs + q * L::REC;
+      const double* f = rec + L::OFF_X;
+      const double* h = f + NN * 3;
+      const double* cc = h + NN * 3;
+      const double c1 = cc[0], c2 = cc[1], c3 = cc[2], c4 = cc[3];
+      double ga[3], pa[3], qa[3], ra[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double fa = f[a * 3 + i], ha = h[a * 3 + i];
+        ga[i] = c1 * rec[L::OFF_G + a * 3 + i];
+        pa[i] = c2 * fa + c3 * ha;
+        qa[i] = c2 * ha;
+        ra[i] = c4 * ha;
+      }
+#pragma unroll
+      for (int b = 0; b < NN; ++b) {
+        double gb[3], fb[3], hb[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          gb[i] = rec[L::OFF_G + b * 3 + i];
+          fb[i] = f[b * 3 + i];
+          hb[i] = h[b * 3 + i];
+        }
+        const double dgg = ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            double v = K[b][i][k];
+            v = fma(pa[i], hb[k], v);
+            v = fma(qa[i], fb[k], v);
+            v = fma(hb[i], ra[k], v);
+            K[b][i][k] = v;
+          }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) K[b][i][i] += dgg;
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < NN; ++b)
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) Krow[i * ND + b * 3 + k] = K[b][i][k];
+  }
+}
+
+// ---- adjoint: -lambda^T dc/dtheta per quadrature point (thread per (cell, q)) -------------------
+template <int NN, int DIM, int VEC, int LAW, int CPB>
+__global__ void __launch_bounds__(CPB* NN) param_grad_kernel(const ElemArgs A) {
+  using L = Layout<NN, DIM, VEC, LAW>;
+  constexpr int NQ = L::NQ;
+  extern __shared__ double sm[];
+  double* tab = sm;
+  const int lc = threadIdx.x / NN, q = threadIdx.x % NN;
+  // per cell: X, U, LAM
+  double* cb = sm + L::TAB_SIZE + lc * (NN * DIM + 2 * NN * VEC);
+  const int64_t c = (int64_t)blockIdx.x * CPB + lc;
+  const bool active = c < A.C;
+  for (int i = threadIdx.x; i < NQ * NN * DIM; i += CPB * NN)
+    tab[(i / (NN * DIM)) * L::TAB_STRIDE + i % (NN * DIM)] = A.ref[i];
+  if (threadIdx.x < NQ) tab[NQ * L::TAB_STRIDE + threadIdx.x] = A.ref[NQ * NN * DIM + threadIdx.x];
+  double* Xs = cb;
+  double* Us = cb + NN * DIM;
+  double* Ls = Us + NN * VEC;
+  if (active) {
+    const int64_t node = A.cells[c * NN + q];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) Xs[q * DIM + d] = A.points[node * DIM + d];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      Us[q * VEC + i] = A.sol[node * VEC + i];
+      Ls[q * VEC + i] = A.lam[node * VEC + i];
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+  double g[NN][DIM];
+  const double w = qp_geometry<NN, DIM>(Xs, tab + q * L::TAB_STRIDE, tab[NQ * L::TAB_STRIDE + q], g);
+  double ug[VEC][DIM];
+  qp_grad_u<NN, DIM, VEC>(Us, g, ug);
+  const double* ivq = A.iv + c * NQ + q;
+  double ds[VEC][DIM];
+  if constexpr (LAW == FEM_LAW_POISSON) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) ds[i][d] = A.p[0] * ug[i][d];
+  } else if constexpr (LAW == FEM_LAW_LINEAR_ELASTIC || LAW == FEM_LAW_SIMP) {
+    const double dE = iso_modulus<LAW>(A.p, ivq, true), nu = iso_nu<LAW>(A.p);
+    iso_stress<DIM>(dE * nu / ((1.0 + nu) * (1.0 - 2.0 * nu)), dE / (2.0 * (1.0 + nu)), ug, ds);
+  } else {
+    const double E = A.p[0], nu = A.p[1];      // P is linear in E: dP/drho = P(rho = 1)
+    NHPoint k;
+    nh_kinematics(ug, E / (2.0 * (1.0 + nu)), A.p[2] != 0.0, k);
+    nh_stress(k, E / (3.0 * (1.0 - 2.0 * nu)), ds);
+  }
+  double acc = 0.0;
+#pragma unroll
+  for (int n = 0; n < NN; ++n)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      double t = 0.0;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) t = fma(ds[i][d], g[n][d], t);
+      acc = fma(Ls[n * VEC + i], t, acc);
+    }
+  A.grad[c * NQ + q] = -acc * w;
+}
+
+template <int NN, int DIM, int VEC, int LAW, int CPB>
+int launch_element(const ElemArgs& A, cudaStream_t st) {
+  using L = Layout<NN, DIM, VEC, LAW>;
+  const size_t smem = sizeof(double) * (L::TAB_SIZE + (size_t)CPB * L::CELL);
+  const unsigned grid = (unsigned)((A.C + CPB - 1) / CPB);
+  if (A.Ke) {
+    auto k = element_kernel<NN, DIM, VEC, LAW, CPB, true>;
+    FEM_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, CPB * NN, smem, st>>>(A);
+  } else {
+    auto k = element_kernel<NN, DIM, VEC, LAW, CPB, false>;
+    FEM_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, CPB * NN, smem, st>>>(A);
+  }
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
+}
+
+template <int NN, int DIM, int VEC, int LAW, int CPB>
+int launch_param_grad(const ElemArgs& A, cudaStream_t st) {
+  using L = Layout<NN, DIM, VEC, LAW>;
+  const size_t smem = sizeof(double) * (L::TAB_SIZE + (size_t)CPB * (NN * DIM + 2 * NN * VEC));
+  const unsigned grid = (unsigned)((A.C + CPB - 1) / CPB);
+  auto k = param_grad_kernel<NN, DIM, VEC, LAW, CPB>;
+  FEM_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<grid, CPB * NN, smem, st>>>(A);
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
+}
+
+// Registry of (element, vec, law) combinations.  Anything else is an error, never a fallback.
+template <bool GRAD>
+int dispatch(int ele, int vec, int law, const ElemArgs& A, cudaStream_t st) {
+#define FEM_CASE(ELE, NN, DIM, VEC, LAW, CPB)                                     \
+  if (ele == ELE && vec == VEC && law == LAW) {                                   \
+    if constexpr (GRAD) return launch_param_grad<NN, DIM, VEC, LAW, CPB>(A, st);  \
+    else return launch_element<NN, DIM, VEC, LAW, CPB>(A, st);                    \
+  }
+  FEM_CASE(FEM_ELE_HEX8, 8, 3, 1, FEM_LAW_POISSON, 32)
+  FEM_CASE(FEM_ELE_HEX8, 8, 3, 3, FEM_LAW_LINEAR_ELASTIC, 32)
+  FEM_CASE(FEM_ELE_HEX8, 8, 3, 3, FEM_LAW_SIMP, 32)
+  FEM_CASE(FEM_ELE_HEX8, 8, 3, 3, FEM_LAW_NEO_HOOKEAN, 16)
+  FEM_CASE(FEM_ELE_QUAD4, 4, 2, 1, FEM_LAW_POISSON, 64)
+  FEM_CASE(FEM_ELE_QUAD4, 4, 2, 2, FEM_LAW_LINEAR_ELASTIC, 64)
+  FEM_CASE(FEM_ELE_QUAD4, 4, 2, 2, FEM_LAW_SIMP, 64)
+#undef FEM_CASE
+  set_error("unregistered (element=%d, vec=%d, law=%d) combination: no kernel, no fallback", ele, vec, law);
+  return FEM_EINVAL;
+}
+
+}  // namespace
+}  // namespace femb200
+
+using namespace femb200;
+
+extern "C" int fem_element_residual_jacobian(int ele_type, int vec, int law_id, const double* law_params_host,
+                                             const double* points, const int32_t* cells, int64_t n_cells,
+                                             const double* sol, const double* internal_var,
+                                             const double* ref_tables, double* Ke, double* Re, void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(points && cells && sol && ref_tables && Re && law_params_host, "null pointer");
+  FEM_REQUIRE(n_cells >= 0, "n_cells < 0");
+  FEM_REQUIRE(!(law_id == FEM_LAW_SIMP && !internal_var), "SIMP needs the per-quadrature-point density");
+  if (n_cells == 0) return FEM_OK;
+  ElemArgs A{};
+  A.points = points; A.cells = cells; A.sol = sol; A.iv = internal_var; A.ref = ref_tables;
+  A.Ke = Ke; A.Re = Re; A.C = n_cells;
+  for (int i = 0; i < 8; ++i) A.p[i] = law_params_host[i];
+  return dispatch<false>(ele_type, vec, law_id, A, (cudaStream_t)stream);
+}
+
+extern "C" int fem_adjoint_param_grad(int ele_type, int vec, int law_id, const double* law_params_host,
+                                      const double* points, const int32_t* cells, int64_t n_cells,
+                                      const double* sol, const double* internal_var, const double* lam,
+                                      const double* ref_tables, double* grad, void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(points && cells && sol && ref_tables && lam && grad && internal_var && law_params_host, "null pointer");
+  if (n_cells == 0) return FEM_OK;
+  ElemArgs A{};
+  A.points = points; A.cells = cells; A.sol = sol; A.iv = internal_var; A.lam = lam; A.ref = ref_tables;
+  A.grad = grad; A.C = n_cells;
+  for (int i = 0; i < 8; ++i) A.p[i] = law_params_host[i];
+  return dispatch<true>(ele_type, vec, law_id, A, (cudaStream_t)stream);
+}

@@ -1,0 +1,449 @@
+// Jacobi-preconditioned CG and BiCGSTAB, whole solve resident on the device.
+//
+// Replaces jax_solve (jax_fem/solver.py:63-92): CSR -> BCOO -> jax.scipy.sparse.linalg.bicgstab with
+// M = 1/diag(A).  Same recurrences, same stopping rule (||r||^2 <= max(tol^2 ||b||^2, atol^2)), same
+// breakdown codes as JAX's _bicgstab_solve / _cg_solve; every scalar (alpha, beta, omega, rho, the
+// iteration counter and the convergence flag) lives in device memory and is produced by the last
+// block of the kernel that completes the corresponding dot product, so an iteration is a fixed
+// sequence of launches with no host round trip.  The host polls the flag every `check_every`
+// iterations; kernels launched after convergence return immediately.
+//
+// Dot products are fused into the SpMV / vector-update kernels that produce their operands and are
+// reduced in a fixed order (warp butterfly -> per-block partial -> last block sums partials by index),
+// so results are bit-reproducible run to run.
+#include "common.cuh"
+
+namespace femb200 {
+int launch_spmv(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data, const double* x,
+                double* y, cudaStream_t st);
+
+namespace {
+
+constexpr int kBlocks = kNumSM * 8;   // upper bound of any persistent grid (sizes the partial buffer)
+constexpr int kThreads = 256;
+constexpr int kScalars = 64;
+constexpr int kMaxDots = 4;
+
+// scalar slots (doubles) at the start of the workspace
+enum {
+  S_GAMMA = 0,   // CG: r.z ; BiCGSTAB: rho (previous)
+  S_ALPHA = 1,
+  S_BETA = 2,
+  S_OMEGA = 3,
+  S_RR = 4,      // ||r||^2
+  S_ATOL2 = 5,
+  S_K = 6,       // iteration counter (JAX breakdown codes -10 / -11)
+  S_DONE = 7,
+  S_MAXIT = 8,
+  S_RHO_NEW = 9, // BiCGSTAB: rhat.r for the coming iteration
+  S_EARLY = 10,  // BiCGSTAB: exit_early
+  S_TOL2 = 11,
+  S_ATOLIN2 = 12,
+  S_TMP = 13,
+  S_TICKET = 32  // unsigned counter (reinterpreted)
+};
+
+struct Ws {
+  double* s;        // scalars
+  double* partial;  // kBlocks * kMaxDots
+  double* v[8];     // vectors
+};
+
+__host__ __device__ inline int64_t pad_n(int64_t n) { return (n + 31) / 32 * 32; }
+
+inline Ws carve(double* w, int64_t n) {
+  Ws o;
+  o.s = w;
+  o.partial = w + kScalars;
+  double* base = o.partial + (int64_t)kBlocks * kMaxDots;
+  for (int i = 0; i < 8; ++i) o.v[i] = base + i * pad_n(n);
+  return o;
+}
+
+// Block partials -> global; the last block to arrive sums them in index order and runs `fin`.
+template <int NV, class Fin>
+__device__ __forceinline__ void reduce_and_finalize(double (&v)[NV], double* __restrict__ S,
+                                                    double* __restrict__ partial, Fin fin) {
+  __shared__ double red[NV * (kThreads / 32)];
+  __shared__ bool is_last;
+  block_sum<NV, kThreads>(v, red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) partial[(int64_t)k * gridDim.x + blockIdx.x] = v[k];
+    __threadfence();
+    const unsigned t = atomicAdd(reinterpret_cast<unsigned*>(S + S_TICKET), 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double tot[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double a = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) a += __ldcg(partial + (int64_t)k * gridDim.x + i);
+    tot[k] = a;
+  }
+  __syncthreads();
+  block_sum<NV, kThreads>(tot, red);
+  if (threadIdx.x == 0) {
+    *reinterpret_cast<unsigned*>(S + S_TICKET) = 0u;
+    fin(tot);
+    __threadfence();
+  }
+}
+
+__device__ __forceinline__ bool solver_done(const double* S) { return __ldcg(S + S_DONE) != 0.0; }
+
+// y = A x over a persistent grid, LPR lanes per row, optional fused dots with (row) entries.
+// MODE 0: plain.  MODE 1 (CG): dot0 = d1[row]*y[row] -> alpha = gamma/dot0.
+// MODE 2 (BiCGSTAB q = A phat): dot0 = rhat.q -> alpha = rho_new/dot0.
+// MODE 3 (BiCGSTAB t = A shat): dot0 = t.s, dot1 = t.t -> omega = dot0/dot1.
+template <int LPR, int MODE>
+__global__ void __launch_bounds__(kThreads) spmv_fused_kernel(int64_t n, const int32_t* __restrict__ indptr,
+                                                              const int32_t* __restrict__ indices,
+                                                              const double* __restrict__ data,
+                                                              const double* __restrict__ x, double* __restrict__ y,
+                                                              const double* __restrict__ d1, double* __restrict__ S,
+                                                              double* __restrict__ partial) {
+  if (MODE != 0 && solver_done(S)) return;
+  constexpr int RPB = kThreads / LPR;
+  const int sub = threadIdx.x % LPR;
+  double dots[2] = {0.0, 0.0};
+  for (int64_t row = (int64_t)blockIdx.x * RPB + threadIdx.x / LPR; row < n; row += (int64_t)gridDim.x * RPB) {
+    const int s = indptr[row], e = indptr[row + 1];
+    double a0 = 0.0, a1 = 0.0;
+    int j = s + sub;
+    for (; j + LPR < e; j += 2 * LPR) {
+      const double v0 = data[j], v1 = data[j + LPR];
+      const int c0 = indices[j], c1 = indices[j + LPR];
+      a0 = fma(v0, __ldg(x + c0), a0);
+      a1 = fma(v1, __ldg(x + c1), a1);
+    }
+    if (j < e) a0 = fma(data[j], __ldg(x + indices[j]), a0);
+    double acc = a0 + a1;
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (sub == 0) {
+      y[row] = acc;
+      if (MODE == 1 || MODE == 2) dots[0] = fma(d1[row], acc, dots[0]);
+      if (MODE == 3) {
+        dots[0] = fma(acc, d1[row], dots[0]);
+        dots[1] = fma(acc, acc, dots[1]);
+      }
+    }
+  }
+  if constexpr (MODE == 1) {
+    double v[1] = {dots[0]};
+    reduce_and_finalize<1>(v, S, partial, [&](double (&t)[1]) { S[S_ALPHA] = S[S_GAMMA] / t[0]; });
+  } else if constexpr (MODE == 2) {
+    double v[1] = {dots[0]};
+    reduce_and_finalize<1>(v, S, partial, [&](double (&t)[1]) { S[S_ALPHA] = S[S_RHO_NEW] / t[0]; });
+  } else if constexpr (MODE == 3) {
+    reduce_and_finalize<2>(dots, S, partial, [&](double (&t)[2]) { S[S_OMEGA] = t[0] / t[1]; });
+  }
+}
+
+__device__ __forceinline__ double precond(const double* __restrict__ diag, int64_t i, double v) {
+  return diag ? v * (1.0 / diag[i]) : v;      // pc = x * (1. / jacobi), solver.py:69
+}
+
+// ---------------------------------------------------------------- CG ------------------------------
+// after q = A x0:  r = b - q ; z = M r ; p = z ; gamma = r.z ; rr = r.r ; bb = b.b
+__global__ void __launch_bounds__(kThreads) cg_init_kernel(int64_t n, const double* __restrict__ b,
+                                                           const double* __restrict__ diag, const double* __restrict__ q,
+                                                           double* __restrict__ r, double* __restrict__ p,
+                                                           double* __restrict__ S, double* __restrict__ partial) {
+  double v[3] = {0.0, 0.0, 0.0};
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    const double bi = b[i], ri = bi - q[i];
+    const double zi = precond(diag, i, ri);
+    r[i] = ri;
+    p[i] = zi;
+    v[0] = fma(ri, zi, v[0]);
+    v[1] = fma(ri, ri, v[1]);
+    v[2] = fma(bi, bi, v[2]);
+  }
+  reduce_and_finalize<3>(v, S, partial, [&](double (&t)[3]) {
+    S[S_GAMMA] = t[0];
+    S[S_RR] = t[1];
+    const double atol2 = fmax(S[S_TOL2] * t[2], S[S_ATOLIN2]);
+    S[S_ATOL2] = atol2;
+    S[S_K] = 0.0;
+    S[S_DONE] = (t[1] > atol2 && 0.0 < S[S_MAXIT]) ? 0.0 : 1.0;
+  });
+}
+
+// x += alpha p ; r -= alpha q ; gamma' = r.(M r) ; rr = r.r ; beta = gamma'/gamma
+__global__ void __launch_bounds__(kThreads) cg_update_kernel(int64_t n, const double* __restrict__ diag,
+                                                             const double* __restrict__ p, const double* __restrict__ q,
+                                                             double* __restrict__ x, double* __restrict__ r,
+                                                             double* __restrict__ S, double* __restrict__ partial) {
+  if (solver_done(S)) return;
+  const double alpha = __ldcg(S + S_ALPHA);
+  double v[2] = {0.0, 0.0};
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    x[i] = fma(alpha, p[i], x[i]);
+    const double ri = fma(-alpha, q[i], r[i]);
+    r[i] = ri;
+    v[0] = fma(ri, precond(diag, i, ri), v[0]);
+    v[1] = fma(ri, ri, v[1]);
+  }
+  reduce_and_finalize<2>(v, S, partial, [&](double (&t)[2]) {
+    S[S_BETA] = t[0] / S[S_GAMMA];
+    S[S_GAMMA] = t[0];
+    S[S_RR] = t[1];
+    const double k = S[S_K] + 1.0;
+    S[S_K] = k;
+    S[S_DONE] = (t[1] > S[S_ATOL2] && k < S[S_MAXIT]) ? 0.0 : 1.0;
+  });
+}
+
+// p = M r + beta p   (skipped once converged: p is dead after the last update of x)
+__global__ void __launch_bounds__(kThreads) cg_direction_kernel(int64_t n, const double* __restrict__ diag,
+                                                                const double* __restrict__ r, double* __restrict__ p,
+                                                                double* __restrict__ S) {
+  if (solver_done(S)) return;
+  const double beta = __ldcg(S + S_BETA);
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+    p[i] = fma(beta, p[i], precond(diag, i, r[i]));
+}
+
+// ------------------------------------------------------------ BiCGSTAB ----------------------------
+// after q0 = A x0:  r = b - q0 ; rhat = p = q = r ; rho = alpha = omega = 1
+__global__ void __launch_bounds__(kThreads) bicg_init_kernel(int64_t n, const double* __restrict__ b,
+                                                             const double* __restrict__ ax, double* __restrict__ r,
+                                                             double* __restrict__ rhat, double* __restrict__ p,
+                                                             double* __restrict__ q, double* __restrict__ S,
+                                                             double* __restrict__ partial) {
+  double v[2] = {0.0, 0.0};
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    const double bi = b[i], ri = bi - ax[i];
+    r[i] = ri;
+    rhat[i] = ri;
+    p[i] = ri;
+    q[i] = ri;
+    v[0] = fma(ri, ri, v[0]);
+    v[1] = fma(bi, bi, v[1]);
+  }
+  reduce_and_finalize<2>(v, S, partial, [&](double (&t)[2]) {
+    S[S_GAMMA] = 1.0;   // rho
+    S[S_ALPHA] = 1.0;
+    S[S_OMEGA] = 1.0;
+    S[S_RR] = t[0];
+    S[S_RHO_NEW] = t[0];                       // rhat.r with rhat = r
+    S[S_BETA] = t[0] / 1.0 * 1.0 / 1.0;        // rho_/rho * alpha/omega
+    const double atol2 = fmax(S[S_TOL2] * t[1], S[S_ATOLIN2]);
+    S[S_ATOL2] = atol2;
+    S[S_K] = 0.0;
+    S[S_DONE] = (t[0] > atol2 && 0.0 < S[S_MAXIT]) ? 0.0 : 1.0;
+  });
+}
+
+// p = r + beta (p - omega q) ; phat = M p
+__global__ void __launch_bounds__(kThreads) bicg_p_kernel(int64_t n, const double* __restrict__ diag,
+                                                          const double* __restrict__ r, const double* __restrict__ q,
+                                                          double* __restrict__ p, double* __restrict__ phat,
+                                                          const double* __restrict__ S) {
+  if (solver_done(S)) return;
+  const double beta = __ldcg(S + S_BETA), omega = __ldcg(S + S_OMEGA);
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    const double pi = r[i] + beta * (p[i] - omega * q[i]);
+    p[i] = pi;
+    phat[i] = precond(diag, i, pi);
+  }
+}
+
+// s = r - alpha q ; shat = M s ; ss = s.s -> exit_early
+__global__ void __launch_bounds__(kThreads) bicg_s_kernel(int64_t n, const double* __restrict__ diag,
+                                                          const double* __restrict__ r, const double* __restrict__ q,
+                                                          double* __restrict__ s, double* __restrict__ shat,
+                                                          double* __restrict__ S, double* __restrict__ partial) {
+  if (solver_done(S)) return;
+  const double alpha = __ldcg(S + S_ALPHA);
+  double v[1] = {0.0};
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    const double si = r[i] - alpha * q[i];
+    s[i] = si;
+    shat[i] = precond(diag, i, si);
+    v[0] = fma(si, si, v[0]);
+  }
+  reduce_and_finalize<1>(v, S, partial, [&](double (&t)[1]) { S[S_EARLY] = (t[0] < S[S_ATOL2]) ? 1.0 : 0.0; });
+}
+
+// x += alpha phat (+ omega shat) ; r = s (- omega t) ; rr, rhat.r ; bookkeeping of the JAX body
+__global__ void __launch_bounds__(kThreads) bicg_x_kernel(int64_t n, const double* __restrict__ phat,
+                                                          const double* __restrict__ shat, const double* __restrict__ s,
+                                                          const double* __restrict__ t, const double* __restrict__ rhat,
+                                                          double* __restrict__ x, double* __restrict__ r,
+                                                          double* __restrict__ S, double* __restrict__ partial) {
+  if (solver_done(S)) return;
+  const double alpha = __ldcg(S + S_ALPHA), omega = __ldcg(S + S_OMEGA);
+  const bool early = __ldcg(S + S_EARLY) != 0.0;
+  double v[2] = {0.0, 0.0};
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    double xi, ri;
+    if (early) {
+      xi = x[i] + alpha * phat[i];
+      ri = s[i];
+    } else {
+      xi = x[i] + (alpha * phat[i] + omega * shat[i]);
+      ri = s[i] - omega * t[i];
+    }
+    x[i] = xi;
+    r[i] = ri;
+    v[0] = fma(ri, ri, v[0]);
+    v[1] = fma(rhat[i], ri, v[1]);
+  }
+  reduce_and_finalize<2>(v, S, partial, [&](double (&tt)[2]) {
+    const double rho_ = S[S_RHO_NEW], al = S[S_ALPHA], om = S[S_OMEGA];
+    double k = (om == 0.0 || al == 0.0) ? -11.0 : S[S_K] + 1.0;
+    if (rho_ == 0.0) k = -10.0;
+    S[S_K] = k;
+    S[S_GAMMA] = rho_;
+    S[S_RR] = tt[0];
+    S[S_RHO_NEW] = tt[1];
+    S[S_BETA] = tt[1] / rho_ * al / om;
+    S[S_DONE] = (tt[0] > S[S_ATOL2] && k < S[S_MAXIT] && k >= 0.0) ? 0.0 : 1.0;
+  });
+}
+
+// ||A x - b|| for the reference's post-solve check (solver.py:87)
+__global__ void __launch_bounds__(kThreads) resnorm_kernel(int64_t n, const double* __restrict__ ax,
+                                                           const double* __restrict__ b, double* __restrict__ S,
+                                                           double* __restrict__ partial) {
+  double v[1] = {0.0};
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    const double d = ax[i] - b[i];
+    v[0] = fma(d, d, v[0]);
+  }
+  reduce_and_finalize<1>(v, S, partial, [&](double (&t)[1]) { S[S_TMP] = sqrt(t[0]); });
+}
+
+constexpr int kLPR = 8;
+
+// Persistent grid = resident CTAs per SM (from the occupancy API) x SM count: exactly one wave.
+template <class K>
+int persistent_grid(K kernel) {
+  static int cached = 0;
+  if (!cached) {
+    int per_sm = 0, dev = 0, sms = kNumSM;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    cached = per_sm * sms;
+    if (cached > kBlocks) cached = kBlocks;
+  }
+  return cached;
+}
+#define FEM_PGRID(kernel) persistent_grid(kernel), kThreads, 0, st
+
+template <int MODE>
+void spmv_fused(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data, const double* x,
+                double* y, const double* d1, const Ws& w, cudaStream_t st) {
+  spmv_fused_kernel<kLPR, MODE><<<FEM_PGRID((spmv_fused_kernel<kLPR, MODE>))>>>(n, indptr, indices, data, x, y, d1, w.s, w.partial);
+}
+
+int init_scalars(const Ws& w, double tol, double atol, int maxiter, cudaStream_t st) {
+  double h[kScalars] = {0};
+  h[S_TOL2] = tol * tol;
+  h[S_ATOLIN2] = atol * atol;
+  h[S_MAXIT] = (double)maxiter;
+  FEM_CUDA_CHECK(cudaMemcpyAsync(w.s, h, sizeof(h), cudaMemcpyHostToDevice, st));
+  FEM_CUDA_CHECK(cudaStreamSynchronize(st));   // h is a stack buffer
+  return FEM_OK;
+}
+
+int finish(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data, const double* b,
+           const double* x, const Ws& w, double* scratch, double* info_host, cudaStream_t st) {
+  double h[kScalars];
+  FEM_CUDA_CHECK(cudaMemcpyAsync(h, w.s, sizeof(h), cudaMemcpyDeviceToHost, st));
+  FEM_CUDA_CHECK(cudaStreamSynchronize(st));
+  info_host[0] = h[S_K];
+  info_host[1] = h[S_RR];
+  spmv_fused<0>(n, indptr, indices, data, x, scratch, nullptr, w, st);
+  resnorm_kernel<<<FEM_PGRID(resnorm_kernel)>>>(n, scratch, b, w.s, w.partial);
+  FEM_LAUNCH_CHECK();
+  FEM_CUDA_CHECK(cudaMemcpyAsync(h, w.s, sizeof(h), cudaMemcpyDeviceToHost, st));
+  FEM_CUDA_CHECK(cudaStreamSynchronize(st));
+  info_host[2] = h[S_TMP];
+  return FEM_OK;
+}
+
+int poll_done(const Ws& w, bool* done, cudaStream_t st) {
+  double flag = 0.0;
+  FEM_CUDA_CHECK(cudaMemcpyAsync(&flag, w.s + S_DONE, sizeof(double), cudaMemcpyDeviceToHost, st));
+  FEM_CUDA_CHECK(cudaStreamSynchronize(st));
+  *done = flag != 0.0;
+  return FEM_OK;
+}
+
+}  // namespace
+}  // namespace femb200
+
+using namespace femb200;
+
+extern "C" int64_t fem_krylov_workspace(int64_t n) {
+  return kScalars + (int64_t)kBlocks * kMaxDots + 8 * pad_n(n);
+}
+
+extern "C" int fem_pcg(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
+                       const double* diag, const double* b, double* x, double tol, double atol, int maxiter,
+                       int check_every, double* workspace, double* info_host, void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(indptr && indices && data && b && x && workspace && info_host, "null pointer");
+  FEM_REQUIRE(n > 0 && maxiter >= 0, "bad size");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (check_every <= 0) check_every = 25;
+  const Ws w = carve(workspace, n);
+  double *r = w.v[0], *p = w.v[1], *q = w.v[2];
+  if (int e = init_scalars(w, tol, atol, maxiter, st)) return e;
+  spmv_fused<0>(n, indptr, indices, data, x, q, nullptr, w, st);
+  cg_init_kernel<<<FEM_PGRID(cg_init_kernel)>>>(n, b, diag, q, r, p, w.s, w.partial);
+  FEM_LAUNCH_CHECK();
+  bool done = false;
+  if (int e = poll_done(w, &done, st)) return e;
+  for (int it = 0; !done && it < maxiter; it += check_every) {
+    for (int j = 0; j < check_every; ++j) {
+      spmv_fused<1>(n, indptr, indices, data, p, q, p, w, st);                 // q = A p ; alpha
+      cg_update_kernel<<<FEM_PGRID(cg_update_kernel)>>>(n, diag, p, q, x, r, w.s, w.partial);
+      cg_direction_kernel<<<FEM_PGRID(cg_direction_kernel)>>>(n, diag, r, p, w.s);
+    }
+    FEM_LAUNCH_CHECK();
+    if (int e = poll_done(w, &done, st)) return e;
+  }
+  return finish(n, indptr, indices, data, b, x, w, q, info_host, st);
+}
+
+extern "C" int fem_pbicgstab(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
+                             const double* diag, const double* b, double* x, double tol, double atol, int maxiter,
+                             int check_every, double* workspace, double* info_host, void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(indptr && indices && data && b && x && workspace && info_host, "null pointer");
+  FEM_REQUIRE(n > 0 && maxiter >= 0, "bad size");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (check_every <= 0) check_every = 25;
+  const Ws w = carve(workspace, n);
+  double *r = w.v[0], *rhat = w.v[1], *p = w.v[2], *q = w.v[3], *s = w.v[4], *t = w.v[5], *phat = w.v[6],
+         *shat = w.v[7];
+  if (int e = init_scalars(w, tol, atol, maxiter, st)) return e;
+  spmv_fused<0>(n, indptr, indices, data, x, t, nullptr, w, st);
+  bicg_init_kernel<<<FEM_PGRID(bicg_init_kernel)>>>(n, b, t, r, rhat, p, q, w.s, w.partial);
+  FEM_LAUNCH_CHECK();
+  bool done = false;
+  if (int e = poll_done(w, &done, st)) return e;
+  for (int it = 0; !done && it < maxiter; it += check_every) {
+    for (int j = 0; j < check_every; ++j) {
+      bicg_p_kernel<<<FEM_PGRID(bicg_p_kernel)>>>(n, diag, r, q, p, phat, w.s);
+      spmv_fused<2>(n, indptr, indices, data, phat, q, rhat, w, st);           // q = A phat ; alpha
+      bicg_s_kernel<<<FEM_PGRID(bicg_s_kernel)>>>(n, diag, r, q, s, shat, w.s, w.partial);
+      spmv_fused<3>(n, indptr, indices, data, shat, t, s, w, st);              // t = A shat ; omega
+      bicg_x_kernel<<<FEM_PGRID(bicg_x_kernel)>>>(n, phat, shat, s, t, rhat, x, r, w.s, w.partial);
+    }
+    FEM_LAUNCH_CHECK();
+    if (int e = poll_done(w, &done, st)) return e;
+  }
+  return finish(n, indptr, indices, data, b, x, w, t, info_host, st);
+}

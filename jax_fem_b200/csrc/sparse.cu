@@ -1,0 +1,343 @@
+// Global assembly (deterministic gather), Dirichlet operations, CSR SpMV and small vector kernels.
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace femb200 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_device() {
+  static int cached = -1;
+  if (cached < 0) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+      set_error("no CUDA device (%s): libfem_b200 has no CPU fallback", cudaGetErrorString(e));
+      cudaGetLastError();
+      return FEM_ENODEV;
+    }
+    cached = n;
+  }
+  return FEM_OK;
+}
+
+namespace {
+
+// ---- get_A: one thread per node-block entry; fixed source order => bit-reproducible -----------
+template <int VEC, int NN>
+__global__ void gather_csr_kernel(int64_t n_nodes, const int32_t* __restrict__ brow_ptr,
+                                  const int32_t* __restrict__ bcol, const int32_t* __restrict__ src_ptr,
+                                  const int32_t* __restrict__ src, const double* __restrict__ Ke,
+                                  const uint8_t* __restrict__ bc_flag, double* __restrict__ data) {
+  constexpr int ND = NN * VEC;
+  // one warp per node row-block; lanes stride over its entries
+  const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= n_nodes) return;
+  const int lane = threadIdx.x & 31;
+  const int e0 = brow_ptr[n], e1 = brow_ptr[n + 1];
+  const int len = e1 - e0;
+  const int64_t row0 = (int64_t)VEC * VEC * e0;      // indptr[vec*n]
+  bool bc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) bc[i] = bc_flag ? bc_flag[n * VEC + i] != 0 : false;
+  for (int s = lane; s < len; s += 32) {
+    const int e = e0 + s;
+    double acc[VEC][VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[i][k] = 0.0;
+    const int p0 = src_ptr[e], p1 = src_ptr[e + 1];
+    for (int p = p0; p < p1; ++p) {
+      const int code = src[p];
+      const int b = code % NN, a = (code / NN) % NN;
+      const int64_t c = code / (NN * NN);
+      const double* blk = Ke + c * (int64_t)(ND * ND) + (int64_t)(a * VEC) * ND + b * VEC;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[i][k] += blk[i * ND + k];
+    }
+    const bool diag_block = bcol[e] == n;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      double* out = data + row0 + (int64_t)i * VEC * len + (int64_t)VEC * s;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k)
+        out[k] = bc[i] ? ((diag_block && i == k) ? 1.0 : 0.0) : acc[i][k];       // zeroRows, solver.py:527-528
+    }
+  }
+}
+
+template <int VEC, int NN>
+__global__ void gather_residual_kernel(int64_t n_nodes, const int32_t* __restrict__ nc_ptr,
+                                       const int32_t* __restrict__ nc, const double* __restrict__ Re,
+                                       const double* __restrict__ f_ext, double* __restrict__ res) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_nodes) return;
+  double acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.0;
+  for (int p = nc_ptr[n]; p < nc_ptr[n + 1]; ++p) {
+    const double* r = Re + (int64_t)nc[p] * VEC;      // code = c*NN + a  ->  Re[(c*NN + a)*VEC]
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] += r[i];
+  }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) res[n * VEC + i] = acc[i] + (f_ext ? f_ext[n * VEC + i] : 0.0);
+}
+
+__global__ void apply_bc_vec_kernel(int64_t n_bc, const int32_t* __restrict__ rows, const double* __restrict__ vals,
+                                    double scale, const double* __restrict__ sol, double* __restrict__ res) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_bc) {
+    const int r = rows[i];
+    res[r] = sol[r] - vals[i] * scale;                 // solver.py:299-301
+  }
+}
+
+__global__ void bc_x0_kernel(int64_t n_bc, const int32_t* __restrict__ rows, const double* __restrict__ vals,
+                             const double* __restrict__ dofs, double* __restrict__ x0) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_bc) {
+    const int r = rows[i];
+    x0[r] = vals[i] - dofs[r];                         // solver.py:403-409
+  }
+}
+
+// ---- CSR SpMV: LPR lanes per row, 64-bit values + 32-bit columns streamed at full sector width --
+template <int LPR>
+__global__ void __launch_bounds__(256) spmv_kernel(int64_t n, const int32_t* __restrict__ indptr,
+                                                   const int32_t* __restrict__ indices,
+                                                   const double* __restrict__ data, const double* __restrict__ x,
+                                                   double* __restrict__ y) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int sub = threadIdx.x % LPR;
+  double acc = 0.0;
+  if (row < n) {
+    const int s = indptr[row], e = indptr[row + 1];
+    for (int j = s + sub; j < e; j += LPR) acc = fma(data[j], __ldg(x + indices[j]), acc);
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (row < n && sub == 0) y[row] = acc;
+}
+
+__global__ void csr_diag_kernel(int64_t n, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                const double* __restrict__ data, double* __restrict__ diag) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  int lo = indptr[row], hi = indptr[row + 1] - 1;
+  double d = 0.0;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    const int c = indices[mid];
+    if (c == row) { d = data[mid]; break; }
+    if (c < row) lo = mid + 1; else hi = mid - 1;
+  }
+  diag[row] = d;
+}
+
+template <int VEC>
+__global__ void transpose_values_kernel(int64_t n_nodes, const int32_t* __restrict__ brow_ptr,
+                                        const int32_t* __restrict__ bcol, const int32_t* __restrict__ tperm, const double* __restrict__ data,
+                                        double* __restrict__ data_t) {
+  const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= n_nodes) return;
+  const int e0 = brow_ptr[n], len = brow_ptr[n + 1] - e0;
+  const int64_t row0 = (int64_t)VEC * VEC * e0;
+  for (int s = (threadIdx.x & 31); s < len; s += 32) {
+    // entry (n, m) at slot s; its transpose (m, n) is entry te of row block m
+    const int te = tperm[e0 + s];
+    const int64_t m = bcol[e0 + s];
+    const int f0 = brow_ptr[m], lenm = brow_ptr[m + 1] - f0, sm = te - f0;
+    const int64_t rowm = (int64_t)VEC * VEC * f0;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k)
+        data_t[row0 + (int64_t)i * VEC * len + (int64_t)VEC * s + k] =
+            data[rowm + (int64_t)k * VEC * lenm + (int64_t)VEC * sm + i];
+  }
+}
+
+__global__ void axpy_kernel(int64_t n, double alpha, const double* __restrict__ x, double* __restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = fma(alpha, x[i], y[i]);
+}
+
+__global__ void __launch_bounds__(256) dot_kernel(int64_t n, const double* __restrict__ x, const double* __restrict__ y,
+                                                  double* __restrict__ partial) {
+  __shared__ double red[8];
+  double v[1] = {0.0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    v[0] = fma(x[i], y[i], v[0]);
+  block_sum<1, 256>(v, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = v[0];
+}
+
+__global__ void final_sum_kernel(int nblocks, const double* __restrict__ partial, double* __restrict__ out) {
+  __shared__ double red[8];
+  double v[1] = {0.0};
+  for (int i = threadIdx.x; i < nblocks; i += 256) v[0] += partial[i];
+  block_sum<1, 256>(v, red);
+  if (threadIdx.x == 0) *out = v[0];
+}
+
+inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+}  // namespace
+}  // namespace femb200
+
+using namespace femb200;
+
+extern "C" const char* fem_last_error(void) { return g_err; }
+extern "C" int fem_version(void) { return 100; }
+extern "C" int fem_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    set_error("no CUDA device (%s)", cudaGetErrorString(e));
+    return FEM_ENODEV;
+  }
+  return n;
+}
+
+extern "C" int fem_gather_csr(int vec, int nn, int64_t n_nodes, const int32_t* brow_ptr, const int32_t* bcol,
+                              const int32_t* src_ptr, const int32_t* src, const double* Ke,
+                              const uint8_t* bc_flag, double* data, void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(brow_ptr && bcol && src_ptr && src && Ke && data, "null pointer");
+  if (n_nodes == 0) return FEM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = blocks_for(n_nodes, 8);
+#define FEM_G(V, N)                                                                                            \
+  if (vec == V && nn == N) {                                                                                   \
+    gather_csr_kernel<V, N><<<grid, 256, 0, st>>>(n_nodes, brow_ptr, bcol, src_ptr, src, Ke, bc_flag, data);   \
+    FEM_LAUNCH_CHECK();                                                                                        \
+    return FEM_OK;                                                                                             \
+  }
+  FEM_G(3, 8) FEM_G(1, 8) FEM_G(1, 4) FEM_G(2, 4) FEM_G(3, 27) FEM_G(1, 27)
+#undef FEM_G
+  set_error("fem_gather_csr: unregistered (vec=%d, nodes/cell=%d)", vec, nn);
+  return FEM_EINVAL;
+}
+
+extern "C" int fem_gather_residual(int vec, int nn, int64_t n_nodes, const int32_t* nc_ptr, const int32_t* nc,
+                                   const double* Re, const double* f_ext, double* res, void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(nc_ptr && nc && Re && res, "null pointer");
+  if (n_nodes == 0) return FEM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = blocks_for(n_nodes, 256);
+#define FEM_G(V, N)                                                                                  \
+  if (vec == V && nn == N) {                                                                         \
+    gather_residual_kernel<V, N><<<grid, 256, 0, st>>>(n_nodes, nc_ptr, nc, Re, f_ext, res);         \
+    FEM_LAUNCH_CHECK();                                                                              \
+    return FEM_OK;                                                                                   \
+  }
+  FEM_G(3, 8) FEM_G(1, 8) FEM_G(1, 4) FEM_G(2, 4) FEM_G(3, 27) FEM_G(1, 27)
+#undef FEM_G
+  set_error("fem_gather_residual: unregistered (vec=%d, nodes/cell=%d)", vec, nn);
+  return FEM_EINVAL;
+}
+
+extern "C" int fem_apply_bc_vec(int64_t n_bc, const int32_t* bc_rows, const double* bc_vals, double scale,
+                                const double* sol, double* res, void* stream) {
+  if (int e = check_device()) return e;
+  if (n_bc == 0) return FEM_OK;
+  FEM_REQUIRE(bc_rows && bc_vals && sol && res, "null pointer");
+  apply_bc_vec_kernel<<<blocks_for(n_bc, 256), 256, 0, (cudaStream_t)stream>>>(n_bc, bc_rows, bc_vals, scale, sol, res);
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
+}
+
+extern "C" int fem_bc_initial_guess(int64_t n, int64_t n_bc, const int32_t* bc_rows, const double* bc_vals,
+                                    const double* dofs, double* x0, void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(dofs && x0, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  FEM_CUDA_CHECK(cudaMemsetAsync(x0, 0, sizeof(double) * n, st));
+  if (n_bc == 0) return FEM_OK;
+  bc_x0_kernel<<<blocks_for(n_bc, 256), 256, 0, st>>>(n_bc, bc_rows, bc_vals, dofs, x0);
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
+}
+
+namespace femb200 {
+int launch_spmv(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data, const double* x,
+                double* y, cudaStream_t st) {
+  constexpr int LPR = 8;
+  spmv_kernel<LPR><<<blocks_for(n * LPR, 256), 256, 0, st>>>(n, indptr, indices, data, x, y);
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
+}
+}  // namespace femb200
+
+extern "C" int fem_spmv(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
+                        const double* x, double* y, void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(indptr && indices && data && x && y, "null pointer");
+  if (n == 0) return FEM_OK;
+  return launch_spmv(n, indptr, indices, data, x, y, (cudaStream_t)stream);
+}
+
+extern "C" int fem_csr_diagonal(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
+                                double* diag, void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(indptr && indices && data && diag, "null pointer");
+  if (n == 0) return FEM_OK;
+  csr_diag_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, indptr, indices, data, diag);
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
+}
+
+extern "C" int fem_csr_transpose_values(int vec, int64_t n_nodes, const int32_t* brow_ptr, const int32_t* bcol,
+                                        const int32_t* tperm,
+                                        const double* data, double* data_t, void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(brow_ptr && bcol && tperm && data && data_t, "null pointer");
+  if (n_nodes == 0) return FEM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = blocks_for(n_nodes, 8);
+  if (vec == 1) transpose_values_kernel<1><<<grid, 256, 0, st>>>(n_nodes, brow_ptr, bcol, tperm, data, data_t);
+  else if (vec == 2) transpose_values_kernel<2><<<grid, 256, 0, st>>>(n_nodes, brow_ptr, bcol, tperm, data, data_t);
+  else if (vec == 3) transpose_values_kernel<3><<<grid, 256, 0, st>>>(n_nodes, brow_ptr, bcol, tperm, data, data_t);
+  else {
+    set_error("fem_csr_transpose_values: unregistered vec=%d", vec);
+    return FEM_EINVAL;
+  }
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
+}
+
+extern "C" int fem_dot(int64_t n, const double* x, const double* y, double* result_host, double* workspace,
+                       void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(x && y && result_host && workspace, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = (int)((n + 255) / 256 < 1184 ? ((n + 255) / 256 > 0 ? (n + 255) / 256 : 1) : 1184);
+  dot_kernel<<<nb, 256, 0, st>>>(n, x, y, workspace + 1);
+  final_sum_kernel<<<1, 256, 0, st>>>(nb, workspace + 1, workspace);
+  FEM_LAUNCH_CHECK();
+  FEM_CUDA_CHECK(cudaMemcpyAsync(result_host, workspace, sizeof(double), cudaMemcpyDeviceToHost, st));
+  FEM_CUDA_CHECK(cudaStreamSynchronize(st));
+  return FEM_OK;
+}
+
+extern "C" int fem_axpy(int64_t n, double alpha, const double* x, double* y, void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(x && y, "null pointer");
+  if (n == 0) return FEM_OK;
+  axpy_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, alpha, x, y);
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
+}

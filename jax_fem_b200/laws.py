@@ -1,0 +1,103 @@
+"""Registry of constitutive laws that have a hand-written sm_100a element kernel.
+
+In the reference ``Problem.get_tensor_map()`` returns an arbitrary Python function that JAX traces
+and differentiates (jax_fem/problem.py:189-214, 262-266).  A CUDA kernel cannot be generated from
+an arbitrary callable, so on this path ``get_tensor_map()`` must return one of the objects below;
+anything else raises ``UnregisteredLawError`` -- it never falls back to another implementation.
+
+Each law cites the reference ``get_tensor_map`` body it reproduces (formulas in SURVEY.md 8a).
+"""
+from . import _lib
+
+
+class UnregisteredLawError(NotImplementedError):
+    pass
+
+
+class Law:
+    law_id = -1
+    n_internal_vars = 0       # per-quadrature-point parameter arrays the kernel accepts
+    requires_internal_var = False
+
+    def params(self):
+        raise NotImplementedError
+
+    def __call__(self, *a, **k):
+        raise UnregisteredLawError("registered laws are evaluated by CUDA kernels, not called from Python")
+
+
+class Poisson(Law):
+    """f(grad u) = k grad u.  tests/benchmarks/linear_poisson/test_linear_poisson.py:15-17 (k = 1),
+    applications/thermal_mechanical/example.py:35-38 (heat conduction).  An optional per-quad
+    internal variable scales k."""
+    law_id = 0
+    n_internal_vars = 1
+
+    def __init__(self, k=1.0):
+        self.k = float(k)
+
+    def params(self):
+        return [self.k]
+
+
+Heat = Poisson
+
+
+class LinearElasticity(Law):
+    """sigma = lambda tr(eps) I + 2 mu eps.
+    tests/benchmarks/linear_elasticity_cube/test_linear_elasticity_cube.py:17-25."""
+    law_id = 1
+
+    def __init__(self, E, nu):
+        self.E, self.nu = float(E), float(nu)
+
+    def params(self):
+        return [self.E, self.nu]
+
+
+class NeoHookean(Law):
+    """psi = mu/2 (J^-2/3 I1 - 3) + kappa/2 (J-1)^2, P = d psi/dF.
+    tests/benchmarks/hyperelasticity/test_hyper_elasticity.py:16-34;
+    applications/scalability/hyperelastic3d_common.py:18-35; with ``clamp_J`` and a per-quad
+    modulus scale rho: hyperelastic3d_common.py:52-70."""
+    law_id = 2
+    n_internal_vars = 1
+
+    def __init__(self, E, nu, clamp_J=False):
+        self.E, self.nu, self.clamp_J = float(E), float(nu), bool(clamp_J)
+
+    def params(self):
+        return [self.E, self.nu, 1.0 if self.clamp_J else 0.0]
+
+
+class SIMP(Law):
+    """E(theta) = Emin + (Emax - Emin) theta^penal, then isotropic linear elasticity.
+    docs/source/learn/topology_optimization/example.ipynb cell 9;
+    applications/outdated/top_opt/fem_model.py:68-80 (3-D)."""
+    law_id = 3
+    n_internal_vars = 1
+    requires_internal_var = True
+
+    def __init__(self, Emax, Emin, nu, penal=3.0):
+        self.Emax, self.Emin, self.nu, self.penal = float(Emax), float(Emin), float(nu), float(penal)
+
+    def params(self):
+        return [self.Emax, self.Emin, self.nu, self.penal]
+
+
+REGISTERED = {
+    ('HEX8', 1, Poisson), ('HEX8', 3, LinearElasticity), ('HEX8', 3, NeoHookean), ('HEX8', 3, SIMP),
+    ('QUAD4', 1, Poisson), ('QUAD4', 2, LinearElasticity), ('QUAD4', 2, SIMP),
+}
+
+
+def resolve(tensor_map, ele_type, vec):
+    if not isinstance(tensor_map, Law):
+        raise UnregisteredLawError(
+            f"get_tensor_map() returned {type(tensor_map).__name__}; the B200 hot path only runs registered "
+            f"laws (jax_fem_b200.laws.Poisson/Heat, LinearElasticity, NeoHookean, SIMP). "
+            f"Unregistered tensor maps raise; they do not fall back.")
+    if (ele_type, vec, type(tensor_map)) not in REGISTERED:
+        raise UnregisteredLawError(
+            f"no sm_100a kernel is registered for (ele_type={ele_type}, vec={vec}, law={type(tensor_map).__name__})")
+    return tensor_map

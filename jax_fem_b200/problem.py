@@ -1,0 +1,263 @@
+"""Weak-form container with the reference's Problem API, executing on the B200.
+
+Mirror of jax_fem/problem.py::Problem (ctor fields :46-54, custom_init :184, compute_residual :462,
+newton_update :477, set_params :493, internal_vars :125).  What differs is where the work happens:
+
+  reference                                             here
+  ---------                                             ----
+  get_tensor_map() -> Python fn, traced + jacfwd'ed     -> a registered law (jax_fem_b200.laws.*), run by the
+  (problem.py:189-214, 262-266)                            hand-written element kernels of csrc/element.cu
+  shape_grads/JxW/v_grads_JxW (C,Q,N,dim) in memory     recomputed per cell inside the kernel
+  I, J (C*ndof^2 ints, :95-107)                         AssemblyPlan (node-block graph + slot maps); I/J/V
+                                                        are materialised only if the caller reads them
+  20 batches + host vstack of Jacobians (:359-396)      one launch, element matrices stay in HBM
+  .at[].add scatter of the residual (:426-437)          deterministic per-node gather
+
+Only one FE variable is supported (every configuration on the hot path is single-variable);
+multi-variable problems, universal kernels and u-dependent mass/surface maps are not registered and
+raise NotImplementedError instead of falling back.
+"""
+from dataclasses import dataclass
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import _lib, laws, logger
+from .fe import FiniteElement, evaluate_point_fn
+from .generate_mesh import Mesh
+from .plan import build_plan
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("jax_fem_b200 needs a CUDA device: the hot path is sm_100a CUDA with no CPU fallback")
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def _eval_load_map(fn, u, x, vec):
+    """Evaluate a reference-style mass/surface map ``fn(u, x)`` at many points -> (P, vec).
+
+    Registered loads are u-independent (true for every configuration on the hot path: body forces and
+    tractions).  The map is evaluated at u = 0; a second evaluation at a perturbed u must agree,
+    otherwise the map contributes to the tangent and is not registered."""
+    def at(uvals):
+        return evaluate_point_fn(lambda z: fn(z[:vec], z[vec:]), np.concatenate([uvals, x], axis=1), (vec,))
+    f0 = at(np.zeros((len(x), vec)))
+    f1 = at(np.full((len(x), vec), 0.37))
+    if not np.array_equal(f0, f1):
+        raise NotImplementedError("solution-dependent mass/surface maps are not registered on the B200 hot path "
+                                  "(their tangent would need a kernel of its own); they do not fall back")
+    return f0
+
+
+@dataclass
+class Problem:
+    mesh: Mesh
+    vec: int
+    dim: int
+    ele_type: str = 'HEX8'
+    quadrature_rule: Any = None
+    quadrature_order: int = None
+    dirichlet_bc_info: list = None
+    location_fns: list = None
+    additional_info: tuple = ()
+
+    def __post_init__(self):
+        if isinstance(self.mesh, list):
+            if len(self.mesh) != 1:
+                raise NotImplementedError("multi-variable problems are outside the B200 hot path (SURVEY.md 8)")
+            self.mesh, self.vec, self.ele_type = self.mesh[0], self.vec[0], self.ele_type[0]
+            for name in ('quadrature_rule', 'quadrature_order', 'dirichlet_bc_info'):
+                v = getattr(self, name)
+                if isinstance(v, list) and name != 'dirichlet_bc_info':
+                    setattr(self, name, v[0])
+        for hook in ('get_universal_kernel', 'get_universal_kernels_surface'):
+            if hasattr(self, hook):
+                raise NotImplementedError(f"{hook} is not registered on the B200 hot path; it does not fall back")
+        self.device = _device()
+        self.num_vars = 1
+        fe = FiniteElement(mesh=self.mesh, vec=self.vec, dim=self.dim, ele_type=self.ele_type,
+                           quadrature_rule=self.quadrature_rule, quadrature_order=self.quadrature_order,
+                           dirichlet_bc_info=self.dirichlet_bc_info)
+        self.fes = [fe]
+        self.cells_list = [fe.cells]
+        self.num_cells = fe.num_cells
+        self.boundary_inds_list = fe.get_boundary_conditions_inds(self.location_fns)
+        self.offset = [0]
+        self.num_total_dofs_all_vars = fe.num_total_dofs
+        self.cells_list_face_list = [[fe.cells[b[:, 0]]] for b in self.boundary_inds_list]
+
+        dev = self.device
+        self._points = torch.from_numpy(fe.points).to(dev)
+        self._cells = torch.from_numpy(fe.cells).to(dev)
+        self._ref = torch.from_numpy(np.concatenate([fe.shape_grads_ref.reshape(-1), fe.quad_weights])).to(dev)
+        self.plan = build_plan(self._cells, fe.num_total_nodes, fe.vec)
+        self._Ke = None
+        self._Re = torch.empty((self.num_cells, fe.num_nodes * fe.vec), dtype=torch.float64, device=dev)
+        self._bc_cache = None
+        self._law = None
+
+        self.internal_vars = ()
+        self.internal_vars_surfaces = [() for _ in range(len(self.boundary_inds_list))]
+        self.custom_init(*self.additional_info)
+        self.pre_jit_fns()
+
+    # ---- hooks kept from the reference ------------------------------------------------------------
+    def custom_init(self):
+        """Child class should override if more things need to be done in initialization."""
+        pass
+
+    def set_params(self, params):
+        raise NotImplementedError("Child class must implement this function!")
+
+    def pre_jit_fns(self):
+        """The reference jits/vmaps its Python kernels here (problem.py:261-356); this version resolves the
+        registered law and precomputes the (solution-independent) load vector."""
+        if hasattr(self, 'get_tensor_map'):
+            self._law = laws.resolve(self.get_tensor_map(), self.ele_type, self.vec)
+        else:
+            raise NotImplementedError("a Problem without get_tensor_map has no registered kernel")
+        num_surfaces = len(self.boundary_inds_list)
+        if hasattr(self, 'get_surface_maps'):
+            assert num_surfaces == len(self.get_surface_maps())
+        else:
+            assert num_surfaces == 0, "Missing definitions for surface integral"
+        self._f_ext = self._assemble_loads()
+
+    def _assemble_loads(self):
+        """mass_kernel + surface_kernel of the reference (problem.py:216-259) for u-independent maps: a constant
+        nodal vector, assembled once on the host (face sets are small; cell loads use bincount)."""
+        fe = self.fes[0]
+        f = np.zeros((fe.num_total_nodes, fe.vec))
+        used = False
+        if hasattr(self, 'get_mass_map'):
+            x = fe.get_physical_quad_points()                                      # (C,Q,dim)
+            _, JxW = fe.get_shape_grads()
+            val = _eval_load_map(self.get_mass_map(), None, x.reshape(-1, self.dim), fe.vec).reshape(*x.shape[:2], fe.vec)
+            contrib = np.einsum('cqv,qn,cq->cnv', val, fe.shape_vals, JxW)
+            for i in range(fe.vec):
+                f[:, i] += np.bincount(fe.cells.reshape(-1), weights=contrib[:, :, i].reshape(-1), minlength=fe.num_total_nodes)
+            used = True
+        if hasattr(self, 'get_surface_maps'):
+            for k, b in enumerate(self.boundary_inds_list):
+                if len(b) == 0:
+                    continue
+                x = fe.get_physical_surface_quad_points(b)
+                _, nanson = fe.get_face_shape_grads(b)
+                val = _eval_load_map(self.get_surface_maps()[k], None, x.reshape(-1, self.dim), fe.vec)
+                val = val.reshape(*x.shape[:2], fe.vec)
+                contrib = np.einsum('fqv,fqn,fq->fnv', val, fe.face_shape_vals[b[:, 1]], nanson)
+                nodes = fe.cells[b[:, 0]].reshape(-1)
+                for i in range(fe.vec):
+                    f[:, i] += np.bincount(nodes, weights=contrib[:, :, i].reshape(-1), minlength=fe.num_total_nodes)
+                used = True
+        return torch.from_numpy(f).to(self.device) if used else None
+
+    # ---- flat <-> list helpers (jax.flatten_util in the reference) -----------------------------------
+    def unflatten_fn_sol_list(self, dofs):
+        return [dofs.reshape(self.fes[0].num_total_nodes, self.fes[0].vec)]
+
+    # ---- Dirichlet rows, merged with the reference's "later groups overwrite" rule --------------------
+    def bc_data(self):
+        """(rows int32, vals float64, flag uint8 per dof) on the device; rebuilt when fe.*_list objects change
+        (same identity test as _PetscTangentCache._refresh_bc_rows_if_needed, solver.py:494-520)."""
+        fe = self.fes[0]
+        key = tuple(id(a) for lst in (fe.node_inds_list, fe.vec_inds_list, fe.vals_list) for a in lst)
+        if self._bc_cache is None or self._bc_cache[0] != key:
+            n = self.num_total_dofs_all_vars
+            val = np.zeros(n)
+            flag = np.zeros(n, dtype=np.uint8)
+            for i in range(len(fe.node_inds_list)):
+                rows = np.asarray(fe.node_inds_list[i]) * fe.vec + np.asarray(fe.vec_inds_list[i])
+                val[rows] = np.asarray(fe.vals_list[i], dtype=np.float64)          # last group wins
+                flag[rows] = 1
+            rows = np.flatnonzero(flag).astype(np.int32)
+            dev = self.device
+            self._bc_cache = (key, torch.from_numpy(rows).to(dev), torch.from_numpy(val[rows]).to(dev),
+                              torch.from_numpy(flag).to(dev),
+                              (fe.node_inds_list, fe.vec_inds_list, fe.vals_list))   # keep refs alive
+        return self._bc_cache[1], self._bc_cache[2], self._bc_cache[3]
+
+    # ---- the hot path -----------------------------------------------------------------------------------
+    def _internal_var(self):
+        law = self._law
+        iv = list(self.internal_vars)
+        if len(iv) > law.n_internal_vars:
+            raise NotImplementedError(f"{type(law).__name__} takes {law.n_internal_vars} internal variable(s), got {len(iv)}")
+        if not iv:
+            if law.requires_internal_var:
+                raise ValueError(f"{type(law).__name__} needs internal_vars = [theta (num_cells, num_quads)]")
+            return None
+        t = iv[0]
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(np.asarray(t), dtype=torch.float64)
+        t = t.detach().to(device=self.device, dtype=torch.float64).contiguous()
+        assert t.shape == (self.num_cells, self.fes[0].num_quads), \
+            f"internal variable must have shape (num_cells, num_quads) = {(self.num_cells, self.fes[0].num_quads)}"
+        return t
+
+    def _as_sol(self, sol_list):
+        sol = sol_list[0] if isinstance(sol_list, (list, tuple)) else sol_list
+        if not isinstance(sol, torch.Tensor):
+            sol = torch.as_tensor(np.asarray(sol), dtype=torch.float64)
+        return sol.detach().to(device=self.device, dtype=torch.float64).contiguous()
+
+    def _run_element_kernel(self, sol, jac):
+        fe = self.fes[0]
+        ndof = fe.num_nodes * fe.vec
+        if jac and self._Ke is None:
+            self._Ke = torch.empty((self.num_cells, ndof, ndof), dtype=torch.float64, device=self.device)
+        iv = self._internal_var()
+        lib = _lib.load()
+        _lib.check(lib.fem_element_residual_jacobian(
+            _lib.ELE[self.ele_type], fe.vec, self._law.law_id, _lib.host_doubles(self._law.params()),
+            _lib.ptr(self._points), _lib.ptr(self._cells), self.num_cells, _lib.ptr(sol), _lib.ptr(iv),
+            _lib.ptr(self._ref), _lib.ptr(self._Ke) if jac else None, _lib.ptr(self._Re), _lib.stream_ptr()))
+        res = torch.empty((fe.num_total_nodes, fe.vec), dtype=torch.float64, device=self.device)
+        p = self.plan
+        _lib.check(lib.fem_gather_residual(fe.vec, fe.num_nodes, fe.num_total_nodes, _lib.ptr(p.nc_ptr), _lib.ptr(p.nc),
+                                           _lib.ptr(self._Re), _lib.ptr(self._f_ext), _lib.ptr(res), _lib.stream_ptr()))
+        return res
+
+    def compute_residual(self, sol_list):
+        """sol_list: [ (num_total_nodes, vec) ] -> res_list of the same shapes (problem.py:462-475)."""
+        return [self._run_element_kernel(self._as_sol(sol_list), jac=False)]
+
+    def newton_update(self, sol_list):
+        """Residual list; the element tangents stay on the device for get_A (problem.py:477-491)."""
+        return [self._run_element_kernel(self._as_sol(sol_list), jac=True)]
+
+    # ---- reference attributes, materialised on demand ---------------------------------------------------
+    @property
+    def V(self):
+        """COO values aligned with I/J: cell blocks, then (zero) face blocks (problem.py:453-458)."""
+        if self._Ke is None:
+            raise AttributeError("V is defined after newton_update()")
+        ndof = self._Ke.shape[1]
+        nface = sum(len(b) for b in self.boundary_inds_list)
+        return torch.cat([self._Ke.reshape(-1), torch.zeros(nface * ndof * ndof, dtype=torch.float64, device=self.device)])
+
+    def _coo(self):
+        fe = self.fes[0]
+        inds = (fe.vec * fe.cells[:, :, None].astype(np.int64) + np.arange(fe.vec)[None, None, :]).reshape(self.num_cells, -1)
+        blocks = [inds] + [inds[b[:, 0]] for b in self.boundary_inds_list]
+        n = inds.shape[1]
+        I = np.concatenate([np.repeat(x[:, :, None], n, axis=2).reshape(-1) for x in blocks])
+        J = np.concatenate([np.repeat(x[:, None, :], n, axis=1).reshape(-1) for x in blocks])
+        return I, J
+
+    @property
+    def I(self):
+        return self._coo()[0]
+
+    @property
+    def J(self):
+        return self._coo()[1]
+
+    def print_BC_info(self):
+        fe = self.fes[0]
+        for i, b in enumerate(self.boundary_inds_list):
+            print(f"Surface boundary set {i + 1}: (num_selected_faces, 2) = {b.shape}")
+        for i in range(len(fe.node_inds_list)):
+            print(f"Dirichlet part {i + 1}: {len(fe.node_inds_list[i])} dofs on component {fe.vec_inds_list[i][:1]}")

@@ -1,0 +1,335 @@
+"""Nonlinear / linear solvers and the implicit adjoint, with the reference's API.
+
+Mirror of jax_fem/solver.py: solver (:1112-1356), newton_step (:390-421), get_A (:540-553),
+apply_bc_vec / assign_bc / copy_bc (:290-363), linear_solver (:261-284), jax_solve (:63-92),
+implicit_vjp (:1362-1418), ad_wrapper (:1421-1455), option resolution (:1079-1106).
+
+One linear back-end exists: the device-resident Jacobi-preconditioned BiCGSTAB / CG of
+csrc/krylov.cu (``jax_solver``; option ``method`` in {'bicgstab' (reference default), 'cg'}) plus
+the documented ``custom_solver`` hook.  ``petsc_solver`` / ``amgx_solver`` / ``spsolve_solver``,
+arc-length and dynamic relaxation are outside the hot path and raise NotImplementedError.
+"""
+import math
+import time
+
+import numpy as np
+import torch
+
+from . import _lib, logger
+from .sparse import CSRMatrix
+
+################################################################################
+# logging helpers (same buckets as the reference: local_assembly / global_matrix / linear)
+
+
+def _timing_record(timing, name, dt):
+    timing[name] += dt
+
+
+def _log_newton_iter_summary(iter_num, local_s, global_s, res_val, rel_res_val, linear_s=None):
+    logger.info("  iter %d  nonlinear residual: L2 norm = %.3g (relative to initial = %.3g)", iter_num, res_val, rel_res_val)
+    if linear_s is None:
+        logger.info("           timing: local assembly %6.3f s, global matrix %6.3f s", local_s, global_s)
+    else:
+        logger.info("           timing: linear solve %6.3f s, local assembly %6.3f s, global matrix %6.3f s",
+                    linear_s, local_s, global_s)
+
+
+def _log_timing_table(n_iters, parts, wall_s):
+    logger.info("Timing summary -- %d Newton iter, %.3f s wall", n_iters, wall_s)
+    for key, label in (('local_assembly', 'local'), ('global_matrix', 'global'), ('linear', 'linear')):
+        dt = parts[key]
+        logger.info("  %-8s %7.3f s  %5.1f%%", label, dt, 100. * dt / wall_s if wall_s > 0 else 0.)
+
+
+def _sync_time():
+    torch.cuda.synchronize()
+    return time.perf_counter()
+
+
+################################################################################
+# small device helpers
+
+def _norm(v):
+    """L2 norm through the library's deterministic dot."""
+    ws = torch.empty(2048, dtype=torch.float64, device=v.device)
+    out = (_lib.ctypes.c_double * 1)()
+    _lib.check(_lib.load().fem_dot(v.numel(), _lib.ptr(v), _lib.ptr(v), out, _lib.ptr(ws), _lib.stream_ptr()))
+    return math.sqrt(out[0])
+
+
+################################################################################
+# Dirichlet boundary conditions ("row elimination")
+
+def apply_bc_vec(res_vec, dofs, problem, scale=1.):
+    """res[bc rows] = dofs[bc rows] - value*scale  (solver.py:290-304); returns a new vector."""
+    rows, vals, _ = problem.bc_data()
+    res = res_vec.reshape(-1).clone()
+    _lib.check(_lib.load().fem_apply_bc_vec(rows.numel(), _lib.ptr(rows), _lib.ptr(vals), float(scale),
+                                            _lib.ptr(dofs.reshape(-1).contiguous()), _lib.ptr(res), _lib.stream_ptr()))
+    return res
+
+
+def apply_bc(res_fn, problem, scale=1.):
+    def res_fn_bc(dofs):
+        return apply_bc_vec(res_fn(dofs), dofs, problem, scale)
+    return res_fn_bc
+
+
+def assign_bc(dofs, problem):
+    rows, vals, _ = problem.bc_data()
+    out = dofs.reshape(-1).clone()
+    out[rows.long()] = vals
+    return out
+
+
+def assign_ones_bc(dofs, problem):
+    rows, _, _ = problem.bc_data()
+    out = dofs.reshape(-1).clone()
+    out[rows.long()] = 1.
+    return out
+
+
+def assign_zeros_bc(dofs, problem):
+    rows, _, _ = problem.bc_data()
+    out = dofs.reshape(-1).clone()
+    out[rows.long()] = 0.
+    return out
+
+
+def copy_bc(dofs, problem):
+    rows, _, _ = problem.bc_data()
+    out = torch.zeros_like(dofs.reshape(-1))
+    out[rows.long()] = dofs.reshape(-1)[rows.long()]
+    return out
+
+
+def get_flatten_fn(fn_sol_list, problem):
+    def fn_dofs(dofs):
+        return torch.cat([v.reshape(-1) for v in fn_sol_list(problem.unflatten_fn_sol_list(dofs))])
+    return fn_dofs
+
+
+################################################################################
+# Tangent stiffness matrix
+
+def get_A(problem):
+    """Assemble the element tangents of the last newton_update into CSR, Dirichlet rows zeroed with unit
+    diagonal and the full pattern kept (solver.py:469-553).  Returns a device CSRMatrix."""
+    if hasattr(problem, 'P_mat'):
+        raise NotImplementedError("P_mat (multipoint constraints) is outside the B200 hot path")
+    if problem._Ke is None:
+        raise RuntimeError("get_A() needs problem.newton_update(sol_list) first")
+    p = problem.plan
+    fe = problem.fes[0]
+    _, _, flag = problem.bc_data()
+    data = torch.empty(p.nnz, dtype=torch.float64, device=problem.device)
+    _lib.check(_lib.load().fem_gather_csr(fe.vec, fe.num_nodes, fe.num_total_nodes, _lib.ptr(p.brow_ptr),
+                                          _lib.ptr(p.bcol), _lib.ptr(p.src_ptr), _lib.ptr(p.src), _lib.ptr(problem._Ke),
+                                          _lib.ptr(flag), _lib.ptr(data), _lib.stream_ptr()))
+    return CSRMatrix(p, data)
+
+
+################################################################################
+# Linear solvers
+
+_workspaces = {}
+
+
+def _krylov_workspace(n, device):
+    key = (n, device)
+    if key not in _workspaces:
+        size = _lib.load().fem_krylov_workspace(n)
+        _workspaces.clear()
+        _workspaces[key] = torch.zeros(size, dtype=torch.float64, device=device)
+    return _workspaces[key]
+
+
+def jax_solve(A, b, x0, precond, method='bicgstab', tol=1e-10, atol=1e-10, maxiter=10000, check_every=25,
+              return_info=False):
+    """Jacobi-preconditioned Krylov solve on the device; stopping rule and post-check of solver.py:63-92."""
+    n = A.getSize()[0]
+    indptr, indices, data = A.getValuesCSR()
+    b = b.reshape(-1).contiguous()
+    x = torch.zeros_like(b) if x0 is None else x0.reshape(-1).clone().contiguous()
+    diag = A.diagonal() if precond else None
+    ws = _krylov_workspace(n, b.device)
+    info = (_lib.ctypes.c_double * 4)()
+    fn = {'bicgstab': _lib.load().fem_pbicgstab, 'cg': _lib.load().fem_pcg}[method]
+    _lib.check(fn(n, _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(data), _lib.ptr(diag), _lib.ptr(b), _lib.ptr(x),
+                  float(tol), float(atol), int(maxiter), int(check_every), _lib.ptr(ws), info, _lib.stream_ptr()))
+    iters, err = int(info[0]), float(info[2])
+    logger.debug("jax_solver(%s) - %d iterations, linear solve res = %.3g", method, iters, err)
+    assert err < 0.1, f"JAX linear solver failed to converge with err = {err}"
+    if return_info:
+        return x, {'iterations': iters, 'rr': float(info[1]), 'err': err}
+    return x
+
+
+def linear_solver(A, b, x0, linear_options):
+    """Dispatch of solver.py:261-284, restricted to the single device back-end + the custom hook."""
+    known = {'jax_solver', 'amgx_solver', 'spsolve_solver', 'petsc_solver', 'custom_solver'}
+    if len(linear_options.keys() & known) == 0:
+        linear_options['jax_solver'] = {}
+    if 'jax_solver' in linear_options:
+        opts = linear_options['jax_solver']
+        return jax_solve(A, b, x0, opts.get('precond', True), method=opts.get('method', 'bicgstab'),
+                         tol=opts.get('tol', 1e-10), atol=opts.get('atol', 1e-10), maxiter=opts.get('maxiter', 10000))
+    if 'custom_solver' in linear_options:
+        return linear_options['custom_solver'](A, b, x0, linear_options)
+    raise NotImplementedError("only 'jax_solver' (device Jacobi-BiCGSTAB/CG) and 'custom_solver' exist on the B200 "
+                              "hot path; petsc/amgx/spsolve back-ends are out of scope and do not fall back")
+
+
+################################################################################
+# Newton
+
+_METHOD_KEYS = frozenset({'newton', 'arc_length', 'dynamic_relax'})
+_LINEAR_OPTION_KEYS = frozenset({'jax_solver', 'amgx_solver', 'spsolve_solver', 'petsc_solver', 'custom_solver'})
+_NEWTON_OPTION_KEYS = frozenset({'tol', 'rel_tol', 'line_search_flag', 'initial_guess'})
+
+
+def _resolve_solver_options(solver_options):
+    """(method, cfg); legacy flat dicts become Newton (solver.py:1088-1106)."""
+    opts = solver_options or {}
+    methods = [m for m in _METHOD_KEYS if m in opts]
+    if not methods:
+        linear = {k: opts[k] for k in _LINEAR_OPTION_KEYS if k in opts}
+        cfg = {k: opts[k] for k in _NEWTON_OPTION_KEYS if k in opts}
+        if linear:
+            cfg['linear'] = linear
+        return 'newton', cfg
+    if len(methods) > 1:
+        raise ValueError(f"Pick one nonlinear method, got {methods}.")
+    method = methods[0]
+    if not isinstance(opts[method], dict):
+        raise ValueError(f"solver_options['{method}'] must be a dict.")
+    return method, opts[method]
+
+
+def newton_step(problem, res_vec, A, dofs, newton_cfg, timing):
+    """Solve A inc = -res with the BC-exact initial guess x0 = assign_bc(0) - copy_bc(dofs) (solver.py:390-421)."""
+    b = -res_vec
+    rows, vals, _ = problem.bc_data()
+    x0 = torch.empty_like(dofs)
+    _lib.check(_lib.load().fem_bc_initial_guess(dofs.numel(), rows.numel(), _lib.ptr(rows), _lib.ptr(vals),
+                                                _lib.ptr(dofs), _lib.ptr(x0), _lib.stream_ptr()))
+    t0 = _sync_time()
+    inc = linear_solver(A, b, x0, newton_cfg.get('linear', {}))
+    linear_s = _sync_time() - t0
+    _timing_record(timing, 'linear', linear_s)
+    if newton_cfg.get('line_search_flag', False):
+        raise NotImplementedError("line search is outside the B200 hot path")
+    return dofs + inc, linear_s
+
+
+def solver(problem, solver_options={}):
+    """Newton solve; returns sol_list = [ (num_total_nodes, vec) CUDA float64 tensor ]."""
+    method, cfg = _resolve_solver_options(solver_options)
+    if method != 'newton':
+        raise NotImplementedError(f"'{method}' is outside the B200 hot path (SURVEY.md 2: rows 9-10)")
+    logger.info("Solving the nonlinear problem...")
+    timing = {'local_assembly': 0., 'global_matrix': 0., 'linear': 0.}
+    wall_start = time.perf_counter()
+    n = problem.num_total_dofs_all_vars
+    if 'initial_guess' in cfg:
+        dofs = torch.cat([problem._as_sol([g]).reshape(-1) for g in cfg['initial_guess']]).clone()
+    else:
+        dofs = torch.zeros(n, dtype=torch.float64, device=problem.device)
+    rel_tol = cfg.get('rel_tol', 1e-8)
+    tol = cfg.get('tol', 1e-6)
+
+    def newton_update_helper(dofs):
+        t0 = _sync_time()
+        res_list = problem.newton_update(problem.unflatten_fn_sol_list(dofs))
+        local_s = _sync_time() - t0
+        _timing_record(timing, 'local_assembly', local_s)
+        res_vec = apply_bc_vec(res_list[0].reshape(-1), dofs, problem)
+        t0 = _sync_time()
+        A = get_A(problem)
+        global_s = _sync_time() - t0
+        _timing_record(timing, 'global_matrix', global_s)
+        return res_vec, A, local_s, global_s
+
+    res_vec, A, local_s, global_s = newton_update_helper(dofs)
+    res_val = _norm(res_vec)
+    res_val_initial = res_val
+    rel_res_val = res_val / res_val_initial if res_val_initial > 0 else 0.
+    _log_newton_iter_summary(0, local_s, global_s, res_val, rel_res_val)
+    n_iters = 0
+    while (rel_res_val > rel_tol) and (res_val > tol):
+        n_iters += 1
+        dofs, linear_s = newton_step(problem, res_vec, A, dofs, cfg, timing)
+        res_vec, A, local_s, global_s = newton_update_helper(dofs)
+        res_val = _norm(res_vec)
+        rel_res_val = res_val / res_val_initial
+        _log_newton_iter_summary(n_iters, local_s, global_s, res_val, rel_res_val, linear_s)
+    assert math.isfinite(res_val), "res_val contains NaN, stop the program!"
+    assert bool(torch.isfinite(dofs).all()), "dofs contains NaN, stop the program!"
+    problem.last_newton_info = {'iterations': n_iters, 'res_val': res_val, 'timing': dict(timing)}
+    _log_timing_table(n_iters, timing, time.perf_counter() - wall_start)
+    return problem.unflatten_fn_sol_list(dofs)
+
+
+################################################################################
+# Implicit differentiation (adjoint method)
+
+def implicit_vjp(problem, sol_list, params, v_list, adjoint_solver_options):
+    """-lambda^T dc/dp with A^T lambda = v (solver.py:1362-1418) for per-quadrature-point parameters.
+
+    Returns d/d(internal_vars[0]) of shape (num_cells, num_quads); the chain through the user's
+    ``set_params`` (params -> internal_vars) is left to torch.autograd by ad_wrapper."""
+    if params is not None:
+        problem.set_params(params)
+    problem.newton_update(sol_list)
+    A = get_A(problem)
+    v_vec = torch.cat([v.reshape(-1) for v in v_list]).contiguous()
+    A_T = A.transpose()
+    adjoint_vec = linear_solver(A_T, v_vec, None, dict(adjoint_solver_options))
+    # c = apply_bc(residual): Dirichlet rows of c do not depend on the parameters
+    lam = assign_zeros_bc(adjoint_vec, problem)
+    fe = problem.fes[0]
+    iv = problem._internal_var()
+    if iv is None:
+        raise ValueError("implicit_vjp needs a per-quadrature-point parameter in problem.internal_vars")
+    grad = torch.empty_like(iv)
+    law = problem._law
+    _lib.check(_lib.load().fem_adjoint_param_grad(
+        _lib.ELE[problem.ele_type], fe.vec, law.law_id, _lib.host_doubles(law.params()), _lib.ptr(problem._points),
+        _lib.ptr(problem._cells), problem.num_cells, _lib.ptr(problem._as_sol(sol_list)), _lib.ptr(iv), _lib.ptr(lam),
+        _lib.ptr(problem._ref), _lib.ptr(grad), _lib.stream_ptr()))
+    return grad
+
+
+def ad_wrapper(problem, solver_options={}, adjoint_solver_options={}):
+    """Differentiable forward map params -> sol_list (solver.py:1421-1455).
+
+    The reference registers a jax.custom_vjp; here ``fwd_pred`` is differentiable by torch.autograd:
+    ``set_params(params)`` (user code, torch ops) builds ``problem.internal_vars``; the solve is a custom
+    autograd Function whose backward is the implicit adjoint, so ``objective(fwd_pred(params)).backward()``
+    fills ``params.grad`` exactly as ``jax.grad`` does in the reference."""
+
+    class _Solve(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, theta):
+            problem.internal_vars = [theta.detach()] + list(problem.internal_vars[1:])
+            sol = solver(problem, solver_options)[0]
+            ctx.save_for_backward(theta.detach(), sol)
+            return sol
+
+        @staticmethod
+        def backward(ctx, v):
+            theta, sol = ctx.saved_tensors
+            logger.info("Running backward and solving the adjoint problem...")
+            problem.internal_vars = [theta] + list(problem.internal_vars[1:])
+            return implicit_vjp(problem, [sol], None, [v.contiguous()], adjoint_solver_options)
+
+    def fwd_pred(params):
+        problem.set_params(params)
+        iv = problem.internal_vars
+        if len(iv) == 0 or not isinstance(iv[0], torch.Tensor):
+            raise ValueError("set_params must store a torch tensor of shape (num_cells, num_quads) in internal_vars[0]")
+        theta = iv[0].to(device=problem.device, dtype=torch.float64)
+        return [_Solve.apply(theta)]
+
+    return fwd_pred

@@ -148,6 +148,12 @@ class FiniteElement:
 
 def _eval_location(fn, points, inds):
     nargs = fn.__code__.co_argcount
+    try:    # NumPy-style predicates evaluate on the transposed array in one call (point[d] -> all d-coordinates)
+        flags = np.asarray(fn(points.T) if nargs == 1 else fn(points.T, inds))
+        if flags.shape == (len(points),) and flags.dtype == np.bool_:
+            return flags
+    except Exception:
+        pass
     if nargs == 1:
         return np.array([bool(fn(p)) for p in points])
     if nargs == 2:
@@ -223,7 +229,12 @@ class Problem:
         """value_and_jacfwd of the cell kernel, problem.py:262-266 -> (C, ndof, ndof), row = test dof."""
         A = self.law.tangent(self._u_grads(sol, sl), *self._iv(sl))                     # (C,Q,v,d,v,d)
         g = self.shape_grads[sl]
-        K = np.einsum('cqidkl,cqnd,cqml,cq->cnimk', A, g, g, self.JxW[sl], optimize=True)
+        C, Q, N, d = g.shape
+        v = self.vec
+        # B[(i,d),(n,i')] = delta_ii' g[n,d]  =>  K_e = sum_q JxW B^T A B  (batched GEMMs instead of a 6-index einsum)
+        B = np.einsum('cqnd,ij->cqidnj', g, np.eye(v)).reshape(C, Q, v * d, N * v)
+        AB = np.matmul(A.reshape(C, Q, v * d, v * d) * self.JxW[sl][:, :, None, None], B)
+        K = np.matmul(B.transpose(0, 1, 3, 2), AB).sum(axis=1)
         return K.reshape(K.shape[0], self.ndof, self.ndof)
 
     def face_residuals(self, sol, k):
@@ -285,11 +296,13 @@ def csr_pattern_from_cells(cells, vec, n):
 def zero_rows(A, rows_list):
     """Mat.zeroRows with KEEP_NONZERO_PATTERN (solver.py:477,527-528): row <- 0, diagonal <- 1."""
     A = A.copy()
-    for rows in rows_list:
-        for r in rows:
-            s, e = A.indptr[r], A.indptr[r + 1]
-            A.data[s:e] = 0.0
-            A.data[s + np.searchsorted(A.indices[s:e], r)] = 1.0
+    if len(rows_list) == 0:
+        return A
+    mask = np.zeros(A.shape[0], dtype=bool)
+    mask[np.concatenate(rows_list)] = True
+    rowid = np.repeat(np.arange(A.shape[0]), np.diff(A.indptr))
+    sel = mask[rowid]
+    A.data[sel] = (A.indices[sel] == rowid[sel]).astype(np.float64)
     return A
 
 

@@ -1,0 +1,289 @@
+"""GPU parity tests: the CUDA path, called through the package's public API (which goes through the
+C ABI of include/fem_b200.h), against the CPU oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): CSR pattern / index arrays / BC masks bit-exact; residual and
+Jacobian values <= 1e-12 relative max-norm; solutions and adjoint gradients <= 1e-8 relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import fem, laws as olaws
+
+pytestmark = pytest.mark.gpu
+
+VAL_TOL = 1e-12
+SOL_TOL = 1e-8
+
+
+def relmax(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300)
+
+
+def perturbed_box(N, seed=0, amp=0.2):
+    import jax_fem_b200 as jf
+    m = jf.box_mesh(N, N + 1, N + 2, 1.0, 1.2, 0.9)
+    pts = m.points.copy()
+    rng = np.random.default_rng(seed)
+    pts += amp / (N + 2) * rng.uniform(-0.5, 0.5, pts.shape)        # non-affine cells, still valid
+    return pts, m.cells_dict['hexahedron']
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("law_name", ["poisson", "elastic", "neohookean", "neohookean_rho", "simp"])
+def test_element_residual_and_jacobian_match_oracle(law_name):
+    import jax_fem_b200 as jf
+    import gpu_problems as gp
+    pts, cells = perturbed_box(5)
+    rng = np.random.default_rng(1)
+    vec = 1 if law_name == "poisson" else 3
+    iv = None
+    if law_name == "poisson":
+        prob, olaw = gp.LinearPoisson(jf.Mesh(pts, cells), vec=1, dim=3), olaws.Poisson(1.0)
+    elif law_name == "elastic":
+        prob, olaw = gp.PlainElasticity(jf.Mesh(pts, cells), vec=3, dim=3), olaws.LinearElastic(70e3, 0.3)
+    elif law_name == "neohookean":
+        prob, olaw = gp.HyperElasticity(jf.Mesh(pts, cells), vec=3, dim=3), olaws.NeoHookean(1e3, 0.3)
+    elif law_name == "neohookean_rho":
+        prob = gp.NeoHookeanInverse(jf.Mesh(pts, cells), vec=3, dim=3, location_fns=[lambda p: np.isclose(p[1], 1.2, atol=1e-5)])
+        olaw = olaws.NeoHookean(10.0, 0.3, clamp_J=True)
+        iv = 0.5 + rng.uniform(0, 1, (len(cells), 8))
+    else:
+        prob = gp.SIMPElasticity(jf.Mesh(pts, cells), vec=3, dim=3, location_fns=[lambda p: np.isclose(p[0], 1.0, atol=1e-5)])
+        olaw = olaws.SIMP(70e3, 70.0, 0.3, 3.0)
+        iv = 0.2 + 0.7 * rng.uniform(0, 1, (len(cells), 8))
+    sol = 0.05 * rng.standard_normal((len(pts), vec))
+    if iv is not None:
+        prob.internal_vars = [torch.from_numpy(iv).cuda()]
+    opb = fem.Problem(fem.Mesh(pts, cells), vec, 3, law=olaw, internal_vars=() if iv is None else [iv])
+    prob.newton_update([torch.from_numpy(sol).cuda()])
+    Ke, Re = host(prob._Ke), host(prob._Re)
+    assert relmax(Ke, opb.cell_jacobians(sol)) <= VAL_TOL
+    law_only = fem.Problem(fem.Mesh(pts, cells), vec, 3, law=olaw, internal_vars=() if iv is None else [iv])
+    assert relmax(Re.reshape(len(cells), 8, vec), law_only.cell_residuals(sol)) <= VAL_TOL
+    # reference attribute V (problem.py:453) = cell blocks then zero face blocks
+    assert prob.V.numel() == Ke.size + sum(len(b) for b in prob.boundary_inds_list) * (8 * vec) ** 2
+
+
+def _cube_problems():
+    import jax_fem_b200 as jf
+    import gpu_problems as gp
+    g = cases.load_golden("linear_elasticity_cube")
+    prob = gp.LinearElasticityCube(jf.Mesh(g["points"], g["cells"]), vec=3, dim=3,
+                                   dirichlet_bc_info=cases.CUBE_BC, location_fns=[cases.right])
+    opb = fem.Problem(fem.Mesh(g["points"], g["cells"]), 3, 3, dirichlet_bc_info=cases.CUBE_BC,
+                      location_fns=[cases.right], law=olaws.LinearElastic(70e3, 0.3),
+                      mass_map=cases.cube_mass, surface_maps=[cases.cube_traction])
+    return g, prob, opb
+
+
+def test_pattern_bc_masks_bit_exact_and_values():
+    import jax_fem_b200 as jf
+    g, prob, opb = _cube_problems()
+    rng = np.random.default_rng(3)
+    sol = 1e-3 * rng.standard_normal(g["sol"].shape)
+    res = prob.newton_update([torch.from_numpy(sol).cuda()])[0]
+    A = jf.get_A(prob)
+    ores = opb.newton_update(sol)
+    oA = fem.get_A(opb)
+    indptr, indices, data = [host(t) for t in A.getValuesCSR()]
+    assert indptr.dtype == np.int32 and indices.dtype == np.int32
+    assert np.array_equal(indptr, oA.indptr) and np.array_equal(indices, oA.indices)       # bit-exact pattern
+    rows, vals, flag = [host(t) for t in prob.bc_data()]
+    orows = np.unique(np.concatenate(opb.bc_rows()))
+    assert np.array_equal(rows, orows)                                                    # bit-exact BC mask
+    assert np.array_equal(np.flatnonzero(flag), orows)
+    assert relmax(data, oA.data) <= VAL_TOL
+    assert relmax(host(res), ores) <= VAL_TOL
+    # residual with Dirichlet rows (apply_bc_vec) and the BC-exact initial guess
+    dofs = torch.from_numpy(sol.reshape(-1)).cuda()
+    rb = jf.apply_bc_vec(res.reshape(-1), dofs, prob)
+    assert relmax(host(rb), fem.apply_bc_vec(ores.reshape(-1), sol.reshape(-1), opb)) <= VAL_TOL
+    # COO attributes of the reference API
+    I, J = opb.coo_pattern()
+    assert np.array_equal(prob.I, I) and np.array_equal(prob.J, J)
+    # run-to-run determinism: no atomics anywhere on the path
+    prob.newton_update([torch.from_numpy(sol).cuda()])
+    assert torch.equal(jf.get_A(prob).data, A.data)
+
+
+def test_spmv_diag_transpose_match_scipy():
+    import jax_fem_b200 as jf
+    g, prob, opb = _cube_problems()
+    sol = 1e-3 * np.random.default_rng(4).standard_normal(g["sol"].shape)
+    prob.newton_update([torch.from_numpy(sol).cuda()])
+    A = jf.get_A(prob)
+    S = A.to_scipy()
+    x = np.random.default_rng(0).standard_normal(S.shape[0])
+    y = host(A @ torch.from_numpy(x).cuda())
+    assert relmax(y, S @ x) <= 1e-13
+    assert np.array_equal(host(A.diagonal()), S.diagonal())
+    AT = A.transpose()
+    ST = S.T.tocsr()
+    ST.sort_indices()
+    assert np.array_equal(host(AT.getValuesCSR()[1]), ST.indices)
+    assert np.array_equal(host(AT.data), ST.data)                 # pure permutation: bit-exact
+
+
+@pytest.mark.parametrize("method", ["bicgstab", "cg"])
+def test_krylov_matches_oracle_iterates(method):
+    import jax_fem_b200 as jf
+    from jax_fem_b200.solver import jax_solve, newton_step
+    g, prob, opb = _cube_problems()
+    sol = np.zeros(g["sol"].shape)
+    dofs = torch.zeros(sol.size, dtype=torch.float64, device='cuda')
+    res = jf.apply_bc_vec(prob.newton_update([dofs.reshape(-1, 3)])[0].reshape(-1), dofs, prob)
+    A = jf.get_A(prob)
+    ores = fem.apply_bc_vec(opb.newton_update(sol).reshape(-1), sol.reshape(-1), opb)
+    oA = fem.get_A(opb)
+    ox0 = fem.assign_bc(np.zeros(sol.size), opb) - fem.copy_bc(sol.reshape(-1), opb)
+    ox, ok = fem.jax_solve(oA, -ores, ox0, True, method, return_iters=True)
+    x0 = torch.from_numpy(ox0).cuda()
+    x, info = jax_solve(A, -res, x0, True, method=method, return_info=True)
+    assert abs(info['iterations'] - ok) <= max(3, ok // 20)       # same recurrences; rounding may shift the exit by a few
+    assert relmax(host(x), ox) <= SOL_TOL
+    assert info['err'] < 1e-6
+
+
+@pytest.mark.parametrize("case", ["linear_poisson", "linear_elasticity_cube", "hyperelasticity", "linear_elasticity_cylinder"])
+@pytest.mark.parametrize("method", ["bicgstab", "cg"])
+def test_reference_goldens_through_solver(case, method):
+    """The reference's own four benchmark tests, run through solver(problem) on the GPU."""
+    import jax_fem_b200 as jf
+    import gpu_problems as gp
+    g = cases.load_golden(case)
+    mesh = jf.Mesh(g["points"], g["cells"])
+    omesh = fem.Mesh(g["points"], g["cells"])
+    if case == "linear_poisson":
+        prob = gp.LinearPoisson(mesh, vec=1, dim=3, dirichlet_bc_info=cases.POISSON_BC)
+        opb = fem.Problem(omesh, 1, 3, dirichlet_bc_info=cases.POISSON_BC, law=olaws.Poisson())
+        decimal = 5
+    elif case == "linear_elasticity_cube":
+        prob = gp.LinearElasticityCube(mesh, vec=3, dim=3, dirichlet_bc_info=cases.CUBE_BC, location_fns=[cases.right])
+        opb = fem.Problem(omesh, 3, 3, dirichlet_bc_info=cases.CUBE_BC, location_fns=[cases.right],
+                          law=olaws.LinearElastic(70e3, 0.3), mass_map=cases.cube_mass, surface_maps=[cases.cube_traction])
+        decimal = 5
+    elif case == "hyperelasticity":
+        prob = gp.HyperElasticity(mesh, vec=3, dim=3, dirichlet_bc_info=cases.HYPER_BC)
+        opb = fem.Problem(omesh, 3, 3, dirichlet_bc_info=cases.HYPER_BC, law=olaws.NeoHookean(1e3, 0.3))
+        decimal = 5
+    else:
+        prob = gp.LinearElasticityCylinder(mesh, vec=3, dim=3, dirichlet_bc_info=cases.CYL_BC, location_fns=[cases.top])
+        opb = fem.Problem(omesh, 3, 3, dirichlet_bc_info=cases.CYL_BC, location_fns=[cases.top],
+                          law=olaws.LinearElastic(70e3, 0.3), mass_map=cases.cyl_mass, surface_maps=[cases.cyl_traction])
+        decimal = 3
+    sol = host(jf.solver(prob, {'jax_solver': {'method': method}})[0])
+    gold = g["sol"].reshape(sol.shape)
+    np.testing.assert_array_almost_equal(gold, sol, decimal=decimal)          # the reference's assertion
+    osol = fem.solver(opb, method=method)
+    assert relmax(sol, osol.reshape(sol.shape)) <= SOL_TOL                     # parity with the oracle
+    if case == "hyperelasticity":
+        assert prob.last_newton_info['iterations'] == 4
+
+
+def test_simp_adjoint_gradient_matches_oracle_and_fd():
+    import jax_fem_b200 as jf
+    import gpu_problems as gp
+    m = jf.box_mesh(8, 2, 4, 2.0, 0.5, 1.0)
+    pts, cells = m.points, m.cells_dict['hexahedron']
+    left = lambda p: np.isclose(p[0], 0., atol=1e-5)
+    load = lambda p: np.isclose(p[0], 2.0, atol=1e-5)
+    bc = [[left] * 3, [0, 1, 2], [lambda p: 0.] * 3]
+    prob = gp.SIMPElasticity(jf.Mesh(pts, cells), vec=3, dim=3, dirichlet_bc_info=bc, location_fns=[load])
+    rng = np.random.default_rng(0)
+    rho = 0.5 + 0.1 * rng.uniform(-1, 1, len(cells))
+    fwd = jf.ad_wrapper(prob)
+    params = torch.from_numpy(rho).cuda().requires_grad_(True)
+    sol = fwd(params)[0]
+    f_ext = prob._f_ext                      # residual convention: res = internal + f_ext, f_ext = -int t.v
+    J = -(f_ext * sol).sum()                 # compliance = int t.u ds
+    J.backward()
+    grad = host(params.grad)
+
+    otr = lambda u, x: -np.array([0., 0., -100.]) + 0. * u
+    opb = fem.Problem(fem.Mesh(pts, cells), 3, 3, dirichlet_bc_info=bc, location_fns=[load],
+                      law=olaws.SIMP(70e3, 70.0, 0.3, 3.0), surface_maps=[otr],
+                      internal_vars=[np.repeat(rho[:, None], 8, axis=1)])
+    osol = fem.solver(opb)
+    assert relmax(host(sol), osol) <= SOL_TOL
+    of = np.zeros_like(osol)
+    np.add.at(of, opb.cells[opb.boundary_inds_list[0][:, 0]].reshape(-1), opb.face_residuals(osol, 0).reshape(-1, 3))
+    ograd = fem.implicit_vjp(opb, osol, -of).sum(axis=1)
+    assert relmax(grad, ograd) <= SOL_TOL
+    assert abs(float(J) - float(-(of * osol).sum())) <= SOL_TOL * abs(float(J))
+    # finite-difference check a la docs/source/learn/compute_gradients/example.ipynb cells 24-29
+    k = int(np.argmax(np.abs(grad)))
+    h = 1e-4
+    vals = []
+    for s in (+1, -1):
+        r2 = rho.copy()
+        r2[k] += s * h
+        s2 = fwd(torch.from_numpy(r2).cuda())[0]
+        vals.append(float(-(f_ext * s2).sum()))
+    fd = (vals[0] - vals[1]) / (2 * h)
+    assert abs(fd - grad[k]) <= 1e-5 * abs(grad[k])
+
+
+def test_quad4_poisson_config1_plumbing():
+    """BASELINE.json configs[0]: Poisson on QUAD4 rectangle_mesh 32x32 (Quickstart.md:15-51), bicgstab."""
+    import jax_fem_b200 as jf
+    from jax_fem_b200 import laws
+
+    class Poisson(jf.Problem):
+        def get_tensor_map(self):
+            return laws.Poisson(1.0)
+
+        def get_mass_map(self):
+            return lambda u, x: np.array([-10. * np.exp(-((x[0] - 0.5) ** 2 + (x[1] - 0.5) ** 2) / 0.02)])
+
+    m = jf.rectangle_mesh(32, 32, 1., 1.)
+    fns = [lambda p: np.isclose(p[0], 0., atol=1e-5), lambda p: np.isclose(p[0], 1., atol=1e-5),
+           lambda p: np.isclose(p[1], 0., atol=1e-5), lambda p: np.isclose(p[1], 1., atol=1e-5)]
+    bc = [fns, [0] * 4, [lambda p: 0.] * 4]
+    prob = Poisson(jf.Mesh(m.points, m.cells_dict['quad']), vec=1, dim=2, ele_type='QUAD4', dirichlet_bc_info=bc)
+    sol = host(jf.solver(prob)[0])
+    om = fem.rectangle_mesh(32, 32, 1., 1.)
+    src = lambda u, x: (-10. * np.exp(-((x[..., 0] - 0.5) ** 2 + (x[..., 1] - 0.5) ** 2) / 0.02))[..., None]
+    opb = fem.Problem(om, 1, 2, ele_type='QUAD4', dirichlet_bc_info=bc, law=olaws.Poisson(), mass_map=src)
+    osol = fem.solver(opb)
+    assert prob.plan.nnz == 9409 and sol.shape == (1089, 1)
+    assert relmax(sol, osol) <= SOL_TOL
+    assert sol.max() > 0.01
+
+
+def test_unregistered_paths_raise():
+    import jax_fem_b200 as jf
+    from jax_fem_b200 import laws
+
+    class Custom(jf.Problem):
+        def get_tensor_map(self):
+            return lambda u_grad: u_grad * 2.0
+
+    class Universal(jf.Problem):
+        def get_tensor_map(self):
+            return laws.Poisson()
+
+        def get_universal_kernel(self):
+            return None
+
+    m = jf.box_mesh(2, 2, 2, 1, 1, 1)
+    mesh = jf.Mesh(m.points, m.cells_dict['hexahedron'])
+    with pytest.raises(laws.UnregisteredLawError):
+        Custom(mesh, vec=1, dim=3)
+    with pytest.raises(NotImplementedError):
+        Universal(mesh, vec=1, dim=3)
+    with pytest.raises(NotImplementedError):
+        class P2(jf.Problem):
+            def get_tensor_map(self):
+                return laws.NeoHookean(1., 0.3)
+        P2(mesh, vec=1, dim=3)
+    ok = type("Ok", (jf.Problem,), {"get_tensor_map": lambda self: laws.Poisson()})(mesh, vec=1, dim=3)
+    with pytest.raises(NotImplementedError):
+        jf.solver(ok, {'petsc_solver': {}})
+    with pytest.raises(NotImplementedError):
+        jf.solver(ok, {'arc_length': {}})

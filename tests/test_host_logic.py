@@ -1,0 +1,144 @@
+"""CPU tests of the host side: reference tables, meshes, plan (pattern bit-exact vs the oracle), Dirichlet /
+face index sets, load vectors, law registry, and that the C-ABI library loads and exports every declared
+symbol.  No compute call is made (there is no GPU here and the product has no CPU fallback)."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import basis as obasis, fem, laws as olaws
+import jax_fem_b200 as jf
+from jax_fem_b200 import _lib, basis, laws
+from jax_fem_b200.fe import FiniteElement, evaluate_location_fn, evaluate_point_fn
+from jax_fem_b200.plan import build_plan
+
+
+@pytest.mark.parametrize("ele", ["HEX8", "QUAD4", "HEX27"])
+def test_reference_tables_match_oracle(ele):
+    for a, b in zip(obasis.get_shape_vals_and_grads(ele), basis.get_shape_vals_and_grads(ele)):
+        assert np.abs(a - b).max() < 1e-14
+    for a, b in zip(obasis.get_face_shape_vals_and_grads(ele), basis.get_face_shape_vals_and_grads(ele)):
+        assert np.abs(a - b).max() < 1e-14
+
+
+def test_mesh_generators_match_oracle_numbering():
+    o, p = fem.box_mesh(4, 3, 2, 1., 2., 3.), jf.box_mesh(4, 3, 2, 1., 2., 3.)
+    assert np.array_equal(o.points, p.points) and np.array_equal(o.cells, p.cells_dict['hexahedron'])
+    o, p = fem.rectangle_mesh(5, 3, 1., 2.), jf.rectangle_mesh(5, 3, 1., 2.)
+    assert np.array_equal(o.points, p.points) and np.array_equal(o.cells, p.cells_dict['quad'])
+    h = jf.box_mesh_hex27(2, 3, 2, 1., 1., 1.)
+    cells, pts = h.cells_dict['hexahedron27'], h.points
+    assert cells.shape == (12, 27) and len(pts) == 5 * 7 * 5 and len(np.unique(cells)) == len(pts)
+    # every cell's nodes must sit on the VTK triquadratic lattice of its own corner box
+    lattice = basis.get_elements('HEX27')[3] / 2.0
+    for c in cells[[0, 5, 11]]:
+        x = pts[c]
+        lo, hi = x[0], x[6]
+        assert np.allclose(x, lo + lattice * (hi - lo))
+
+
+@pytest.mark.parametrize("N,vec", [(3, 3), (6, 3), (5, 1)])
+def test_plan_pattern_bit_exact(N, vec):
+    m = jf.box_mesh(N, N + 1, N, 1, 1, 1)
+    cells = m.cells_dict['hexahedron']
+    plan = build_plan(torch.from_numpy(cells), len(m.points), vec)
+    indptr, indices = fem.csr_pattern_from_cells(cells, vec, vec * len(m.points))
+    assert plan.indptr.dtype == torch.int32 and plan.indices.dtype == torch.int32
+    assert np.array_equal(plan.indptr.numpy(), indptr) and np.array_equal(plan.indices.numpy(), indices)
+    # source lists: every (cell, a, b) appears exactly once and lands in the right block
+    src = plan.src.numpy().astype(np.int64)
+    assert np.array_equal(np.sort(src), np.arange(cells.shape[0] * 64))
+    c, a, b = src // 64, (src // 8) % 8, src % 8
+    counts = np.diff(plan.src_ptr.numpy())
+    brow = np.repeat(np.arange(len(m.points)), np.diff(plan.brow_ptr.numpy()))
+    assert np.array_equal(np.repeat(brow, counts), cells[c, a])
+    assert np.array_equal(np.repeat(plan.bcol.numpy(), counts), cells[c, b])
+    # transpose permutation is an involution mapping (n,m) -> (m,n)
+    t = plan.tperm.numpy()
+    assert np.array_equal(t[t], np.arange(len(t)))
+    assert np.array_equal(plan.bcol.numpy()[t], brow)
+    nc = plan.nc.numpy()
+    assert np.array_equal(np.repeat(np.arange(len(m.points)), np.diff(plan.nc_ptr.numpy())), cells.reshape(-1)[nc])
+
+
+def test_plan_on_unstructured_golden_mesh():
+    g = cases.load_golden("hyperelasticity")
+    plan = build_plan(torch.from_numpy(g["cells"]), len(g["points"]), 3)
+    indptr, indices = fem.csr_pattern_from_cells(g["cells"], 3, 3 * len(g["points"]))
+    assert np.array_equal(plan.indptr.numpy(), indptr) and np.array_equal(plan.indices.numpy(), indices)
+
+
+def test_dirichlet_and_face_sets_match_oracle():
+    g = cases.load_golden("linear_elasticity_cylinder")
+    mesh = jf.Mesh(g["points"], g["cells"])
+    fe = FiniteElement(mesh, 3, 3, 'HEX8', dirichlet_bc_info=cases.CYL_BC)
+    ofe = fem.FiniteElement(fem.Mesh(g["points"], g["cells"]), 3, 3, 'HEX8', dirichlet_bc_info=cases.CYL_BC)
+    for a, b in zip(fe.node_inds_list, ofe.node_inds_list):
+        assert np.array_equal(a, b)
+    for a, b in zip(fe.vals_list, ofe.vals_list):
+        assert np.array_equal(a, b)
+    b1 = fe.get_boundary_conditions_inds([cases.top])[0]
+    b2 = ofe.get_boundary_conditions_inds([cases.top])[0]
+    assert np.array_equal(b1, b2)
+    g1, n1 = fe.get_face_shape_grads(b1)
+    g2, n2 = ofe.get_face_shape_grads(b2)
+    assert np.abs(g1 - g2).max() < 1e-13 and np.abs(n1 - n2).max() < 1e-14
+    np.testing.assert_almost_equal(n1.sum(), float(g["surface_area"]), decimal=10)
+    s1, j1 = fe.get_shape_grads()
+    s2, j2 = ofe.get_shape_grads()
+    assert np.abs(s1 - s2).max() < 1e-13 and np.abs(j1 - j2).max() < 1e-14
+
+
+def test_vectorised_predicates_fall_back_to_pointwise():
+    pts = np.random.default_rng(0).uniform(0, 1, (200, 3))
+    vect = lambda p: np.isclose(p[0], pts[7, 0], atol=1e-5)
+    scalar_only = lambda p: bool(p[0] > 0.5 and p[1] < 0.5)          # `and` breaks on arrays -> per-point loop
+    with_index = lambda p, i: (p[2] > 0.3) & (i % 2 == 0)
+    assert np.array_equal(evaluate_location_fn(vect, pts), np.isclose(pts[:, 0], pts[7, 0], atol=1e-5))
+    assert np.array_equal(evaluate_location_fn(scalar_only, pts), (pts[:, 0] > 0.5) & (pts[:, 1] < 0.5))
+    assert np.array_equal(evaluate_location_fn(with_index, pts), (pts[:, 2] > 0.3) & (np.arange(200) % 2 == 0))
+    with pytest.raises(ValueError):
+        evaluate_location_fn(lambda a, b, c: True, pts)
+    assert np.array_equal(evaluate_point_fn(lambda p: 1.5, pts), np.full(200, 1.5))
+    assert np.allclose(evaluate_point_fn(lambda p: np.array([p[0], 2 * p[1], 0.]), pts, (3,)),
+                       np.stack([pts[:, 0], 2 * pts[:, 1], 0 * pts[:, 0]], 1))
+    assert evaluate_point_fn(lambda p: 1.0, pts[:0]).shape == (0,)   # empty Dirichlet set
+
+
+def test_law_registry_raises_on_unregistered():
+    assert laws.resolve(laws.NeoHookean(1., 0.3), 'HEX8', 3).law_id == 2
+    with pytest.raises(laws.UnregisteredLawError):
+        laws.resolve(lambda u_grad: u_grad, 'HEX8', 3)
+    with pytest.raises(laws.UnregisteredLawError):
+        laws.resolve(laws.NeoHookean(1., 0.3), 'QUAD4', 2)
+    with pytest.raises(NotImplementedError):
+        basis.get_elements('TET4')
+
+
+def test_library_exports_every_declared_symbol_and_has_no_cpu_fallback():
+    lib = _lib.load()
+    declared = _lib.declared_symbols()
+    assert len(declared) >= 17
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert set(declared) == set(_lib._SIGNATURES)
+    assert lib.fem_version() >= 100
+    if not torch.cuda.is_available():
+        assert lib.fem_device_count() == -3                                      # FEM_ENODEV
+        assert lib.fem_spmv(0, None, None, None, None, None, None) == -3         # refuses to compute without a GPU
+        assert b"no CUDA device" in lib.fem_last_error()
+        m = jf.box_mesh(2, 2, 2, 1, 1, 1)
+        with pytest.raises(RuntimeError):
+            type("P", (jf.Problem,), {"get_tensor_map": lambda self: laws.Poisson()})(
+                jf.Mesh(m.points, m.cells_dict['hexahedron']), vec=1, dim=3)
+
+
+def test_product_never_imports_the_oracle():
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dirpath, _, files in os.walk(os.path.join(root, "jax_fem_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
