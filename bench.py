@@ -24,6 +24,13 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    """Progress on stderr (stdout carries exactly one JSON line)."""
+    if os.environ.get("RANK", "0") == "0":
+        print(f"[bench {time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
 
 HBM_FALLBACK_GBS = 6650.0
 
@@ -85,9 +92,10 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------
-def cpu_oracle_assembly(size, repeats=1):
+def cpu_oracle_assembly(size, repeats=1, threads=None):
     """Time the oracle's assembly (element einsum + COO->CSR + BC rows) on the host; returns (DOFs/s, dict)."""
     from oracle import fem, laws
+    threads = threads or min(32, os.cpu_count() or 1)
     t0 = time.perf_counter()
     mesh = fem.box_mesh(size, size, size, 1., 1., 1.)
     left = lambda p: np.isclose(p[0], 0., atol=1e-5)
@@ -97,9 +105,22 @@ def cpu_oracle_assembly(size, repeats=1):
     sol = 1e-3 * np.random.default_rng(0).standard_normal((len(mesh.points), 3))
     I, J = pb.coo_pattern()
     best = None
+    # Element phase: cell chunks on a thread pool (NumPy releases the GIL in einsum/matmul) with BLAS pinned to one
+    # thread per call -- many-core hosts otherwise spend their time in BLAS thread hand-offs on 24x9 GEMMs.
+    # Global phase (COO -> CSR, BC rows) is single-threaded, like PETSc's setValuesCOO in the reference.
+    from concurrent.futures import ThreadPoolExecutor
+    from threadpoolctl import threadpool_limits
+    C = pb.num_cells
+    bounds = np.linspace(0, C, 4 * threads + 1).astype(int)
+    chunks = [slice(int(a), int(b)) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
     for _ in range(repeats):
         t0 = time.perf_counter()
-        res = pb.newton_update(sol)                                   # element residuals + einsum tangents
+        with threadpool_limits(limits=1), ThreadPoolExecutor(threads) as pool:
+            Ks = list(pool.map(lambda sl: pb.cell_jacobians(sol, sl), chunks))
+            Rs = list(pool.map(lambda sl: pb.cell_residuals(sol, sl), chunks))
+        pb.V_cells = np.concatenate(Ks)
+        res = np.zeros((len(mesh.points), 3))
+        np.add.at(res, pb.cells.reshape(-1), np.concatenate(Rs).reshape(-1, 3))
         t1 = time.perf_counter()
         A = fem.zero_rows(fem.coo_to_csr(I, J, pb.coo_values(), pb.num_total_dofs_all_vars), pb.bc_rows())
         fem.apply_bc_vec(res.reshape(-1), sol.reshape(-1), pb)
@@ -114,7 +135,8 @@ def cpu_oracle_assembly(size, repeats=1):
     spmv_s = (time.perf_counter() - t0) / 5
     n = pb.num_total_dofs_all_vars
     return n / best[0], {"n_dofs": n, "nnz": int(A.nnz), "element_s": best[1], "coo_to_csr_s": best[2],
-                         "spmv_ms": spmv_s * 1e3, "spmv_gbs": (12 * A.nnz + 20 * n) / spmv_s / 1e9, "setup_s": setup_s}
+                         "spmv_ms": spmv_s * 1e3, "spmv_gbs": (12 * A.nnz + 20 * n) / spmv_s / 1e9, "setup_s": setup_s,
+                         "threads": threads}
 
 
 def run_reference(args):
@@ -132,7 +154,7 @@ def run_reference(args):
         v, info = cpu_oracle_assembly(size)
         vals.append(v)
     value = float(np.mean(vals))
-    cores = os.cpu_count()
+    cores = info["threads"]
     line = {
         "impl": "reference", "metric": "assembled DOFs/s (residual+Jacobian), HEX8 linear elasticity", "value": value,
         "unit": "DOF/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": 1, "ms_per_step": 1e3 * info["n_dofs"] / value,
@@ -183,6 +205,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("BENCH_WATCHDOG_S", "900")), exit=True)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -201,8 +225,10 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     t0 = time.perf_counter()
+    log(f"building problem {args.size}^3")
     prob = build_problem(args.size)
     setup_s = time.perf_counter() - t0
+    log(f"problem built in {setup_s:.1f}s: {prob.num_total_dofs_all_vars} dofs, nnz {prob.plan.nnz}")
     fe = prob.fes[0]
     n, nnz = prob.num_total_dofs_all_vars, prob.plan.nnz
     b_asm, b_spmv = algorithmic_bytes(n, nnz, prob.num_cells, fe.num_total_nodes)
@@ -225,6 +251,7 @@ def main():
     for _ in range(args.warmup):
         res_vec, A = step(sol)
     barrier()
+    log("warm-up done")
 
     # ---- timed region: device-resident inputs -------------------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -258,6 +285,7 @@ def main():
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1) / args.steps
+    log(f"assembly {ms_step:.3f} ms/step (element {t_elem:.3f}, bc {t_bc:.3f}, gather {t_gather:.3f}); e2e {e2e_ms:.3f} ms")
 
     # ---- SpMV (the CG kernel) on the assembled matrix -----------------------------------------------------
     x = torch.from_numpy(np.random.default_rng(0).standard_normal(n)).to(dev)
@@ -273,6 +301,7 @@ def main():
     s1.record()
     torch.cuda.synchronize()
     spmv_ms = s0.elapsed_time(s1) / reps
+    log(f"spmv {spmv_ms:.3f} ms = {b_spmv / spmv_ms / 1e6:.0f} GB/s")
 
     solve = None
     if args.solve:
@@ -284,6 +313,7 @@ def main():
         _, info = jax_solve(A0, -r0, torch.zeros_like(dofs), True, method='cg', return_info=True)
         torch.cuda.synchronize()
         cs = time.perf_counter() - c0
+        log(f"cg: {info}, {cs:.2f}s")
         solve = {"method": "jacobi-cg", "iterations": info['iterations'], "seconds": cs, "err": info['err'],
                  "ms_per_iteration": 1e3 * cs / max(info['iterations'], 1),
                  "effective_spmv_gbs": b_spmv / (cs / max(info['iterations'], 1)) / 1e9}
@@ -323,8 +353,9 @@ def main():
         if solve:
             line["cg_solve"] = solve
         if not args.no_cpu_baseline and world == 1:
+            log(f"timing the CPU oracle on {args.ref_size}^3")
             v, info = cpu_oracle_assembly(args.ref_size)
-            line["cpu_baseline"] = {"value": v, "unit": "DOF/s", "cores": os.cpu_count(), "kind": "port",
+            line["cpu_baseline"] = {"value": v, "unit": "DOF/s", "cores": info["threads"], "kind": "port",
                                     "sample": f"{args.ref_size}^3 HEX8 cells ({info['n_dofs']} DOF) of the same workload: element "
                                               f"{info['element_s']:.2f}s + COO->CSR+BC {info['coo_to_csr_s']:.2f}s; "
                                               f"SpMV {info['spmv_gbs']:.1f} GB/s"}

@@ -110,21 +110,27 @@ __global__ void __launch_bounds__(kThreads) spmv_fused_kernel(int64_t n, const i
   constexpr int RPB = kThreads / LPR;
   const int sub = threadIdx.x % LPR;
   double dots[2] = {0.0, 0.0};
-  for (int64_t row = (int64_t)blockIdx.x * RPB + threadIdx.x / LPR; row < n; row += (int64_t)gridDim.x * RPB) {
-    const int s = indptr[row], e = indptr[row + 1];
+  // the trip count is uniform across the block (loop on the block's first row) because the intra-row
+  // shuffle below names every lane of the warp
+  for (int64_t base = (int64_t)blockIdx.x * RPB; base < n; base += (int64_t)gridDim.x * RPB) {
+    const int64_t row = base + threadIdx.x / LPR;
+    const bool valid = row < n;
     double a0 = 0.0, a1 = 0.0;
-    int j = s + sub;
-    for (; j + LPR < e; j += 2 * LPR) {
-      const double v0 = data[j], v1 = data[j + LPR];
-      const int c0 = indices[j], c1 = indices[j + LPR];
-      a0 = fma(v0, __ldg(x + c0), a0);
-      a1 = fma(v1, __ldg(x + c1), a1);
+    if (valid) {
+      const int s = indptr[row], e = indptr[row + 1];
+      int j = s + sub;
+      for (; j + LPR < e; j += 2 * LPR) {
+        const double v0 = data[j], v1 = data[j + LPR];
+        const int c0 = indices[j], c1 = indices[j + LPR];
+        a0 = fma(v0, __ldg(x + c0), a0);
+        a1 = fma(v1, __ldg(x + c1), a1);
+      }
+      if (j < e) a0 = fma(data[j], __ldg(x + indices[j]), a0);
     }
-    if (j < e) a0 = fma(data[j], __ldg(x + indices[j]), a0);
     double acc = a0 + a1;
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (sub == 0) {
+    if (valid && sub == 0) {
       y[row] = acc;
       if (MODE == 1 || MODE == 2) dots[0] = fma(d1[row], acc, dots[0]);
       if (MODE == 3) {

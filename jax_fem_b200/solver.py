@@ -228,6 +228,12 @@ def solver(problem, solver_options={}):
     method, cfg = _resolve_solver_options(solver_options)
     if method != 'newton':
         raise NotImplementedError(f"'{method}' is outside the B200 hot path (SURVEY.md 2: rows 9-10)")
+    unsupported = set(cfg.get('linear', {})) & {'petsc_solver', 'amgx_solver', 'spsolve_solver'}
+    if unsupported:
+        raise NotImplementedError(f"linear back-end(s) {sorted(unsupported)} are outside the B200 hot path: only "
+                                  "'jax_solver' (device Jacobi-BiCGSTAB/CG) and 'custom_solver' exist; no fallback")
+    if cfg.get('line_search_flag', False):
+        raise NotImplementedError("line search is outside the B200 hot path")
     logger.info("Solving the nonlinear problem...")
     timing = {'local_assembly': 0., 'global_matrix': 0., 'linear': 0.}
     wall_start = time.perf_counter()

@@ -31,6 +31,17 @@ import scipy.sparse as sp
 
 from . import basis as _basis
 
+try:
+    from threadpoolctl import threadpool_limits as _tpl
+
+    def _blas_single_thread():
+        return _tpl(limits=1, user_api='blas')
+except Exception:            # pragma: no cover
+    import contextlib
+
+    def _blas_single_thread():
+        return contextlib.nullcontext()
+
 
 # ----------------------------------------------------------------------------
 # generate_mesh.py:120-189
@@ -233,8 +244,9 @@ class Problem:
         v = self.vec
         # B[(i,d),(n,i')] = delta_ii' g[n,d]  =>  K_e = sum_q JxW B^T A B  (batched GEMMs instead of a 6-index einsum)
         B = np.einsum('cqnd,ij->cqidnj', g, np.eye(v)).reshape(C, Q, v * d, N * v)
-        AB = np.matmul(A.reshape(C, Q, v * d, v * d) * self.JxW[sl][:, :, None, None], B)
-        K = np.matmul(B.transpose(0, 1, 3, 2), AB).sum(axis=1)
+        with _blas_single_thread():      # tiny GEMMs: BLAS thread hand-offs dominate on many-core hosts
+            AB = np.matmul(A.reshape(C, Q, v * d, v * d) * self.JxW[sl][:, :, None, None], B)
+            K = np.matmul(B.transpose(0, 1, 3, 2), AB).sum(axis=1)
         return K.reshape(K.shape[0], self.ndof, self.ndof)
 
     def face_residuals(self, sol, k):
