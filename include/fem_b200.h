@@ -54,8 +54,10 @@ int fem_device_count(void);
  *             (jax_fem/basis.py:141-175), device memory.
  * internal_var: (n_cells, NQ) per-quadrature-point parameter (problem.internal_vars[0],
  *             jax_fem/problem.py:125,493-556) or NULL.
- * Ke: (n_cells, ndof, ndof) row-major, row = test dof -- identical to the reference's
- *     problem.V cell blocks (problem.py:265,453); NULL = residual only.
+ * Ke: (n_cells, NN(NN+1)/2, vec, vec): the node-pair blocks (a, b >= a) of the element tangent
+ *     d r_(a,i) / d u_(b,k), pair index a*NN - a(a-1)/2 + (b-a).  The tangent of every registered law is
+ *     symmetric, so the lower blocks are the transposes; expanding gives exactly the reference's
+ *     problem.V cell blocks (problem.py:265,453).  NULL = residual only.
  * Re: (n_cells, ndof) element residuals (weak_form_flat, problem.py:443).
  */
 int fem_element_residual_jacobian(int ele_type, int vec, int law_id, const double* law_params_host,
@@ -66,17 +68,21 @@ int fem_element_residual_jacobian(int ele_type, int vec, int law_id, const doubl
 /* ---- (2) global assembly: _PetscTangentCache.update / get_A (jax_fem/solver.py:469-553)
  *      as a precomputed cell->CSR-slot permutation + deterministic segmented sum (no atomics).
  *
- * Node-block graph: brow_ptr (n_nodes+1), entries e in [brow_ptr[n], brow_ptr[n+1]) are the
- * neighbour nodes of n in ascending order.  src_ptr (nnzb+1) / src: for block entry e the codes
- * p = (c*NN + a)*NN + b of every (cell, local row node, local col node) contributing to it,
- * ascending in p (fixed summation order => bit-reproducible).
- * bc_flag (n_dofs) uint8: 1 on Dirichlet rows -> row zeroed, unit diagonal, pattern kept
- * (Mat.zeroRows with KEEP_NONZERO_PATTERN, solver.py:477,527-528).
- * data: CSR values for the scalar pattern (indptr[vec*n+i] = vec*vec*brow_ptr[n] + i*vec*len(n)).
+ * The node-block graph has one "entry" per (row node n, neighbour node m), rows ascending, columns
+ * ascending.  src_ptr (nnzb+1) / src (n_items): for entry e the codes p = (c*NN + a)*NN + b of every
+ * (cell, local row node, local col node) contributing to it, ascending in p (fixed summation order =>
+ * bit-reproducible).  Ke is the packed output of fem_element_residual_jacobian.
+ * blk_ent (n_blocks+1): first entry whose first source is >= 256*b (n_blocks = ceil(n_items/256)); no entry
+ * may have more than 64 sources.
+ * edst (nnzb): offset in `data` of element (row vec*n, col vec*m) of the scalar CSR pattern
+ *              (indptr[vec*n+i] = vec*vec*brow_ptr[n] + i*vec*len(n)).
+ * einfo (nnzb): bits 0..15 = vec*len(n) (distance between the entry's consecutive scalar rows), bit 16 = m == n,
+ *              bit 17+i = row vec*n+i is a Dirichlet row -> row zeroed, unit diagonal, pattern kept
+ *              (Mat.zeroRows with KEEP_NONZERO_PATTERN, solver.py:477,527-528).
  */
-int fem_gather_csr(int vec, int nn, int64_t n_nodes, const int32_t* brow_ptr, const int32_t* bcol,
-                   const int32_t* src_ptr, const int32_t* src, const double* Ke,
-                   const uint8_t* bc_flag, double* data, void* stream);
+int fem_gather_csr(int vec, int nn, int64_t n_items, int64_t n_blocks, const int32_t* blk_ent,
+                   const int32_t* src_ptr, const int32_t* src, const int32_t* edst, const int32_t* einfo,
+                   const double* Ke, double* data, void* stream);
 
 /* residual scatter-add of problem.py:426-437 as a per-node gather: nc_ptr (n_nodes+1) / nc codes
  * c*NN + a ascending; res = sum Re + f_ext (f_ext may be NULL).                                  */

@@ -32,6 +32,25 @@ int check_device();
 
 constexpr int kNumSM = 148;   // B200
 
+// Packed storage of the symmetric element tangent: node-pair blocks (a, b >= a).
+// For NN >= 8 the element kernel produces the row block in two column halves (b < NN/2, then b >= NN/2),
+// so the pairs of the first half are stored first: [a <= b < NB] then [b >= NB].  Mirrored by
+// jax_fem_b200/plan.py::pair_index.
+template <int NN>
+__host__ __device__ constexpr int pair_split() { return NN >= 8 ? NN / 2 : NN; }
+template <int NN>
+__host__ __device__ constexpr int pair_first_half() { return NN >= 8 ? (NN / 2) * (NN / 2 + 1) / 2 : 0; }
+template <int NN>
+__host__ __device__ __forceinline__ int pair_index(int a, int b) {   // requires a <= b
+  constexpr int NB = pair_split<NN>();
+  if (NB == NN) return a * NN - (a * (a - 1)) / 2 + (b - a);
+  constexpr int P0 = pair_first_half<NN>(), W = NN - NB;
+  if (b < NB) return a * NB - (a * (a - 1)) / 2 + (b - a);
+  if (a < NB) return P0 + a * W + (b - NB);
+  const int r = a - NB;
+  return P0 + NB * W + r * W - (r * (r - 1)) / 2 + (b - a);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

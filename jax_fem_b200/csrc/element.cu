@@ -11,6 +11,9 @@
 //   phase 2: lane = local node a.  r_a = sum_q S_q g_a(q);  K row block (a, :) accumulated in
 //            registers from broadcast shared-memory reads of g_b(q) (all NN lanes of a cell read
 //            the same address), closed-form tangents -- no AD, no per-cell (24x24) temporaries.
+//   output : the tangent of every registered law is symmetric, so only the node-pair blocks
+//            (a, b >= a) are stored (NN(NN+1)/2 blocks of VEC x VEC), staged through shared memory
+//            and written with fully coalesced 16-byte stores.
 #include "common.cuh"
 
 namespace femb200 {
@@ -74,7 +77,12 @@ struct Layout {
   static constexpr int REC = pad_odd(OFF_X + LawExtra<LAW, NN, DIM>::value);
   static constexpr int OFF_XN = 0;                          // X[NN][DIM] node coordinates
   static constexpr int OFF_UN = NN * DIM;                   // U[NN][VEC] nodal solution
-  static constexpr int OFF_REC = NN * DIM + NN * VEC;
+  // Output staging overlays the cell area: the first-half pair blocks go to [0, STAGE_A) (X,U are dead after
+  // phase 1), the remaining blocks to the record zone once the whole warp is past phase 2.
+  static constexpr int NPAIR = NN * (NN + 1) / 2;
+  static constexpr int P0 = pair_first_half<NN>();
+  static constexpr int STAGE_A = (P0 * VEC * VEC + 1) / 2 * 2;
+  static constexpr int OFF_REC = (NN * DIM + NN * VEC > STAGE_A) ? NN * DIM + NN * VEC : STAGE_A;
   static constexpr int CELL_RAW = OFF_REC + NQ * REC;
   // cell stride == 8 (mod 16) doubles: the two cells of a half-warp hit disjoint bank sets
   static constexpr int CELL = CELL_RAW + ((8 - CELL_RAW % 16) + 16) % 16;
@@ -200,10 +208,10 @@ __device__ __forceinline__ void nh_stress(const NHPoint& k, double kappa, double
 
 // ---- the element kernel ----------------------------------------------------------------------------
 template <int NN, int DIM, int VEC, int LAW, int CPB, bool JAC>
-__global__ void __launch_bounds__(CPB* NN) element_kernel(const ElemArgs A) {
+__global__ void __launch_bounds__(CPB* NN, (LAW == FEM_LAW_NEO_HOOKEAN ? 2 : 512 / (CPB * NN))) element_kernel(const ElemArgs A) {
   using L = Layout<NN, DIM, VEC, LAW>;
   constexpr int NQ = L::NQ, ND = L::ND;
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   double* tab = sm;
   const int lc = threadIdx.x / NN, lane = threadIdx.x % NN;
   double* cb = sm + L::TAB_SIZE + lc * L::CELL;
@@ -292,12 +300,12 @@ __global__ void __launch_bounds__(CPB* NN) element_kernel(const ElemArgs A) {
     }
   }
   __syncthreads();
-  if (!active) return;
 
   // ---------------- phase 2: lane = local node a ----------------
+  // (no early return: every lane of the warp must reach the __syncwarp()s below)
   const int a = lane;
   const double* recs = cb + L::OFF_REC;
-  {
+  if (active) {
     double r[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) r[i] = 0.0;
@@ -312,124 +320,162 @@ __global__ void __launch_bounds__(CPB* NN) element_kernel(const ElemArgs A) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) A.Re[c * ND + a * VEC + i] = r[i];
   }
-  if constexpr (!JAC) return;
-
-  double* Krow = A.Ke + c * (int64_t)(ND * ND) + (int64_t)a * VEC * ND;
-  if constexpr (LAW == FEM_LAW_POISSON) {
-    double G[NN];
-#pragma unroll
-    for (int b = 0; b < NN; ++b) G[b] = 0.0;
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const double* rec = recs + q * L::REC;
-      double ga[DIM];
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) ga[d] = rec[L::OFF_G + a * DIM + d] * rec[L::OFF_X];
-#pragma unroll
-      for (int b = 0; b < NN; ++b)
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) G[b] = fma(ga[d], rec[L::OFF_G + b * DIM + d], G[b]);
-    }
-#pragma unroll
-    for (int i = 0; i < VEC; ++i)
-#pragma unroll
-      for (int b = 0; b < NN; ++b)
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) Krow[i * ND + b * VEC + k] = (i == k) ? G[b] : 0.0;
-  } else if constexpr (LAW == FEM_LAW_LINEAR_ELASTIC || LAW == FEM_LAW_SIMP) {
-    // K_ab[i][k] = lam' G[i][k] + mu' G[k][i] + mu' tr(G) delta_ik,  G = sum_q E_q w_q g_a (x) g_b
-    double G[NN][DIM][DIM];
-#pragma unroll
-    for (int b = 0; b < NN; ++b)
-#pragma unroll
-      for (int i = 0; i < DIM; ++i)
-#pragma unroll
-        for (int k = 0; k < DIM; ++k) G[b][i][k] = 0.0;
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const double* rec = recs + q * L::REC;
-      double ga[DIM];
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) ga[d] = rec[L::OFF_G + a * DIM + d] * rec[L::OFF_X];
-#pragma unroll
-      for (int b = 0; b < NN; ++b) {
-        double gb[DIM];
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) gb[d] = rec[L::OFF_G + b * DIM + d];
-#pragma unroll
-        for (int i = 0; i < DIM; ++i)
-#pragma unroll
-          for (int k = 0; k < DIM; ++k) G[b][i][k] = fma(ga[i], gb[k], G[b][i][k]);
-      }
-    }
-    const double nu = iso_nu<LAW>(A.p);
-    const double mu1 = 1.0 / (2.0 * (1.0 + nu)), lam1 = nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
-#pragma unroll
-    for (int b = 0; b < NN; ++b) {
-      double tr = 0.0;
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) tr += G[b][d][d];
-#pragma unroll
-      for (int i = 0; i < DIM; ++i)
-#pragma unroll
-        for (int k = 0; k < DIM; ++k)
-          Krow[i * ND + b * VEC + k] = lam1 * G[b][i][k] + mu1 * G[b][k][i] + (i == k ? mu1 * tr : 0.0);
-    }
-  } else {
-    // Neo-Hookean: K_ab[i][k] = c1 (g_a.g_b) d_ik + (c2 f_a + c3 h_a)_i h_b[k] + c2 h_a[i] f_b[k] + c4 h_b[i] h_a[k]
-    double K[NN][3][3];
-#pragma unroll
-    for (int b = 0; b < NN; ++b)
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) K[b][i][k] = 0.0;
+  if constexpr (JAC) {
+    // Row block (a, :) of the element tangent, NB column nodes at a time in registers
+    // (K[j][i][k] = d r_(a,i) / d u_(b0+j,k)); NB = NN/2 keeps the kernel under 128 registers so that
+    // several CTAs share an SM and hide each other's global-load and phase-change latencies.
+    // The tangent is symmetric for every registered (hyperelastic) law: only the node-pair blocks
+    // (a, b >= a) are kept, packed as [pair(a,b)][i][k].  They are staged in the tail of the cell's own
+    // shared-memory area (free: the packed block list is shorter than X,U + records it overlays only after
+    // the warp is past phase 2) so that the global store is a coalesced copy of contiguous doubles.
+    constexpr int VV = VEC * VEC;
+    constexpr int NPAIR = L::NPAIR, P0 = L::P0;
+    constexpr int NB = pair_split<NN>();
+    static_assert((NPAIR - P0) * VV <= NQ * L::REC && (L::OFF_REC % 2) == 0, "output staging must fit the record zone");
 #pragma unroll 1
-    for (int q = 0; q < NQ; ++q) {
-      const double* rec = recs + q * L::REC;
-      const double* f = rec + L::OFF_X;
-      const double* h = f + NN * 3;
-      const double* cc = h + NN * 3;
-      const double c1 = cc[0], c2 = cc[1], c3 = cc[2], c4 = cc[3];
-      double ga[3], pa[3], qa[3], ra[3];
+    for (int b0 = 0; b0 < NN; b0 += NB) {
+      double K[NB][VEC][VEC];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const double fa = f[a * 3 + i], ha = h[a * 3 + i];
-        ga[i] = c1 * rec[L::OFF_G + a * 3 + i];
-        pa[i] = c2 * fa + c3 * ha;
-        qa[i] = c2 * ha;
-        ra[i] = c4 * ha;
-      }
+      for (int j = 0; j < NB; ++j)
 #pragma unroll
-      for (int b = 0; b < NN; ++b) {
-        double gb[3], fb[3], hb[3];
+        for (int i = 0; i < VEC; ++i)
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          gb[i] = rec[L::OFF_G + b * 3 + i];
-          fb[i] = f[b * 3 + i];
-          hb[i] = h[b * 3 + i];
-        }
-        const double dgg = ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2];
+          for (int k = 0; k < VEC; ++k) K[j][i][k] = 0.0;
+      if (active) {
+        if constexpr (LAW == FEM_LAW_POISSON) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+          for (int q = 0; q < NQ; ++q) {
+            const double* rec = recs + q * L::REC;
+            double ga[DIM];
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            double v = K[b][i][k];
-            v = fma(pa[i], hb[k], v);
-            v = fma(qa[i], fb[k], v);
-            v = fma(hb[i], ra[k], v);
-            K[b][i][k] = v;
+            for (int d = 0; d < DIM; ++d) ga[d] = rec[L::OFF_G + a * DIM + d] * rec[L::OFF_X];
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+#pragma unroll
+              for (int d = 0; d < DIM; ++d) K[j][0][0] = fma(ga[d], rec[L::OFF_G + (b0 + j) * DIM + d], K[j][0][0]);
           }
 #pragma unroll
-        for (int i = 0; i < 3; ++i) K[b][i][i] += dgg;
+          for (int j = 0; j < NB; ++j)
+#pragma unroll
+            for (int i = 1; i < VEC; ++i) K[j][i][i] = K[j][0][0];
+        } else if constexpr (LAW == FEM_LAW_LINEAR_ELASTIC || LAW == FEM_LAW_SIMP) {
+          // K_ab[i][k] = lam' G[i][k] + mu' G[k][i] + mu' tr(G) delta_ik,  G = sum_q E_q w_q g_a (x) g_b
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            const double* rec = recs + q * L::REC;
+            double ga[DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) ga[d] = rec[L::OFF_G + a * DIM + d] * rec[L::OFF_X];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+              double gb[DIM];
+#pragma unroll
+              for (int d = 0; d < DIM; ++d) gb[d] = rec[L::OFF_G + (b0 + j) * DIM + d];
+#pragma unroll
+              for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) K[j][i][k] = fma(ga[i], gb[k], K[j][i][k]);
+            }
+          }
+          const double nu = iso_nu<LAW>(A.p);
+          const double mu1 = 1.0 / (2.0 * (1.0 + nu)), lam1 = nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            double G[DIM][DIM];
+            double tr = 0.0;
+#pragma unroll
+            for (int i = 0; i < DIM; ++i) {
+              tr += K[j][i][i];
+#pragma unroll
+              for (int k = 0; k < DIM; ++k) G[i][k] = K[j][i][k];
+            }
+#pragma unroll
+            for (int i = 0; i < DIM; ++i)
+#pragma unroll
+              for (int k = 0; k < DIM; ++k) K[j][i][k] = lam1 * G[i][k] + mu1 * G[k][i] + (i == k ? mu1 * tr : 0.0);
+          }
+        } else {
+          // Neo-Hookean: K_ab[i][k] = c1 (g_a.g_b) d_ik + (c2 f_a + c3 h_a)_i h_b[k] + c2 h_a[i] f_b[k] + c4 h_b[i] h_a[k]
+#pragma unroll 1
+          for (int q = 0; q < NQ; ++q) {
+            const double* rec = recs + q * L::REC;
+            const double* f = rec + L::OFF_X;
+            const double* h = f + NN * 3;
+            const double* cc = h + NN * 3;
+            const double c1 = cc[0], c2 = cc[1], c3 = cc[2], c4 = cc[3];
+            double ga[3], pa[3], qa[3], ra[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const double fa = f[a * 3 + i], ha = h[a * 3 + i];
+              ga[i] = c1 * rec[L::OFF_G + a * 3 + i];
+              pa[i] = c2 * fa + c3 * ha;
+              qa[i] = c2 * ha;
+              ra[i] = c4 * ha;
+            }
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+              const int b = b0 + j;
+              double gb[3], fb[3], hb[3];
+#pragma unroll
+              for (int i = 0; i < 3; ++i) {
+                gb[i] = rec[L::OFF_G + b * 3 + i];
+                fb[i] = f[b * 3 + i];
+                hb[i] = h[b * 3 + i];
+              }
+              const double dgg = ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2];
+#pragma unroll
+              for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                  double v = K[j][i][k];
+                  v = fma(pa[i], hb[k], v);
+                  v = fma(qa[i], fb[k], v);
+                  v = fma(hb[i], ra[k], v);
+                  K[j][i][k] = v;
+                }
+#pragma unroll
+              for (int i = 0; i < 3; ++i) K[j][i][i] += dgg;
+            }
+          }
+        }
+      }
+      // second (or only) column half overwrites the record zone: every lane of the warp must be done reading it
+      if (b0 + NB >= NN) __syncwarp();
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const int b = b0 + j;
+          if (b >= a) {
+            const int pi = pair_index<NN>(a, b);
+            double* dst = cb + (pi < P0 ? pi * VV : L::OFF_REC + (pi - P0) * VV);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i)
+#pragma unroll
+              for (int k = 0; k < VEC; ++k) dst[i * VEC + k] = K[j][i][k];
+          }
+        }
       }
     }
-#pragma unroll
-    for (int b = 0; b < NN; ++b)
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) Krow[i * ND + b * 3 + k] = K[b][i][k];
+    __syncwarp();
+    constexpr int CPW = 32 / NN;                        // cells per warp
+    const int wl = threadIdx.x & 31;
+    const int lc0 = (threadIdx.x >> 5) * CPW;
+#pragma unroll 1
+    for (int j = 0; j < CPW; ++j) {
+      const int64_t cj = (int64_t)blockIdx.x * CPB + lc0 + j;
+      if (cj >= A.C) break;
+      const double* cellp = sm + L::TAB_SIZE + (lc0 + j) * L::CELL;
+      double* dstp = A.Ke + cj * (int64_t)(NPAIR * VV);
+      // two contiguous ranges: [0, P0*VV) from the head of the cell area, the rest from the record zone
+      if constexpr ((P0 * VV) % 2 == 0 && (NPAIR * VV) % 2 == 0 && L::CELL % 2 == 0 && L::TAB_SIZE % 2 == 0) {   // 16-byte aligned
+        for (int t = wl; t < NPAIR * VV / 2; t += 32) {
+          const int off = 2 * t < P0 * VV ? 2 * t : L::OFF_REC + (2 * t - P0 * VV);
+          reinterpret_cast<double2*>(dstp)[t] = *reinterpret_cast<const double2*>(cellp + off);
+        }
+      } else {
+        for (int t = wl; t < NPAIR * VV; t += 32) dstp[t] = cellp[t < P0 * VV ? t : L::OFF_REC + (t - P0 * VV)];
+      }
+    }
   }
 }
 
@@ -534,13 +580,13 @@ int dispatch(int ele, int vec, int law, const ElemArgs& A, cudaStream_t st) {
     if constexpr (GRAD) return launch_param_grad<NN, DIM, VEC, LAW, CPB>(A, st);  \
     else return launch_element<NN, DIM, VEC, LAW, CPB>(A, st);                    \
   }
-  FEM_CASE(FEM_ELE_HEX8, 8, 3, 1, FEM_LAW_POISSON, 32)
-  FEM_CASE(FEM_ELE_HEX8, 8, 3, 3, FEM_LAW_LINEAR_ELASTIC, 32)
-  FEM_CASE(FEM_ELE_HEX8, 8, 3, 3, FEM_LAW_SIMP, 32)
+  FEM_CASE(FEM_ELE_HEX8, 8, 3, 1, FEM_LAW_POISSON, 16)
+  FEM_CASE(FEM_ELE_HEX8, 8, 3, 3, FEM_LAW_LINEAR_ELASTIC, 16)
+  FEM_CASE(FEM_ELE_HEX8, 8, 3, 3, FEM_LAW_SIMP, 16)
   FEM_CASE(FEM_ELE_HEX8, 8, 3, 3, FEM_LAW_NEO_HOOKEAN, 16)
-  FEM_CASE(FEM_ELE_QUAD4, 4, 2, 1, FEM_LAW_POISSON, 64)
-  FEM_CASE(FEM_ELE_QUAD4, 4, 2, 2, FEM_LAW_LINEAR_ELASTIC, 64)
-  FEM_CASE(FEM_ELE_QUAD4, 4, 2, 2, FEM_LAW_SIMP, 64)
+  FEM_CASE(FEM_ELE_QUAD4, 4, 2, 1, FEM_LAW_POISSON, 32)
+  FEM_CASE(FEM_ELE_QUAD4, 4, 2, 2, FEM_LAW_LINEAR_ELASTIC, 32)
+  FEM_CASE(FEM_ELE_QUAD4, 4, 2, 2, FEM_LAW_SIMP, 32)
 #undef FEM_CASE
   set_error("unregistered (element=%d, vec=%d, law=%d) combination: no kernel, no fallback", ele, vec, law);
   return FEM_EINVAL;

@@ -30,49 +30,88 @@ int check_device() {
 
 namespace {
 
-// ---- get_A: one thread per node-block entry; fixed source order => bit-reproducible -----------
+// ---- get_A: deterministic segmented sum of the packed element tangents into CSR --------------------
+// One thread per SOURCE (cell, a, b) in the load phase: CTA b owns the block entries whose first source
+// lies in [kGatherItems*b, kGatherItems*(b+1)); every thread fetches one packed 3x3 block (plus the short
+// tail that belongs to the CTA's last entries) into shared memory, so ~256 independent 72-byte loads are
+// in flight per CTA and the dependency chain is  src code -> block -> shared  (no per-entry serial loop
+// over global memory).  Then one thread per block entry adds its sources from shared memory in ascending
+// source order (the same fixed order on every run => bit-reproducible, no atomics) and writes the VEC
+// scalar CSR rows of the entry; Dirichlet rows become unit rows (zeroRows, solver.py:527-528).
+constexpr int kGatherItems = 256;
+constexpr int kGatherTail = 64;     // max sources of one entry (checked when the plan is built)
+
 template <int VEC, int NN>
-__global__ void gather_csr_kernel(int64_t n_nodes, const int32_t* __restrict__ brow_ptr,
-                                  const int32_t* __restrict__ bcol, const int32_t* __restrict__ src_ptr,
-                                  const int32_t* __restrict__ src, const double* __restrict__ Ke,
-                                  const uint8_t* __restrict__ bc_flag, double* __restrict__ data) {
-  constexpr int ND = NN * VEC;
-  // one warp per node row-block; lanes stride over its entries
-  const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (n >= n_nodes) return;
-  const int lane = threadIdx.x & 31;
-  const int e0 = brow_ptr[n], e1 = brow_ptr[n + 1];
-  const int len = e1 - e0;
-  const int64_t row0 = (int64_t)VEC * VEC * e0;      // indptr[vec*n]
-  bool bc[VEC];
+__global__ void __launch_bounds__(kGatherItems) gather_csr_kernel(
+    int64_t n_items, const int32_t* __restrict__ blk_ent, const int32_t* __restrict__ src_ptr,
+    const int32_t* __restrict__ src, const int32_t* __restrict__ edst, const int32_t* __restrict__ einfo,
+    const double* __restrict__ Ke, double* __restrict__ data) {
+  constexpr int VV = VEC * VEC;
+  constexpr int NPAIR = NN * (NN + 1) / 2;
+  constexpr int STRIDE = (VV % 2) ? VV : VV + 1;           // odd stride: conflict-free shared rows
+  constexpr int MAXI = kGatherItems + kGatherTail;
+  __shared__ double sh[MAXI * STRIDE];
+  __shared__ int s_blk[MAXI];                               // packed block index, bit 31 = read transposed
+  __shared__ int s_beg[kGatherItems + 1];                   // first source (CTA-relative) of each entry
+  __shared__ int s_dst[kGatherItems], s_info[kGatherItems];
+  const int E0 = blk_ent[blockIdx.x], E1 = blk_ent[blockIdx.x + 1];
+  if (E0 >= E1) return;
+  const int nE = E1 - E0;
+  const int64_t P0 = (int64_t)blockIdx.x * kGatherItems;
+  const int nI = (int)(src_ptr[E1] - P0);                   // sources of the CTA incl. the tail of its last entries
+
+  // phase A: one source code per thread -> packed block index; one entry per thread -> its metadata
+  for (int t = threadIdx.x; t < nI; t += kGatherItems) {
+    const int code = src[P0 + t];
+    const int b = code % NN, a = (code / NN) % NN;
+    const int c = code / (NN * NN);
+    const int lo = a < b ? a : b, hi = a < b ? b : a;       // packed upper storage; lower blocks are transposes
+    s_blk[t] = (c * NPAIR + pair_index<NN>(lo, hi)) | (a > b ? (int)0x80000000 : 0);
+  }
+  if (threadIdx.x == 0) s_beg[nE] = nI;
+  if (threadIdx.x < nE) {
+    s_beg[threadIdx.x] = (int)(src_ptr[E0 + threadIdx.x] - P0);
+    s_dst[threadIdx.x] = edst[E0 + threadIdx.x];
+    s_info[threadIdx.x] = einfo[E0 + threadIdx.x];
+  }
+  __syncthreads();
+
+  // phase B: consecutive threads read consecutive words of a block (VV threads per 8*VV-byte block), so a warp
+  // request spans a few contiguous blocks instead of 32 scattered ones
+  constexpr int U = 6;                                      // independent 8-byte loads in flight per thread
+  for (int w0 = threadIdx.x; w0 < nI * VV; w0 += U * kGatherItems) {
+    double v[U];
+    int dst[U];
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) bc[i] = bc_flag ? bc_flag[n * VEC + i] != 0 : false;
-  for (int s = lane; s < len; s += 32) {
-    const int e = e0 + s;
-    double acc[VEC][VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i)
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) acc[i][k] = 0.0;
-    const int p0 = src_ptr[e], p1 = src_ptr[e + 1];
-    for (int p = p0; p < p1; ++p) {
-      const int code = src[p];
-      const int b = code % NN, a = (code / NN) % NN;
-      const int64_t c = code / (NN * NN);
-      const double* blk = Ke + c * (int64_t)(ND * ND) + (int64_t)(a * VEC) * ND + b * VEC;
-#pragma unroll
-      for (int i = 0; i < VEC; ++i)
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) acc[i][k] += blk[i * ND + k];
+    for (int u = 0; u < U; ++u) {
+      const int w = w0 + u * kGatherItems;
+      dst[u] = -1;
+      if (w < nI * VV) {
+        const int item = w / VV, word = w % VV;
+        const int info = s_blk[item];
+        const int64_t idx = info & 0x7fffffff;
+        dst[u] = item * STRIDE + ((info < 0) ? (word % VEC) * VEC + word / VEC : word);
+        v[u] = Ke[idx * VV + word];
+      }
     }
-    const bool diag_block = bcol[e] == n;
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      double* out = data + row0 + (int64_t)i * VEC * len + (int64_t)VEC * s;
-#pragma unroll
-      for (int k = 0; k < VEC; ++k)
-        out[k] = bc[i] ? ((diag_block && i == k) ? 1.0 : 0.0) : acc[i][k];       // zeroRows, solver.py:527-528
-    }
+    for (int u = 0; u < U; ++u)
+      if (dst[u] >= 0) sh[dst[u]] = v[u];
+  }
+  __syncthreads();
+
+  // phase C: one thread per output scalar, ordered (row i, entry, column k) so that consecutive threads write
+  // consecutive addresses of a CSR row; sources are added in ascending source order (bit-reproducible)
+  for (int w = threadIdx.x; w < nE * VV; w += kGatherItems) {
+    const int i = w / (VEC * nE), rem = w % (VEC * nE);
+    const int el = rem / VEC, k = rem % VEC;
+    double acc = 0.0;
+    for (int sidx = s_beg[el]; sidx < s_beg[el + 1]; ++sidx) acc += sh[sidx * STRIDE + i * VEC + k];
+    // einfo: bits 0..15 = VEC*len(row node), bit 16 = diagonal block, bits 17.. = Dirichlet flag of row i
+    const int info = s_info[el];
+    const bool bc = (info >> (17 + i)) & 1;
+    if (bc) acc = (((info >> 16) & 1) && i == k) ? 1.0 : 0.0;                  // zeroRows: unit diagonal
+    data[(int64_t)s_dst[el] + (int64_t)i * (info & 0xffff) + k] = acc;
   }
 }
 
@@ -211,21 +250,22 @@ extern "C" int fem_device_count(void) {
   return n;
 }
 
-extern "C" int fem_gather_csr(int vec, int nn, int64_t n_nodes, const int32_t* brow_ptr, const int32_t* bcol,
-                              const int32_t* src_ptr, const int32_t* src, const double* Ke,
-                              const uint8_t* bc_flag, double* data, void* stream) {
+extern "C" int fem_gather_csr(int vec, int nn, int64_t n_items, int64_t n_blocks, const int32_t* blk_ent,
+                              const int32_t* src_ptr, const int32_t* src, const int32_t* edst, const int32_t* einfo,
+                              const double* Ke, double* data, void* stream) {
   if (int e = check_device()) return e;
-  FEM_REQUIRE(brow_ptr && bcol && src_ptr && src && Ke && data, "null pointer");
-  if (n_nodes == 0) return FEM_OK;
+  FEM_REQUIRE(blk_ent && src_ptr && src && edst && einfo && Ke && data, "null pointer");
+  FEM_REQUIRE(n_blocks == (n_items + kGatherItems - 1) / kGatherItems, "n_blocks must be ceil(n_items / 256)");
+  if (n_items == 0) return FEM_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned grid = blocks_for(n_nodes, 8);
-#define FEM_G(V, N)                                                                                            \
-  if (vec == V && nn == N) {                                                                                   \
-    gather_csr_kernel<V, N><<<grid, 256, 0, st>>>(n_nodes, brow_ptr, bcol, src_ptr, src, Ke, bc_flag, data);   \
-    FEM_LAUNCH_CHECK();                                                                                        \
-    return FEM_OK;                                                                                             \
+#define FEM_G(V, N)                                                                                              \
+  if (vec == V && nn == N) {                                                                                     \
+    gather_csr_kernel<V, N><<<(unsigned)n_blocks, kGatherItems, 0, st>>>(n_items, blk_ent, src_ptr, src, edst,   \
+                                                                         einfo, Ke, data);                       \
+    FEM_LAUNCH_CHECK();                                                                                          \
+    return FEM_OK;                                                                                               \
   }
-  FEM_G(3, 8) FEM_G(1, 8) FEM_G(1, 4) FEM_G(2, 4) FEM_G(3, 27) FEM_G(1, 27)
+  FEM_G(3, 8) FEM_G(1, 8) FEM_G(1, 4) FEM_G(2, 4)
 #undef FEM_G
   set_error("fem_gather_csr: unregistered (vec=%d, nodes/cell=%d)", vec, nn);
   return FEM_EINVAL;

@@ -22,6 +22,15 @@ import torch
 INT32_MAX = 2 ** 31 - 1
 
 
+def packed_pairs(nn):
+    """(a, b) of every stored node-pair block, in the order of csrc/common.cuh::pair_index: for nn >= 8 the
+    pairs with b < nn/2 come first (the element kernel emits the row block in two column halves)."""
+    nb = nn // 2 if nn >= 8 else nn
+    first = [(a, b) for a in range(nb) for b in range(a, nb)] if nb != nn else []
+    rest = [(a, b) for a in range(nn) for b in range(max(a, nb if nb != nn else a), nn)]
+    return first + rest
+
+
 @dataclass
 class AssemblyPlan:
     num_nodes: int
@@ -36,7 +45,34 @@ class AssemblyPlan:
     nc: torch.Tensor
     indptr: torch.Tensor
     indices: torch.Tensor
+    blk_ent: torch.Tensor = None       # gather CTA b owns entries [blk_ent[b], blk_ent[b+1])
+    edst: torch.Tensor = None          # offset in CSR data of (row vec*n, col vec*m) per entry
+    erow: torch.Tensor = None          # row node of every entry (int32)
     _tperm: torch.Tensor = None
+
+    GATHER_ITEMS = 256                 # csrc/sparse.cu::kGatherItems
+    GATHER_TAIL = 64                   # csrc/sparse.cu::kGatherTail
+
+    @property
+    def n_items(self):
+        return int(self.src.numel())
+
+    @property
+    def n_gather_blocks(self):
+        return (self.n_items + self.GATHER_ITEMS - 1) // self.GATHER_ITEMS
+
+    def entry_info(self, bc_flag):
+        """einfo of fem_gather_csr: vec*len(n) | diag << 16 | Dirichlet flags of the entry's rows << 17."""
+        v = self.vec
+        lens = (self.brow_ptr[1:] - self.brow_ptr[:-1]).long()
+        erow = self.erow.long()
+        info = v * lens[erow]
+        info = info | ((self.bcol.long() == erow).long() << 16)
+        if bc_flag is not None:
+            f = bc_flag.long().reshape(self.num_nodes, v)
+            for i in range(v):
+                info = info | (f[erow, i] << (17 + i))
+        return info.to(torch.int32)
 
     @property
     def nnzb(self):
@@ -117,10 +153,26 @@ def build_plan(cells, num_nodes, vec):
     brow = torch.div(ukeys, num_nodes, rounding_mode='floor')
     bcol = (ukeys - brow * num_nodes).to(torch.int32)
     brow_ptr = _exclusive_ptr(torch.bincount(brow, minlength=num_nodes)).to(torch.int32)
-    del brow, ukeys
+    del ukeys
     flat = cells.reshape(-1)
     nc = torch.sort(flat, stable=True)[1].to(torch.int32)
     nc_ptr = _exclusive_ptr(torch.bincount(flat, minlength=num_nodes)).to(torch.int32)
     indptr, indices = expand_scalar_pattern(brow_ptr, bcol, vec)
-    return AssemblyPlan(num_nodes=num_nodes, num_cells=C, nodes_per_cell=N, vec=vec, brow_ptr=brow_ptr, bcol=bcol,
+    # gather work decomposition (csrc/sparse.cu::gather_csr_kernel)
+    max_src = int(counts.max()) if counts.numel() else 0
+    if max_src > AssemblyPlan.GATHER_TAIL:
+        raise ValueError(f"a node pair is shared by {max_src} cells (> {AssemblyPlan.GATHER_TAIL}): mesh valence too high")
+    n_items = int(src.numel())
+    n_blocks = (n_items + AssemblyPlan.GATHER_ITEMS - 1) // AssemblyPlan.GATHER_ITEMS
+    starts = torch.arange(n_blocks + 1, device=dev, dtype=torch.int64) * AssemblyPlan.GATHER_ITEMS
+    blk_ent = torch.searchsorted(src_ptr[:-1].long().contiguous(), starts).to(torch.int32)
+    lens = (brow_ptr[1:] - brow_ptr[:-1]).long()
+    erow = torch.repeat_interleave(torch.arange(num_nodes, device=dev), lens)
+    slot = torch.arange(bcol.numel(), device=dev) - brow_ptr[:-1].long()[erow]
+    edst = (vec * vec * brow_ptr[:-1].long()[erow] + vec * slot)
+    assert int(edst.max()) <= INT32_MAX if edst.numel() else True
+    edst = edst.to(torch.int32)
+    erow = erow.to(torch.int32)
+    del counts
+    return AssemblyPlan(blk_ent=blk_ent, edst=edst, erow=erow, num_nodes=num_nodes, num_cells=C, nodes_per_cell=N, vec=vec, brow_ptr=brow_ptr, bcol=bcol,
                         src_ptr=src_ptr, src=src, nc_ptr=nc_ptr, nc=nc, indptr=indptr, indices=indices)

@@ -26,7 +26,7 @@ import torch
 from . import _lib, laws, logger
 from .fe import FiniteElement, evaluate_point_fn
 from .generate_mesh import Mesh
-from .plan import build_plan
+from .plan import build_plan, packed_pairs
 
 
 def _device():
@@ -174,10 +174,16 @@ class Problem:
                 flag[rows] = 1
             rows = np.flatnonzero(flag).astype(np.int32)
             dev = self.device
-            self._bc_cache = (key, torch.from_numpy(rows).to(dev), torch.from_numpy(val[rows]).to(dev),
-                              torch.from_numpy(flag).to(dev),
-                              (fe.node_inds_list, fe.vec_inds_list, fe.vals_list))   # keep refs alive
+            flag_dev = torch.from_numpy(flag).to(dev)
+            self._bc_cache = (key, torch.from_numpy(rows).to(dev), torch.from_numpy(val[rows]).to(dev), flag_dev,
+                              (fe.node_inds_list, fe.vec_inds_list, fe.vals_list),   # keep refs alive
+                              self.plan.entry_info(flag_dev))
         return self._bc_cache[1], self._bc_cache[2], self._bc_cache[3]
+
+    def entry_info(self):
+        """Per-entry row stride / diagonal / Dirichlet bits consumed by the CSR gather kernel."""
+        self.bc_data()
+        return self._bc_cache[5]
 
     # ---- the hot path -----------------------------------------------------------------------------------
     def _internal_var(self):
@@ -205,9 +211,9 @@ class Problem:
 
     def _run_element_kernel(self, sol, jac):
         fe = self.fes[0]
-        ndof = fe.num_nodes * fe.vec
         if jac and self._Ke is None:
-            self._Ke = torch.empty((self.num_cells, ndof, ndof), dtype=torch.float64, device=self.device)
+            npair = fe.num_nodes * (fe.num_nodes + 1) // 2          # packed symmetric node-pair blocks (a, b >= a)
+            self._Ke = torch.empty((self.num_cells, npair, fe.vec, fe.vec), dtype=torch.float64, device=self.device)
         iv = self._internal_var()
         lib = _lib.load()
         _lib.check(lib.fem_element_residual_jacobian(
@@ -229,14 +235,26 @@ class Problem:
         return [self._run_element_kernel(self._as_sol(sol_list), jac=True)]
 
     # ---- reference attributes, materialised on demand ---------------------------------------------------
+    def element_tangents(self):
+        """Full (num_cells, ndof, ndof) element tangents, expanded from the packed symmetric storage."""
+        if self._Ke is None:
+            raise AttributeError("element tangents are defined after newton_update()")
+        fe = self.fes[0]
+        N, v = fe.num_nodes, fe.vec
+        pairs = torch.tensor(packed_pairs(N), device=self.device)
+        a, b = pairs[:, 0], pairs[:, 1]
+        full = torch.empty((self.num_cells, N, v, N, v), dtype=torch.float64, device=self.device)
+        full[:, b, :, a, :] = self._Ke.permute(1, 0, 3, 2)                     # mirror: K_ba = K_ab^T
+        full[:, a, :, b, :] = self._Ke.permute(1, 0, 2, 3)                     # stored blocks (a, b >= a) as computed
+        return full.reshape(self.num_cells, N * v, N * v)
+
     @property
     def V(self):
         """COO values aligned with I/J: cell blocks, then (zero) face blocks (problem.py:453-458)."""
-        if self._Ke is None:
-            raise AttributeError("V is defined after newton_update()")
-        ndof = self._Ke.shape[1]
+        Ke = self.element_tangents()
+        ndof = Ke.shape[1]
         nface = sum(len(b) for b in self.boundary_inds_list)
-        return torch.cat([self._Ke.reshape(-1), torch.zeros(nface * ndof * ndof, dtype=torch.float64, device=self.device)])
+        return torch.cat([Ke.reshape(-1), torch.zeros(nface * ndof * ndof, dtype=torch.float64, device=self.device)])
 
     def _coo(self):
         fe = self.fes[0]

@@ -122,11 +122,11 @@ def get_A(problem):
         raise RuntimeError("get_A() needs problem.newton_update(sol_list) first")
     p = problem.plan
     fe = problem.fes[0]
-    _, _, flag = problem.bc_data()
+    einfo = problem.entry_info()
     data = torch.empty(p.nnz, dtype=torch.float64, device=problem.device)
-    _lib.check(_lib.load().fem_gather_csr(fe.vec, fe.num_nodes, fe.num_total_nodes, _lib.ptr(p.brow_ptr),
-                                          _lib.ptr(p.bcol), _lib.ptr(p.src_ptr), _lib.ptr(p.src), _lib.ptr(problem._Ke),
-                                          _lib.ptr(flag), _lib.ptr(data), _lib.stream_ptr()))
+    _lib.check(_lib.load().fem_gather_csr(fe.vec, fe.num_nodes, p.n_items, p.n_gather_blocks, _lib.ptr(p.blk_ent),
+                                          _lib.ptr(p.src_ptr), _lib.ptr(p.src), _lib.ptr(p.edst), _lib.ptr(einfo),
+                                          _lib.ptr(problem._Ke), _lib.ptr(data), _lib.stream_ptr()))
     return CSRMatrix(p, data)
 
 
