@@ -54,33 +54,38 @@ int fem_device_count(void);
  *             (jax_fem/basis.py:141-175), device memory.
  * internal_var: (n_cells, NQ) per-quadrature-point parameter (problem.internal_vars[0],
  *             jax_fem/problem.py:125,493-556) or NULL.
- * Ke: (n_cells, NN(NN+1)/2, vec, vec): the node-pair blocks (a, b >= a) of the element tangent
- *     d r_(a,i) / d u_(b,k), pair index a*NN - a(a-1)/2 + (b-a).  The tangent of every registered law is
- *     symmetric, so the lower blocks are the transposes; expanding gives exactly the reference's
- *     problem.V cell blocks (problem.py:265,453).  NULL = residual only.
+ * Ke: (n_cells*NN, NN, vec, vec): for every corner (cell c, local node a) the row block
+ *     d r_(a,i) / d u_(b,k), b = 0..NN-1, stored at row-block position corner_pos[c*NN + a]
+ *     (corner_pos == NULL: c*NN + a, which is exactly the reference's problem.V cell blocks,
+ *     problem.py:265,453).  The assembly plan passes its node-sorted corner order so that all row blocks
+ *     of a mesh node are adjacent ("COO sorted by row").  Ke == NULL: residual only.
  * Re: (n_cells, ndof) element residuals (weak_form_flat, problem.py:443).
  */
 int fem_element_residual_jacobian(int ele_type, int vec, int law_id, const double* law_params_host,
                                   const double* points, const int32_t* cells, int64_t n_cells,
                                   const double* sol, const double* internal_var,
-                                  const double* ref_tables, double* Ke, double* Re, void* stream);
+                                  const double* ref_tables, const int32_t* corner_pos, double* Ke, double* Re,
+                                  void* stream);
 
 /* ---- (2) global assembly: _PetscTangentCache.update / get_A (jax_fem/solver.py:469-553)
  *      as a precomputed cell->CSR-slot permutation + deterministic segmented sum (no atomics).
  *
  * The node-block graph has one "entry" per (row node n, neighbour node m), rows ascending, columns
- * ascending.  src_ptr (nnzb+1) / src (n_items): for entry e the codes p = (c*NN + a)*NN + b of every
- * (cell, local row node, local col node) contributing to it, ascending in p (fixed summation order =>
- * bit-reproducible).  Ke is the packed output of fem_element_residual_jacobian.
- * blk_ent (n_blocks+1): first entry whose first source is >= 256*b (n_blocks = ceil(n_items/256)); no entry
- * may have more than 64 sources.
+ * ascending.  src_ptr (nnzb+1) / src (n_items): for entry e the Ke block index corner_pos[c*NN+a]*NN + b of
+ * every (cell, local row node, local col node) contributing to it, in ascending (c,a,b) order (fixed
+ * summation order => bit-reproducible).  Ke is the output of fem_element_residual_jacobian.
+ * gdesc (4*(n_blocks+1)): work split.  CTA b owns the nodes whose first corner (in node-sorted order) lies in
+ *              [32 b, 32 (b+1)); gdesc[4b..4b+2] = first corner, first entry, first source of CTA b (the next
+ *              CTA's triple closes the ranges).  No node may have more than 32 corners.
+ * eorder (nnzb): processing order of the entries inside each CTA (a permutation of the CTA's entry range, sorted by
+ *              descending source count so that the lanes of a warp loop equally long); results do not depend on it.
  * edst (nnzb): offset in `data` of element (row vec*n, col vec*m) of the scalar CSR pattern
  *              (indptr[vec*n+i] = vec*vec*brow_ptr[n] + i*vec*len(n)).
  * einfo (nnzb): bits 0..15 = vec*len(n) (distance between the entry's consecutive scalar rows), bit 16 = m == n,
  *              bit 17+i = row vec*n+i is a Dirichlet row -> row zeroed, unit diagonal, pattern kept
  *              (Mat.zeroRows with KEEP_NONZERO_PATTERN, solver.py:477,527-528).
  */
-int fem_gather_csr(int vec, int nn, int64_t n_items, int64_t n_blocks, const int32_t* blk_ent,
+int fem_gather_csr(int vec, int nn, int64_t n_blocks, const int32_t* gdesc, const int32_t* eorder,
                    const int32_t* src_ptr, const int32_t* src, const int32_t* edst, const int32_t* einfo,
                    const double* Ke, double* data, void* stream);
 

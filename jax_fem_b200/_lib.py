@@ -20,8 +20,8 @@ _SIGNATURES = {
     "fem_last_error": (ctypes.c_char_p, []),
     "fem_version": (_i, []),
     "fem_device_count": (_i, []),
-    "fem_element_residual_jacobian": (_i, [_i, _i, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "fem_gather_csr": (_i, [_i, _i, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fem_element_residual_jacobian": (_i, [_i, _i, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fem_gather_csr": (_i, [_i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fem_gather_residual": (_i, [_i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fem_apply_bc_vec": (_i, [_i64, _vp, _vp, _d, _vp, _vp, _vp]),
     "fem_bc_initial_guess": (_i, [_i64, _i64, _vp, _vp, _vp, _vp, _vp]),

@@ -32,23 +32,39 @@ int check_device();
 
 constexpr int kNumSM = 148;   // B200
 
-// Packed storage of the symmetric element tangent: node-pair blocks (a, b >= a).
-// For NN >= 8 the element kernel produces the row block in two column halves (b < NN/2, then b >= NN/2),
-// so the pairs of the first half are stored first: [a <= b < NB] then [b >= NB].  Mirrored by
-// jax_fem_b200/plan.py::pair_index.
+// The element kernels produce the row block of a corner in column chunks of pair_split<NN>() nodes.
 template <int NN>
 __host__ __device__ constexpr int pair_split() { return NN >= 8 ? NN / 2 : NN; }
-template <int NN>
-__host__ __device__ constexpr int pair_first_half() { return NN >= 8 ? (NN / 2) * (NN / 2 + 1) / 2 : 0; }
-template <int NN>
-__host__ __device__ __forceinline__ int pair_index(int a, int b) {   // requires a <= b
-  constexpr int NB = pair_split<NN>();
-  if (NB == NN) return a * NN - (a * (a - 1)) / 2 + (b - a);
-  constexpr int P0 = pair_first_half<NN>(), W = NN - NB;
-  if (b < NB) return a * NB - (a * (a - 1)) / 2 + (b - a);
-  if (a < NB) return P0 + a * W + (b - NB);
-  const int r = a - NB;
-  return P0 + NB * W + r * W - (r * (r - 1)) / 2 + (b - a);
+
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers -----------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy; dst/src 16-byte aligned, bytes a multiple of 16; completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -11,9 +11,8 @@
 //   phase 2: lane = local node a.  r_a = sum_q S_q g_a(q);  K row block (a, :) accumulated in
 //            registers from broadcast shared-memory reads of g_b(q) (all NN lanes of a cell read
 //            the same address), closed-form tangents -- no AD, no per-cell (24x24) temporaries.
-//   output : the tangent of every registered law is symmetric, so only the node-pair blocks
-//            (a, b >= a) are stored (NN(NN+1)/2 blocks of VEC x VEC), staged through shared memory
-//            and written with fully coalesced 16-byte stores.
+//   output : one contiguous row block (NN blocks of VEC x VEC) per corner (cell, a), placed at the
+//            corner's position in the plan's node-sorted order.
 #include "common.cuh"
 
 namespace femb200 {
@@ -77,12 +76,7 @@ struct Layout {
   static constexpr int REC = pad_odd(OFF_X + LawExtra<LAW, NN, DIM>::value);
   static constexpr int OFF_XN = 0;                          // X[NN][DIM] node coordinates
   static constexpr int OFF_UN = NN * DIM;                   // U[NN][VEC] nodal solution
-  // Output staging overlays the cell area: the first-half pair blocks go to [0, STAGE_A) (X,U are dead after
-  // phase 1), the remaining blocks to the record zone once the whole warp is past phase 2.
-  static constexpr int NPAIR = NN * (NN + 1) / 2;
-  static constexpr int P0 = pair_first_half<NN>();
-  static constexpr int STAGE_A = (P0 * VEC * VEC + 1) / 2 * 2;
-  static constexpr int OFF_REC = (NN * DIM + NN * VEC > STAGE_A) ? NN * DIM + NN * VEC : STAGE_A;
+  static constexpr int OFF_REC = NN * DIM + NN * VEC;
   static constexpr int CELL_RAW = OFF_REC + NQ * REC;
   // cell stride == 8 (mod 16) doubles: the two cells of a half-warp hit disjoint bank sets
   static constexpr int CELL = CELL_RAW + ((8 - CELL_RAW % 16) + 16) % 16;
@@ -95,6 +89,7 @@ struct ElemArgs {
   const double* iv;      // (C, NQ) or nullptr
   const double* lam;     // adjoint vector (nodes, vec) for the parameter-gradient kernel
   const double* ref;     // [NQ*NN*DIM] dN, [NQ] w
+  const int32_t* corner_pos;   // (C*NN) output row-block position of corner (c,a); nullptr = c*NN + a
   double* Ke;
   double* Re;
   double* grad;          // (C, NQ)
@@ -324,14 +319,13 @@ __global__ void __launch_bounds__(CPB* NN, (LAW == FEM_LAW_NEO_HOOKEAN ? 2 : 512
     // Row block (a, :) of the element tangent, NB column nodes at a time in registers
     // (K[j][i][k] = d r_(a,i) / d u_(b0+j,k)); NB = NN/2 keeps the kernel under 128 registers so that
     // several CTAs share an SM and hide each other's global-load and phase-change latencies.
-    // The tangent is symmetric for every registered (hyperelastic) law: only the node-pair blocks
-    // (a, b >= a) are kept, packed as [pair(a,b)][i][k].  They are staged in the tail of the cell's own
-    // shared-memory area (free: the packed block list is shorter than X,U + records it overlays only after
-    // the warp is past phase 2) so that the global store is a coalesced copy of contiguous doubles.
+    // Output: the row block of corner (c,a) is NN*VEC*VEC contiguous doubles at position corner_pos[c*NN+a];
+    // with corner_pos = the node-sorted corner order of the plan, all row blocks of a mesh node are adjacent
+    // in memory ("COO sorted by row"), which is what the CSR gather streams.
     constexpr int VV = VEC * VEC;
-    constexpr int NPAIR = L::NPAIR, P0 = L::P0;
     constexpr int NB = pair_split<NN>();
-    static_assert((NPAIR - P0) * VV <= NQ * L::REC && (L::OFF_REC % 2) == 0, "output staging must fit the record zone");
+    const int64_t opos = active ? (A.corner_pos ? (int64_t)A.corner_pos[c * NN + a] : c * NN + a) : 0;
+    double* orow = A.Ke + opos * (int64_t)(NN * VV);
 #pragma unroll 1
     for (int b0 = 0; b0 < NN; b0 += NB) {
       double K[NB][VEC][VEC];
@@ -439,41 +433,19 @@ __global__ void __launch_bounds__(CPB* NN, (LAW == FEM_LAW_NEO_HOOKEAN ? 2 : 512
           }
         }
       }
-      // second (or only) column half overwrites the record zone: every lane of the warp must be done reading it
-      if (b0 + NB >= NN) __syncwarp();
       if (active) {
+        double* dst = orow + b0 * VV;
+        if constexpr ((NB * VV) % 2 == 0 && (NN * VV) % 2 == 0) {          // 16-byte aligned pieces
 #pragma unroll
-        for (int j = 0; j < NB; ++j) {
-          const int b = b0 + j;
-          if (b >= a) {
-            const int pi = pair_index<NN>(a, b);
-            double* dst = cb + (pi < P0 ? pi * VV : L::OFF_REC + (pi - P0) * VV);
-#pragma unroll
-            for (int i = 0; i < VEC; ++i)
-#pragma unroll
-              for (int k = 0; k < VEC; ++k) dst[i * VEC + k] = K[j][i][k];
+          for (int t = 0; t < NB * VV / 2; ++t) {
+            const int e0 = 2 * t, e1 = 2 * t + 1;
+            reinterpret_cast<double2*>(dst)[t] =
+                make_double2(K[e0 / VV][(e0 % VV) / VEC][e0 % VEC], K[e1 / VV][(e1 % VV) / VEC][e1 % VEC]);
           }
+        } else {
+#pragma unroll
+          for (int t = 0; t < NB * VV; ++t) dst[t] = K[t / VV][(t % VV) / VEC][t % VEC];
         }
-      }
-    }
-    __syncwarp();
-    constexpr int CPW = 32 / NN;                        // cells per warp
-    const int wl = threadIdx.x & 31;
-    const int lc0 = (threadIdx.x >> 5) * CPW;
-#pragma unroll 1
-    for (int j = 0; j < CPW; ++j) {
-      const int64_t cj = (int64_t)blockIdx.x * CPB + lc0 + j;
-      if (cj >= A.C) break;
-      const double* cellp = sm + L::TAB_SIZE + (lc0 + j) * L::CELL;
-      double* dstp = A.Ke + cj * (int64_t)(NPAIR * VV);
-      // two contiguous ranges: [0, P0*VV) from the head of the cell area, the rest from the record zone
-      if constexpr ((P0 * VV) % 2 == 0 && (NPAIR * VV) % 2 == 0 && L::CELL % 2 == 0 && L::TAB_SIZE % 2 == 0) {   // 16-byte aligned
-        for (int t = wl; t < NPAIR * VV / 2; t += 32) {
-          const int off = 2 * t < P0 * VV ? 2 * t : L::OFF_REC + (2 * t - P0 * VV);
-          reinterpret_cast<double2*>(dstp)[t] = *reinterpret_cast<const double2*>(cellp + off);
-        }
-      } else {
-        for (int t = wl; t < NPAIR * VV; t += 32) dstp[t] = cellp[t < P0 * VV ? t : L::OFF_REC + (t - P0 * VV)];
       }
     }
   }
@@ -600,7 +572,8 @@ using namespace femb200;
 extern "C" int fem_element_residual_jacobian(int ele_type, int vec, int law_id, const double* law_params_host,
                                              const double* points, const int32_t* cells, int64_t n_cells,
                                              const double* sol, const double* internal_var,
-                                             const double* ref_tables, double* Ke, double* Re, void* stream) {
+                                             const double* ref_tables, const int32_t* corner_pos, double* Ke, double* Re,
+                                             void* stream) {
   if (int e = check_device()) return e;
   FEM_REQUIRE(points && cells && sol && ref_tables && Re && law_params_host, "null pointer");
   FEM_REQUIRE(n_cells >= 0, "n_cells < 0");
@@ -608,7 +581,7 @@ extern "C" int fem_element_residual_jacobian(int ele_type, int vec, int law_id, 
   if (n_cells == 0) return FEM_OK;
   ElemArgs A{};
   A.points = points; A.cells = cells; A.sol = sol; A.iv = internal_var; A.ref = ref_tables;
-  A.Ke = Ke; A.Re = Re; A.C = n_cells;
+  A.Ke = Ke; A.Re = Re; A.C = n_cells; A.corner_pos = corner_pos;
   for (int i = 0; i < 8; ++i) A.p[i] = law_params_host[i];
   return dispatch<false>(ele_type, vec, law_id, A, (cudaStream_t)stream);
 }

@@ -30,89 +30,104 @@ int check_device() {
 
 namespace {
 
-// ---- get_A: deterministic segmented sum of the packed element tangents into CSR --------------------
-// One thread per SOURCE (cell, a, b) in the load phase: CTA b owns the block entries whose first source
-// lies in [kGatherItems*b, kGatherItems*(b+1)); every thread fetches one packed 3x3 block (plus the short
-// tail that belongs to the CTA's last entries) into shared memory, so ~256 independent 72-byte loads are
-// in flight per CTA and the dependency chain is  src code -> block -> shared  (no per-entry serial loop
-// over global memory).  Then one thread per block entry adds its sources from shared memory in ascending
-// source order (the same fixed order on every run => bit-reproducible, no atomics) and writes the VEC
-// scalar CSR rows of the entry; Dirichlet rows become unit rows (zeroRows, solver.py:527-528).
-constexpr int kGatherItems = 256;
-constexpr int kGatherTail = 64;     // max sources of one entry (checked when the plan is built)
+// ---- get_A: deterministic segmented sum of the element row blocks into CSR -------------------------
+// The element kernel stores the row block of every corner (cell, a) in node-sorted order, so the row
+// blocks of a mesh node are one contiguous segment ("COO sorted by row").  CTA b owns the nodes whose
+// first corner lies in [kGatherCorners*b, kGatherCorners*(b+1)):
+//   phase A: its segment is brought into shared memory by ONE TMA bulk copy (cp.async.bulk + mbarrier: no
+//            registers, no indirection, the whole segment in flight at once) while the threads fetch the
+//            per-source block offsets and the per-entry metadata;
+//   phase B: one thread per output scalar, ordered (row i, entry, column k) so that consecutive threads
+//            write consecutive addresses of a CSR row; the sources of an entry are added in ascending
+//            (cell, a, b) order -- the same fixed order on every run => bit-reproducible, no atomics.
+// Dirichlet rows become unit rows with the pattern kept (zeroRows, solver.py:527-528).
+constexpr int kGatherThreads = 256;
+constexpr int kGatherCorners = 32;      // corners per CTA (4 interior HEX8 nodes)
+constexpr int kGatherTail = 32;         // max corners of one node (checked when the plan is built)
 
 template <int VEC, int NN>
-__global__ void __launch_bounds__(kGatherItems) gather_csr_kernel(
-    int64_t n_items, const int32_t* __restrict__ blk_ent, const int32_t* __restrict__ src_ptr,
+__global__ void __launch_bounds__(kGatherThreads) gather_csr_kernel(
+    const int32_t* __restrict__ gdesc, const int32_t* __restrict__ eorder, const int32_t* __restrict__ src_ptr,
     const int32_t* __restrict__ src, const int32_t* __restrict__ edst, const int32_t* __restrict__ einfo,
     const double* __restrict__ Ke, double* __restrict__ data) {
   constexpr int VV = VEC * VEC;
-  constexpr int NPAIR = NN * (NN + 1) / 2;
-  constexpr int STRIDE = (VV % 2) ? VV : VV + 1;           // odd stride: conflict-free shared rows
-  constexpr int MAXI = kGatherItems + kGatherTail;
-  __shared__ double sh[MAXI * STRIDE];
-  __shared__ int s_blk[MAXI];                               // packed block index, bit 31 = read transposed
-  __shared__ int s_beg[kGatherItems + 1];                   // first source (CTA-relative) of each entry
-  __shared__ int s_dst[kGatherItems], s_info[kGatherItems];
-  const int E0 = blk_ent[blockIdx.x], E1 = blk_ent[blockIdx.x + 1];
-  if (E0 >= E1) return;
-  const int nE = E1 - E0;
-  const int64_t P0 = (int64_t)blockIdx.x * kGatherItems;
-  const int nI = (int)(src_ptr[E1] - P0);                   // sources of the CTA incl. the tail of its last entries
+  constexpr int ROW = NN * VV;                                    // doubles per corner row block
+  constexpr int MAXC = kGatherCorners + kGatherTail;
+  constexpr int MAXS = MAXC * NN;                                 // sources (blocks) of the CTA
+  constexpr int EPT = (MAXS + kGatherThreads - 1) / kGatherThreads;   // entries per thread (worst case)
+  static_assert(ROW % 2 == 0, "row blocks must be 16-byte multiples");
+  __shared__ __align__(128) double sh[MAXC * ROW];
+  __shared__ int s_off[MAXS];                                     // block offset (in blocks) inside sh
+  __shared__ __align__(8) uint64_t bar;
+  // descriptor: first corner / entry / source of this CTA and of the next one
+  const int C0 = gdesc[blockIdx.x * 4 + 0], C1 = gdesc[blockIdx.x * 4 + 4];
+  const int E0 = gdesc[blockIdx.x * 4 + 1], E1 = gdesc[blockIdx.x * 4 + 5];
+  const int S0 = gdesc[blockIdx.x * 4 + 2], S1 = gdesc[blockIdx.x * 4 + 6];
+  if (C0 >= C1) return;
+  const int nE = E1 - E0, nS = S1 - S0;
 
-  // phase A: one source code per thread -> packed block index; one entry per thread -> its metadata
-  for (int t = threadIdx.x; t < nI; t += kGatherItems) {
-    const int code = src[P0 + t];
-    const int b = code % NN, a = (code / NN) % NN;
-    const int c = code / (NN * NN);
-    const int lo = a < b ? a : b, hi = a < b ? b : a;       // packed upper storage; lower blocks are transposes
-    s_blk[t] = (c * NPAIR + pair_index<NN>(lo, hi)) | (a > b ? (int)0x80000000 : 0);
+  // phase A: the CTA's segment of row blocks is one contiguous, 16-byte aligned range: a single TMA bulk copy
+  // (cp.async.bulk) brings it in while the threads fetch the source offsets and their entries' metadata
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = (uint32_t)(C1 - C0) * ROW * sizeof(double);
+    mbar_expect_tx(&bar, bytes);
+    bulk_g2s(sh, Ke + (int64_t)C0 * ROW, bytes, &bar);
   }
-  if (threadIdx.x == 0) s_beg[nE] = nI;
-  if (threadIdx.x < nE) {
-    s_beg[threadIdx.x] = (int)(src_ptr[E0 + threadIdx.x] - P0);
-    s_dst[threadIdx.x] = edst[E0 + threadIdx.x];
-    s_info[threadIdx.x] = einfo[E0 + threadIdx.x];
+  for (int t = threadIdx.x; t < nS; t += kGatherThreads) s_off[t] = src[S0 + t] - C0 * NN;
+  // each thread owns up to EPT entries, taken in the plan's balanced order (entries of a CTA sorted by source
+  // count, so the lanes of a warp loop over the same number of sources)
+  int sb[EPT], se[EPT], dst[EPT], info[EPT];
+#pragma unroll
+  for (int r = 0; r < EPT; ++r) {
+    const int t = threadIdx.x + r * kGatherThreads;
+    sb[r] = se[r] = 0;
+    dst[r] = -1;
+    info[r] = 0;
+    if (t < nE) {
+      const int e = eorder[E0 + t];
+      sb[r] = src_ptr[e] - S0;
+      se[r] = src_ptr[e + 1] - S0;
+      dst[r] = edst[e] - VV * E0;
+      info[r] = einfo[e];
+    }
+  }
+  __syncthreads();
+  mbar_wait(&bar, 0);
+
+  // phase B: per entry, add its sources in ascending (cell, a, b) order -- fixed order => bit-reproducible
+  double res[EPT][VV];
+#pragma unroll
+  for (int r = 0; r < EPT; ++r) {
+#pragma unroll
+    for (int j = 0; j < VV; ++j) res[r][j] = 0.0;
+    for (int sidx = sb[r]; sidx < se[r]; ++sidx) {
+      const double* blk = sh + s_off[sidx] * VV;
+#pragma unroll
+      for (int j = 0; j < VV; ++j) res[r][j] += blk[j];
+    }
   }
   __syncthreads();
 
-  // phase B: consecutive threads read consecutive words of a block (VV threads per 8*VV-byte block), so a warp
-  // request spans a few contiguous blocks instead of 32 scattered ones
-  constexpr int U = 6;                                      // independent 8-byte loads in flight per thread
-  for (int w0 = threadIdx.x; w0 < nI * VV; w0 += U * kGatherItems) {
-    double v[U];
-    int dst[U];
+  // phase C: results -> shared memory in CSR order (the CTA's rows are one contiguous range of `data`), then a
+  // coalesced copy.  einfo: bits 0..15 = VEC*len(row node), bit 16 = diagonal block, bits 17.. = Dirichlet rows.
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int w = w0 + u * kGatherItems;
-      dst[u] = -1;
-      if (w < nI * VV) {
-        const int item = w / VV, word = w % VV;
-        const int info = s_blk[item];
-        const int64_t idx = info & 0x7fffffff;
-        dst[u] = item * STRIDE + ((info < 0) ? (word % VEC) * VEC + word / VEC : word);
-        v[u] = Ke[idx * VV + word];
+  for (int r = 0; r < EPT; ++r) {
+    if (dst[r] >= 0) {
+      const int rowlen = info[r] & 0xffff;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const bool bc = (info[r] >> (17 + i)) & 1;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+          sh[dst[r] + i * rowlen + k] = bc ? ((((info[r] >> 16) & 1) && i == k) ? 1.0 : 0.0) : res[r][i * VEC + k];
       }
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (dst[u] >= 0) sh[dst[u]] = v[u];
   }
   __syncthreads();
-
-  // phase C: one thread per output scalar, ordered (row i, entry, column k) so that consecutive threads write
-  // consecutive addresses of a CSR row; sources are added in ascending source order (bit-reproducible)
-  for (int w = threadIdx.x; w < nE * VV; w += kGatherItems) {
-    const int i = w / (VEC * nE), rem = w % (VEC * nE);
-    const int el = rem / VEC, k = rem % VEC;
-    double acc = 0.0;
-    for (int sidx = s_beg[el]; sidx < s_beg[el + 1]; ++sidx) acc += sh[sidx * STRIDE + i * VEC + k];
-    // einfo: bits 0..15 = VEC*len(row node), bit 16 = diagonal block, bits 17.. = Dirichlet flag of row i
-    const int info = s_info[el];
-    const bool bc = (info >> (17 + i)) & 1;
-    if (bc) acc = (((info >> 16) & 1) && i == k) ? 1.0 : 0.0;                  // zeroRows: unit diagonal
-    data[(int64_t)s_dst[el] + (int64_t)i * (info & 0xffff) + k] = acc;
-  }
+  double* __restrict__ out = data + (int64_t)VV * E0;
+  for (int t = threadIdx.x; t < nE * VV; t += kGatherThreads) out[t] = sh[t];
 }
 
 template <int VEC, int NN>
@@ -250,20 +265,18 @@ extern "C" int fem_device_count(void) {
   return n;
 }
 
-extern "C" int fem_gather_csr(int vec, int nn, int64_t n_items, int64_t n_blocks, const int32_t* blk_ent,
+extern "C" int fem_gather_csr(int vec, int nn, int64_t n_blocks, const int32_t* gdesc, const int32_t* eorder,
                               const int32_t* src_ptr, const int32_t* src, const int32_t* edst, const int32_t* einfo,
                               const double* Ke, double* data, void* stream) {
   if (int e = check_device()) return e;
-  FEM_REQUIRE(blk_ent && src_ptr && src && edst && einfo && Ke && data, "null pointer");
-  FEM_REQUIRE(n_blocks == (n_items + kGatherItems - 1) / kGatherItems, "n_blocks must be ceil(n_items / 256)");
-  if (n_items == 0) return FEM_OK;
+  FEM_REQUIRE(gdesc && eorder && src_ptr && src && edst && einfo && Ke && data, "null pointer");
+  if (n_blocks == 0) return FEM_OK;
   cudaStream_t st = (cudaStream_t)stream;
-#define FEM_G(V, N)                                                                                              \
-  if (vec == V && nn == N) {                                                                                     \
-    gather_csr_kernel<V, N><<<(unsigned)n_blocks, kGatherItems, 0, st>>>(n_items, blk_ent, src_ptr, src, edst,   \
-                                                                         einfo, Ke, data);                       \
-    FEM_LAUNCH_CHECK();                                                                                          \
-    return FEM_OK;                                                                                               \
+#define FEM_G(V, N)                                                                                                  \
+  if (vec == V && nn == N) {                                                                                         \
+    gather_csr_kernel<V, N><<<(unsigned)n_blocks, kGatherThreads, 0, st>>>(gdesc, eorder, src_ptr, src, edst, einfo, Ke, data); \
+    FEM_LAUNCH_CHECK();                                                                                              \
+    return FEM_OK;                                                                                                   \
   }
   FEM_G(3, 8) FEM_G(1, 8) FEM_G(1, 4) FEM_G(2, 4)
 #undef FEM_G

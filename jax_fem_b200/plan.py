@@ -6,8 +6,11 @@ integers twice (37-74 GB at 200^3); here only the node-block graph is built:
 
     brow_ptr, bcol : CSR of the node adjacency (node m is a neighbour of n iff they share a cell),
                      columns ascending;
-    src_ptr, src   : for every node-block entry the (cell, a, b) triples contributing to it,
-                     coded p = (c*N + a)*N + b, ascending (fixed summation order);
+    src_ptr, src   : for every node-block entry the element blocks contributing to it, as indices
+                     corner_pos[c*N + a]*N + b into the element-tangent buffer, in ascending (c, a, b)
+                     order (fixed summation order);
+    corner_pos     : where the element kernel stores the row block of corner (c, a): the node-sorted
+                     corner order, so that all row blocks of one mesh node are adjacent in memory;
     nc_ptr, nc     : for every node the (cell, a) corners touching it, coded c*N + a, ascending;
     indptr, indices: the scalar CSR pattern PETSc would produce from (I, J): every (I, J) pair is
                      kept (explicit zeros included), columns ascending, int32.
@@ -20,15 +23,6 @@ from dataclasses import dataclass
 import torch
 
 INT32_MAX = 2 ** 31 - 1
-
-
-def packed_pairs(nn):
-    """(a, b) of every stored node-pair block, in the order of csrc/common.cuh::pair_index: for nn >= 8 the
-    pairs with b < nn/2 come first (the element kernel emits the row block in two column halves)."""
-    nb = nn // 2 if nn >= 8 else nn
-    first = [(a, b) for a in range(nb) for b in range(a, nb)] if nb != nn else []
-    rest = [(a, b) for a in range(nn) for b in range(max(a, nb if nb != nn else a), nn)]
-    return first + rest
 
 
 @dataclass
@@ -45,13 +39,15 @@ class AssemblyPlan:
     nc: torch.Tensor
     indptr: torch.Tensor
     indices: torch.Tensor
-    blk_ent: torch.Tensor = None       # gather CTA b owns entries [blk_ent[b], blk_ent[b+1])
+    corner_pos: torch.Tensor = None    # (C*N,) position of corner (c,a) in the node-sorted order (inverse of nc)
+    gdesc: torch.Tensor = None         # gather work split: (first corner, first entry, first source, 0) per CTA
+    eorder: torch.Tensor = None        # entries of every gather CTA sorted by descending source count
     edst: torch.Tensor = None          # offset in CSR data of (row vec*n, col vec*m) per entry
     erow: torch.Tensor = None          # row node of every entry (int32)
     _tperm: torch.Tensor = None
 
-    GATHER_ITEMS = 256                 # csrc/sparse.cu::kGatherItems
-    GATHER_TAIL = 64                   # csrc/sparse.cu::kGatherTail
+    GATHER_CORNERS = 32                # csrc/sparse.cu::kGatherCorners
+    GATHER_TAIL = 32                   # csrc/sparse.cu::kGatherTail
 
     @property
     def n_items(self):
@@ -59,7 +55,7 @@ class AssemblyPlan:
 
     @property
     def n_gather_blocks(self):
-        return (self.n_items + self.GATHER_ITEMS - 1) // self.GATHER_ITEMS
+        return int(self.gdesc.numel()) // 4 - 1
 
     def entry_info(self, bc_flag):
         """einfo of fem_gather_csr: vec*len(n) | diag << 16 | Dirichlet flags of the entry's rows << 17."""
@@ -147,7 +143,7 @@ def build_plan(cells, num_nodes, vec):
     del keys
     ukeys, counts = torch.unique_consecutive(skeys, return_counts=True)
     del skeys
-    src = order.to(torch.int32)
+    codes = order                      # (c*N + a)*N + b of every source, grouped by entry, ascending inside
     del order
     src_ptr = _exclusive_ptr(counts).to(torch.int32)
     brow = torch.div(ukeys, num_nodes, rounding_mode='floor')
@@ -155,17 +151,34 @@ def build_plan(cells, num_nodes, vec):
     brow_ptr = _exclusive_ptr(torch.bincount(brow, minlength=num_nodes)).to(torch.int32)
     del ukeys
     flat = cells.reshape(-1)
-    nc = torch.sort(flat, stable=True)[1].to(torch.int32)
+    nc64 = torch.sort(flat, stable=True)[1]
+    nc = nc64.to(torch.int32)
     nc_ptr = _exclusive_ptr(torch.bincount(flat, minlength=num_nodes)).to(torch.int32)
+    # element row blocks are stored in node-sorted corner order: corner (c,a) -> corner_pos[c*N + a]
+    corner_pos64 = torch.empty_like(nc64)
+    corner_pos64[nc64] = torch.arange(nc64.numel(), device=dev)
+    corner_pos = corner_pos64.to(torch.int32)
+    # src: index of the VEC x VEC block of every source inside the element-tangent buffer
+    src = (corner_pos64[torch.div(codes, N, rounding_mode='floor')] * N + codes % N).to(torch.int32)
+    del codes, nc64, corner_pos64
     indptr, indices = expand_scalar_pattern(brow_ptr, bcol, vec)
-    # gather work decomposition (csrc/sparse.cu::gather_csr_kernel)
-    max_src = int(counts.max()) if counts.numel() else 0
-    if max_src > AssemblyPlan.GATHER_TAIL:
-        raise ValueError(f"a node pair is shared by {max_src} cells (> {AssemblyPlan.GATHER_TAIL}): mesh valence too high")
-    n_items = int(src.numel())
-    n_blocks = (n_items + AssemblyPlan.GATHER_ITEMS - 1) // AssemblyPlan.GATHER_ITEMS
-    starts = torch.arange(n_blocks + 1, device=dev, dtype=torch.int64) * AssemblyPlan.GATHER_ITEMS
-    blk_ent = torch.searchsorted(src_ptr[:-1].long().contiguous(), starts).to(torch.int32)
+    # gather work decomposition (csrc/sparse.cu::gather_csr_kernel): CTA b owns the nodes whose first corner is in
+    # [32 b, 32 (b+1)); their corners / entries / sources are contiguous ranges
+    deg = nc_ptr[1:] - nc_ptr[:-1]
+    if deg.numel() and int(deg.max()) > AssemblyPlan.GATHER_TAIL:
+        raise ValueError(f"a node belongs to {int(deg.max())} cells (> {AssemblyPlan.GATHER_TAIL}): mesh valence too high")
+    n_corners = int(nc.numel())
+    n_blocks = (n_corners + AssemblyPlan.GATHER_CORNERS - 1) // AssemblyPlan.GATHER_CORNERS
+    starts = torch.arange(n_blocks + 1, device=dev, dtype=torch.int64) * AssemblyPlan.GATHER_CORNERS
+    node0 = torch.searchsorted(nc_ptr[:-1].long().contiguous(), starts)            # first node of every CTA
+    ent0 = brow_ptr.long()[node0]
+    gdesc = torch.stack([nc_ptr.long()[node0], ent0, src_ptr.long()[ent0], torch.zeros_like(ent0)], dim=1)
+    gdesc = gdesc.reshape(-1).to(torch.int32)
+    # balanced processing order: inside a CTA, entries sorted by descending source count (stable)
+    cta_of_entry = torch.searchsorted(ent0[1:].contiguous(), torch.arange(bcol.numel(), device=dev), right=True)
+    key = cta_of_entry * (AssemblyPlan.GATHER_TAIL * 4) + (AssemblyPlan.GATHER_TAIL * 4 - 1 - counts)
+    eorder = torch.sort(key, stable=True)[1].to(torch.int32)
+    del cta_of_entry, key
     lens = (brow_ptr[1:] - brow_ptr[:-1]).long()
     erow = torch.repeat_interleave(torch.arange(num_nodes, device=dev), lens)
     slot = torch.arange(bcol.numel(), device=dev) - brow_ptr[:-1].long()[erow]
@@ -174,5 +187,5 @@ def build_plan(cells, num_nodes, vec):
     edst = edst.to(torch.int32)
     erow = erow.to(torch.int32)
     del counts
-    return AssemblyPlan(blk_ent=blk_ent, edst=edst, erow=erow, num_nodes=num_nodes, num_cells=C, nodes_per_cell=N, vec=vec, brow_ptr=brow_ptr, bcol=bcol,
+    return AssemblyPlan(corner_pos=corner_pos, gdesc=gdesc, eorder=eorder, edst=edst, erow=erow, num_nodes=num_nodes, num_cells=C, nodes_per_cell=N, vec=vec, brow_ptr=brow_ptr, bcol=bcol,
                         src_ptr=src_ptr, src=src, nc_ptr=nc_ptr, nc=nc, indptr=indptr, indices=indices)

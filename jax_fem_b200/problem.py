@@ -26,7 +26,7 @@ import torch
 from . import _lib, laws, logger
 from .fe import FiniteElement, evaluate_point_fn
 from .generate_mesh import Mesh
-from .plan import build_plan, packed_pairs
+from .plan import build_plan
 
 
 def _device():
@@ -212,14 +212,16 @@ class Problem:
     def _run_element_kernel(self, sol, jac):
         fe = self.fes[0]
         if jac and self._Ke is None:
-            npair = fe.num_nodes * (fe.num_nodes + 1) // 2          # packed symmetric node-pair blocks (a, b >= a)
-            self._Ke = torch.empty((self.num_cells, npair, fe.vec, fe.vec), dtype=torch.float64, device=self.device)
+            # one (N, vec, vec) row block per corner (cell, a), stored in the plan's node-sorted corner order
+            self._Ke = torch.empty((self.num_cells * fe.num_nodes, fe.num_nodes, fe.vec, fe.vec),
+                                   dtype=torch.float64, device=self.device)
         iv = self._internal_var()
         lib = _lib.load()
         _lib.check(lib.fem_element_residual_jacobian(
             _lib.ELE[self.ele_type], fe.vec, self._law.law_id, _lib.host_doubles(self._law.params()),
             _lib.ptr(self._points), _lib.ptr(self._cells), self.num_cells, _lib.ptr(sol), _lib.ptr(iv),
-            _lib.ptr(self._ref), _lib.ptr(self._Ke) if jac else None, _lib.ptr(self._Re), _lib.stream_ptr()))
+            _lib.ptr(self._ref), _lib.ptr(self.plan.corner_pos), _lib.ptr(self._Ke) if jac else None,
+            _lib.ptr(self._Re), _lib.stream_ptr()))
         res = torch.empty((fe.num_total_nodes, fe.vec), dtype=torch.float64, device=self.device)
         p = self.plan
         _lib.check(lib.fem_gather_residual(fe.vec, fe.num_nodes, fe.num_total_nodes, _lib.ptr(p.nc_ptr), _lib.ptr(p.nc),
@@ -236,17 +238,13 @@ class Problem:
 
     # ---- reference attributes, materialised on demand ---------------------------------------------------
     def element_tangents(self):
-        """Full (num_cells, ndof, ndof) element tangents, expanded from the packed symmetric storage."""
+        """(num_cells, ndof, ndof) element tangents in the reference's layout (row = test dof)."""
         if self._Ke is None:
             raise AttributeError("element tangents are defined after newton_update()")
         fe = self.fes[0]
         N, v = fe.num_nodes, fe.vec
-        pairs = torch.tensor(packed_pairs(N), device=self.device)
-        a, b = pairs[:, 0], pairs[:, 1]
-        full = torch.empty((self.num_cells, N, v, N, v), dtype=torch.float64, device=self.device)
-        full[:, b, :, a, :] = self._Ke.permute(1, 0, 3, 2)                     # mirror: K_ba = K_ab^T
-        full[:, a, :, b, :] = self._Ke.permute(1, 0, 2, 3)                     # stored blocks (a, b >= a) as computed
-        return full.reshape(self.num_cells, N * v, N * v)
+        rows = self._Ke[self.plan.corner_pos.long()]                             # (C*N, N, v, v) in (c, a) order
+        return rows.reshape(self.num_cells, N, N, v, v).permute(0, 1, 3, 2, 4).reshape(self.num_cells, N * v, N * v)
 
     @property
     def V(self):

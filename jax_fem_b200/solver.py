@@ -124,7 +124,7 @@ def get_A(problem):
     fe = problem.fes[0]
     einfo = problem.entry_info()
     data = torch.empty(p.nnz, dtype=torch.float64, device=problem.device)
-    _lib.check(_lib.load().fem_gather_csr(fe.vec, fe.num_nodes, p.n_items, p.n_gather_blocks, _lib.ptr(p.blk_ent),
+    _lib.check(_lib.load().fem_gather_csr(fe.vec, fe.num_nodes, p.n_gather_blocks, _lib.ptr(p.gdesc), _lib.ptr(p.eorder),
                                           _lib.ptr(p.src_ptr), _lib.ptr(p.src), _lib.ptr(p.edst), _lib.ptr(einfo),
                                           _lib.ptr(problem._Ke), _lib.ptr(data), _lib.stream_ptr()))
     return CSRMatrix(p, data)

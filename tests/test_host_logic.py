@@ -45,14 +45,41 @@ def test_plan_pattern_bit_exact(N, vec):
     indptr, indices = fem.csr_pattern_from_cells(cells, vec, vec * len(m.points))
     assert plan.indptr.dtype == torch.int32 and plan.indices.dtype == torch.int32
     assert np.array_equal(plan.indptr.numpy(), indptr) and np.array_equal(plan.indices.numpy(), indices)
-    # source lists: every (cell, a, b) appears exactly once and lands in the right block
+    # source lists: every element block (corner position, b) appears exactly once and lands in the right entry
     src = plan.src.numpy().astype(np.int64)
     assert np.array_equal(np.sort(src), np.arange(cells.shape[0] * 64))
-    c, a, b = src // 64, (src // 8) % 8, src % 8
+    cpos = plan.corner_pos.numpy()
+    assert np.array_equal(np.sort(cpos), np.arange(cells.size))
+    corner_of_pos = np.argsort(cpos)                       # position -> c*8 + a
+    corner, b = corner_of_pos[src // 8], src % 8
+    c, a = corner // 8, corner % 8
     counts = np.diff(plan.src_ptr.numpy())
     brow = np.repeat(np.arange(len(m.points)), np.diff(plan.brow_ptr.numpy()))
     assert np.array_equal(np.repeat(brow, counts), cells[c, a])
     assert np.array_equal(np.repeat(plan.bcol.numpy(), counts), cells[c, b])
+    code = (c * 8 + a) * 8 + b                             # fixed summation order: ascending (c, a, b) inside an entry
+    seg = np.repeat(np.arange(len(counts)), counts)
+    assert np.all((np.diff(code) > 0) | (np.diff(seg) > 0))
+    assert np.array_equal(cells.reshape(-1)[corner_of_pos], np.sort(cells.reshape(-1)))   # node-sorted corners
+    # gather work split: CTA b owns the nodes whose first corner lies in [32 b, 32 (b+1))
+    gd = plan.gdesc.numpy().reshape(-1, 4)
+    ncp, sp, bp = plan.nc_ptr.numpy(), plan.src_ptr.numpy(), plan.brow_ptr.numpy()
+    assert len(gd) == plan.n_gather_blocks + 1 and gd[0, 0] == 0 and gd[-1, 0] == cells.size
+    assert gd[-1, 1] == plan.nnzb and gd[-1, 2] == plan.n_items
+    node0 = np.searchsorted(ncp[:-1], 32 * np.arange(len(gd)))
+    assert np.array_equal(gd[:, 0], ncp[node0]) and np.array_equal(gd[:, 1], bp[node0])
+    assert np.array_equal(gd[:, 2], sp[bp[node0]])
+    assert np.all(np.diff(gd[:, 0]) <= 64) and np.all(np.diff(gd[:, 0]) >= 0)
+    ed, erow = plan.edst.numpy(), plan.erow.numpy()
+    assert np.array_equal(erow, brow)
+    assert np.array_equal(plan.indices.numpy()[ed], vec * plan.bcol.numpy())
+    assert np.all((plan.indptr.numpy()[vec * erow] <= ed) & (ed < plan.indptr.numpy()[vec * erow + 1]))
+    flag = torch.zeros(plan.n, dtype=torch.uint8)
+    flag[vec * 5 + (vec - 1)] = 1
+    info = plan.entry_info(flag).numpy()
+    assert np.array_equal(info & 0xffff, vec * np.diff(plan.brow_ptr.numpy())[erow])
+    assert np.array_equal((info >> 16) & 1, (plan.bcol.numpy() == erow).astype(np.int32))
+    assert np.array_equal(info >> 17, np.where(erow == 5, 1 << (vec - 1), 0))
     # transpose permutation is an involution mapping (n,m) -> (m,n)
     t = plan.tperm.numpy()
     assert np.array_equal(t[t], np.arange(len(t)))
