@@ -77,7 +77,14 @@ struct Layout {
   static constexpr int OFF_XN = 0;                          // X[NN][DIM] node coordinates
   static constexpr int OFF_UN = NN * DIM;                   // U[NN][VEC] nodal solution
   static constexpr int OFF_REC = NN * DIM + NN * VEC;
-  static constexpr int CELL_RAW = OFF_REC + NQ * REC;
+  // Output staging: the row block is produced in HALVES column chunks of NB nodes.  The last chunk overlays
+  // the head of the cell area (dead once the warp is past phase 2); with two chunks the first one needs its
+  // own zone because the records are still live while the second chunk is computed.
+  static constexpr int NB = pair_split<NN>();
+  static constexpr int HALVES = NN / NB;
+  static constexpr int CHUNK = NN * NB * VEC * VEC;          // doubles of one column chunk of a cell (all rows)
+  static constexpr int OFF_STAGE = ((OFF_REC + NQ * REC + 1) / 2) * 2;
+  static constexpr int CELL_RAW = OFF_STAGE + (HALVES == 2 ? CHUNK : 0);
   // cell stride == 8 (mod 16) doubles: the two cells of a half-warp hit disjoint bank sets
   static constexpr int CELL = CELL_RAW + ((8 - CELL_RAW % 16) + 16) % 16;
 };
@@ -203,7 +210,7 @@ __device__ __forceinline__ void nh_stress(const NHPoint& k, double kappa, double
 
 // ---- the element kernel ----------------------------------------------------------------------------
 template <int NN, int DIM, int VEC, int LAW, int CPB, bool JAC>
-__global__ void __launch_bounds__(CPB* NN, (LAW == FEM_LAW_NEO_HOOKEAN ? 2 : 512 / (CPB * NN))) element_kernel(const ElemArgs A) {
+__global__ void __launch_bounds__(CPB* NN, (LAW == FEM_LAW_NEO_HOOKEAN ? 256 / (CPB * NN) : 512 / (CPB * NN))) element_kernel(const ElemArgs A) {
   using L = Layout<NN, DIM, VEC, LAW>;
   constexpr int NQ = L::NQ, ND = L::ND;
   extern __shared__ __align__(16) double sm[];
@@ -323,9 +330,9 @@ __global__ void __launch_bounds__(CPB* NN, (LAW == FEM_LAW_NEO_HOOKEAN ? 2 : 512
     // with corner_pos = the node-sorted corner order of the plan, all row blocks of a mesh node are adjacent
     // in memory ("COO sorted by row"), which is what the CSR gather streams.
     constexpr int VV = VEC * VEC;
-    constexpr int NB = pair_split<NN>();
-    const int64_t opos = active ? (A.corner_pos ? (int64_t)A.corner_pos[c * NN + a] : c * NN + a) : 0;
-    double* orow = A.Ke + opos * (int64_t)(NN * VV);
+    constexpr int NB = L::NB, HALVES = L::HALVES;
+    static_assert(L::CHUNK <= L::OFF_STAGE && (NB * VV) % 2 == 0, "output staging layout");
+    const int opos = active ? (A.corner_pos ? A.corner_pos[c * NN + a] : (int)(c * NN + a)) : 0;
 #pragma unroll 1
     for (int b0 = 0; b0 < NN; b0 += NB) {
       double K[NB][VEC][VEC];
@@ -433,18 +440,40 @@ __global__ void __launch_bounds__(CPB* NN, (LAW == FEM_LAW_NEO_HOOKEAN ? 2 : 512
           }
         }
       }
+      // stage this column chunk in shared memory: [row a][NB blocks][VEC][VEC]
+      const bool last = (b0 + NB >= NN);
+      if (last) __syncwarp();                        // every lane of the warp is done reading X,U and the records
       if (active) {
-        double* dst = orow + b0 * VV;
-        if constexpr ((NB * VV) % 2 == 0 && (NN * VV) % 2 == 0) {          // 16-byte aligned pieces
+        double* dst = cb + ((HALVES == 2 && !last) ? L::OFF_STAGE : 0) + a * (NB * VV);
 #pragma unroll
-          for (int t = 0; t < NB * VV / 2; ++t) {
-            const int e0 = 2 * t, e1 = 2 * t + 1;
-            reinterpret_cast<double2*>(dst)[t] =
-                make_double2(K[e0 / VV][(e0 % VV) / VEC][e0 % VEC], K[e1 / VV][(e1 % VV) / VEC][e1 % VEC]);
-          }
-        } else {
+        for (int t = 0; t < NB * VV / 2; ++t) {
+          const int e0 = 2 * t, e1 = 2 * t + 1;
+          reinterpret_cast<double2*>(dst)[t] =
+              make_double2(K[e0 / VV][(e0 % VV) / VEC][e0 % VEC], K[e1 / VV][(e1 % VV) / VEC][e1 % VEC]);
+        }
+      }
+    }
+    __syncwarp();
+    // coalesced copy-out: per cell, NN rows x HALVES chunks of NB*VV contiguous doubles each; the row block of
+    // corner (c, a) goes to position corner_pos[c*NN + a] (held by lane a of the cell -> warp shuffle)
+    constexpr int CPW = 32 / NN;                        // cells per warp
+    constexpr int P2 = NB * VV / 2;                     // double2 pieces of one (row, chunk)
+    const int wl = threadIdx.x & 31;
+    const int lc0 = (threadIdx.x >> 5) * CPW;
+#pragma unroll 1
+    for (int j = 0; j < CPW; ++j) {
+      const int64_t cj = (int64_t)blockIdx.x * CPB + lc0 + j;
+      const bool live = cj < A.C;                       // warp-uniform
+      const double* cellp = sm + L::TAB_SIZE + (lc0 + j) * L::CELL;
 #pragma unroll
-          for (int t = 0; t < NB * VV; ++t) dst[t] = K[t / VV][(t % VV) / VEC][t % VEC];
+      for (int it = 0; it < (NN * HALVES * P2 + 31) / 32; ++it) {
+        const int p = it * 32 + wl;
+        const int row = (p / P2) / HALVES, h = (p / P2) % HALVES, w2 = p % P2;
+        const int pos = __shfl_sync(0xffffffffu, opos, (j * NN + row) & 31);
+        if (live && p < NN * HALVES * P2) {
+          const double* srcp = cellp + ((HALVES == 2 && h == 0) ? L::OFF_STAGE : 0) + row * (NB * VV);
+          double* dstp = A.Ke + (int64_t)pos * (NN * VV) + h * (NB * VV);
+          reinterpret_cast<double2*>(dstp)[w2] = reinterpret_cast<const double2*>(srcp)[w2];
         }
       }
     }
@@ -553,9 +582,9 @@ int dispatch(int ele, int vec, int law, const ElemArgs& A, cudaStream_t st) {
     else return launch_element<NN, DIM, VEC, LAW, CPB>(A, st);                    \
   }
   FEM_CASE(FEM_ELE_HEX8, 8, 3, 1, FEM_LAW_POISSON, 16)
-  FEM_CASE(FEM_ELE_HEX8, 8, 3, 3, FEM_LAW_LINEAR_ELASTIC, 16)
-  FEM_CASE(FEM_ELE_HEX8, 8, 3, 3, FEM_LAW_SIMP, 16)
-  FEM_CASE(FEM_ELE_HEX8, 8, 3, 3, FEM_LAW_NEO_HOOKEAN, 16)
+  FEM_CASE(FEM_ELE_HEX8, 8, 3, 3, FEM_LAW_LINEAR_ELASTIC, 8)
+  FEM_CASE(FEM_ELE_HEX8, 8, 3, 3, FEM_LAW_SIMP, 8)
+  FEM_CASE(FEM_ELE_HEX8, 8, 3, 3, FEM_LAW_NEO_HOOKEAN, 8)
   FEM_CASE(FEM_ELE_QUAD4, 4, 2, 1, FEM_LAW_POISSON, 32)
   FEM_CASE(FEM_ELE_QUAD4, 4, 2, 2, FEM_LAW_LINEAR_ELASTIC, 32)
   FEM_CASE(FEM_ELE_QUAD4, 4, 2, 2, FEM_LAW_SIMP, 32)
