@@ -76,7 +76,7 @@ int fem_element_residual_jacobian(int ele_type, int vec, int law_id, const doubl
  * summation order => bit-reproducible).  Ke is the output of fem_element_residual_jacobian.
  * gdesc (4*(n_blocks+1)): work split.  CTA b owns the nodes whose first corner (in node-sorted order) lies in
  *              [32 b, 32 (b+1)); gdesc[4b..4b+2] = first corner, first entry, first source of CTA b (the next
- *              CTA's triple closes the ranges).  No node may have more than 32 corners.
+ *              CTA's triple closes the ranges).  No node may have more than 16 corners.
  * eorder (nnzb): processing order of the entries inside each CTA (a permutation of the CTA's entry range, sorted by
  *              descending source count so that the lanes of a warp loop equally long); results do not depend on it.
  * edst (nnzb): offset in `data` of element (row vec*n, col vec*m) of the scalar CSR pattern

@@ -41,9 +41,9 @@ namespace {
 //            write consecutive addresses of a CSR row; the sources of an entry are added in ascending
 //            (cell, a, b) order -- the same fixed order on every run => bit-reproducible, no atomics.
 // Dirichlet rows become unit rows with the pattern kept (zeroRows, solver.py:527-528).
-constexpr int kGatherThreads = 256;
+constexpr int kGatherThreads = 128;
 constexpr int kGatherCorners = 32;      // corners per CTA (4 interior HEX8 nodes)
-constexpr int kGatherTail = 32;         // max corners of one node (checked when the plan is built)
+constexpr int kGatherTail = 16;         // max corners of one node (checked when the plan is built)
 
 template <int VEC, int NN>
 __global__ void __launch_bounds__(kGatherThreads) gather_csr_kernel(

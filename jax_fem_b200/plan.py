@@ -47,7 +47,7 @@ class AssemblyPlan:
     _tperm: torch.Tensor = None
 
     GATHER_CORNERS = 32                # csrc/sparse.cu::kGatherCorners
-    GATHER_TAIL = 32                   # csrc/sparse.cu::kGatherTail
+    GATHER_TAIL = 16                   # csrc/sparse.cu::kGatherTail
 
     @property
     def n_items(self):
