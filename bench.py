@@ -173,7 +173,7 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------
-def build_problem(size, law="elastic"):
+def problem_class():
     import jax_fem_b200 as jf
     from jax_fem_b200 import laws
 
@@ -184,12 +184,23 @@ def build_problem(size, law="elastic"):
         def get_surface_maps(self):
             return [lambda u, x: np.array([0., 0., 100.])]
 
-    m = jf.box_mesh(size, size, size, 1., 1., 1.)
-    mesh = jf.Mesh(m.points, m.cells_dict['hexahedron'])
+    return Elasticity
+
+
+def build_problem(size, world=1, comm=None):
+    """cfg 2 on one GPU; for N GPUs the box is N times longer in x (weak scaling: size^3 cells per rank) and its
+    cells are sharded in x-slabs with one ghost layer (jax_fem_b200/distributed.py).  Returns (problem, sharded)."""
+    import jax_fem_b200 as jf
+    Lx = float(world)
+    m = jf.box_mesh(size * world, size, size, Lx, 1., 1.)
     left = lambda p: np.isclose(p[0], 0., atol=1e-5)
-    right = lambda p: np.isclose(p[0], 1., atol=1e-5)
-    bc = [[left] * 3, [0, 1, 2], [lambda p: 0.] * 3]
-    return Elasticity(mesh, vec=3, dim=3, dirichlet_bc_info=bc, location_fns=[right])
+    right = lambda p: np.isclose(p[0], Lx, atol=1e-5)
+    kw = dict(dirichlet_bc_info=[[left] * 3, [0, 1, 2], [lambda p: 0.] * 3], location_fns=[right])
+    if world == 1:
+        return problem_class()(jf.Mesh(m.points, m.cells_dict['hexahedron']), vec=3, dim=3, **kw), None
+    from jax_fem_b200.distributed import ShardedProblem
+    sp = ShardedProblem(problem_class(), m.points, m.cells_dict['hexahedron'], comm, vec=3, dim=3, **kw)
+    return sp.problem, sp
 
 
 def main():
@@ -225,17 +236,23 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     t0 = time.perf_counter()
-    log(f"building problem {args.size}^3")
-    prob = build_problem(args.size)
+    log(f"building problem {args.size}^3 per GPU, {world} GPU(s)")
+    comm = None
+    if world > 1:
+        from jax_fem_b200.distributed import TorchDistComm
+        comm = TorchDistComm()
+    prob, sharded = build_problem(args.size, world, comm)
     setup_s = time.perf_counter() - t0
-    log(f"problem built in {setup_s:.1f}s: {prob.num_total_dofs_all_vars} dofs, nnz {prob.plan.nnz}")
     fe = prob.fes[0]
-    n, nnz = prob.num_total_dofs_all_vars, prob.plan.nnz
-    b_asm, b_spmv = algorithmic_bytes(n, nnz, prob.num_cells, fe.num_total_nodes)
+    n_local, nnz = prob.num_total_dofs_all_vars, prob.plan.nnz
+    n = sharded.n_owned if sharded else n_local               # dofs this rank owns (what it is credited for)
+    log(f"problem built in {setup_s:.1f}s: {n} owned dofs (+{n_local - n} ghost), local nnz {prob.plan.nnz}")
+    own_frac = n / n_local
+    b_asm, b_spmv = algorithmic_bytes(n, int(nnz * own_frac), int(prob.num_cells * own_frac), int(fe.num_total_nodes * own_frac))
     rng = np.random.default_rng(rank)
     sol_host = torch.from_numpy(1e-3 * rng.standard_normal((fe.num_total_nodes, 3))).pin_memory()
     sol = sol_host.to(dev)
-    res_host = torch.empty(n, dtype=torch.float64).pin_memory()
+    res_host = torch.empty(n_local, dtype=torch.float64).pin_memory()
 
     def step(sol_dev):
         res = prob.newton_update([sol_dev])[0]
@@ -287,48 +304,67 @@ def main():
     e2e_ms = e0.elapsed_time(e1) / args.steps
     log(f"assembly {ms_step:.3f} ms/step (element {t_elem:.3f}, bc {t_bc:.3f}, gather {t_gather:.3f}); e2e {e2e_ms:.3f} ms")
 
-    # ---- SpMV (the CG kernel) on the assembled matrix -----------------------------------------------------
-    x = torch.from_numpy(np.random.default_rng(0).standard_normal(n)).to(dev)
+    # ---- SpMV (the CG kernel) on the assembled matrix; with N > 1 it includes the halo exchange of x ---------
+    x = torch.from_numpy(np.random.default_rng(0).standard_normal(n_local)).to(dev)
     y = torch.empty_like(x)
+    lib = _lib.load()
+    indptr, indices, data = A.getValuesCSR()
+    ws = torch.zeros(lib.fem_krylov_workspace(n_local), dtype=torch.float64, device=dev)
+
+    def spmv():
+        if sharded:
+            sharded.halo.update(x)
+        _lib.check(lib.fem_dcg_spmv_dot(n, n_local, _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(data), _lib.ptr(x),
+                                        _lib.ptr(y), 0, _lib.ptr(ws), _lib.stream_ptr()))
     for _ in range(3):
-        A.mult(x, y)
+        spmv()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 20
-    torch.cuda.synchronize()
+    barrier()
     s0.record()
     for _ in range(reps):
-        A.mult(x, y)
+        spmv()
     s1.record()
-    torch.cuda.synchronize()
+    barrier()
     spmv_ms = s0.elapsed_time(s1) / reps
-    log(f"spmv {spmv_ms:.3f} ms = {b_spmv / spmv_ms / 1e6:.0f} GB/s")
+    log(f"spmv {spmv_ms:.3f} ms = {b_spmv / spmv_ms / 1e6:.0f} GB/s per GPU")
 
     solve = None
     if args.solve:
-        dofs = torch.zeros(n, dtype=torch.float64, device=dev)
-        r0 = jf.apply_bc_vec(prob.newton_update([dofs.reshape(-1, 3)])[0].reshape(-1), dofs, prob)
-        A0 = jf.get_A(prob)
-        torch.cuda.synchronize()
+        dofs = torch.zeros(n_local, dtype=torch.float64, device=dev)
+        barrier()
         c0 = time.perf_counter()
-        _, info = jax_solve(A0, -r0, torch.zeros_like(dofs), True, method='cg', return_info=True)
-        torch.cuda.synchronize()
+        if sharded:
+            sharded.solve_linear()
+            info = dict(sharded.last_info, err=None)
+        else:
+            r0 = jf.apply_bc_vec(prob.newton_update([dofs.reshape(-1, 3)])[0].reshape(-1), dofs, prob)
+            A0 = jf.get_A(prob)
+            torch.cuda.synchronize()
+            c0 = time.perf_counter()
+            _, info = jax_solve(A0, -r0, torch.zeros_like(dofs), True, method='cg', return_info=True)
+        barrier()
         cs = time.perf_counter() - c0
         log(f"cg: {info}, {cs:.2f}s")
-        solve = {"method": "jacobi-cg", "iterations": info['iterations'], "seconds": cs, "err": info['err'],
+        solve = {"method": "jacobi-cg" + (" (sharded: halo + 2 all-reduces per iteration; time includes one assembly)" if sharded else ""),
+                 "iterations": info['iterations'], "seconds": cs, "err": info.get('err'),
                  "ms_per_iteration": 1e3 * cs / max(info['iterations'], 1),
-                 "effective_spmv_gbs": b_spmv / (cs / max(info['iterations'], 1)) / 1e9}
+                 "effective_spmv_gbs": world * b_spmv / (cs / max(info['iterations'], 1)) / 1e9}
     clocks = sampler.stop() if rank == 0 else None
 
     # max over ranks (device times)
     t = torch.tensor([ms_step, e2e_ms, spmv_ms, t_elem, t_gather, t_bc], dtype=torch.float64, device=dev)
+    n_total = torch.tensor([float(n)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n_total, op=dist.ReduceOp.SUM)
+    n_total = int(n_total.item())
     ms_step, e2e_ms, spmv_ms, t_elem, t_gather, t_bc = [float(v) for v in t.tolist()]
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
         hbm = float(peaks["hbm_gbs"])
-        value = world * n / (ms_step * 1e-3)
+        value = n_total / (ms_step * 1e-3)
         asm_kernel_ms = t_elem + t_gather + t_bc
         achieved = b_asm / (asm_kernel_ms * 1e-3) / 1e9
         spmv_gbs = b_spmv / (spmv_ms * 1e-3) / 1e9
@@ -336,8 +372,11 @@ def main():
             "metric": "assembled DOFs/s (residual+Jacobian), HEX8 linear elasticity", "value": value, "unit": "DOF/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"HEX8 box {args.size}^3 linear elasticity E=70e3 nu=0.3, u=0 on x=0, traction on x=1 (cfg 2)",
-                       "n_dofs": n, "nnz": nnz, "cells": prob.num_cells, "per_gpu": "one full mesh per rank (replicas)",
+            "config": {"workload": f"HEX8 box {args.size * world}x{args.size}x{args.size} linear elasticity E=70e3 nu=0.3, u=0 on x=0, "
+                                   f"traction on x=Lx (cfg 2{'' if world == 1 else ' extended in x: weak scaling'})",
+                       "n_dofs_total": n_total, "n_dofs_per_gpu": n, "nnz_per_gpu": int(nnz * own_frac), "cells_per_gpu": int(prob.num_cells * own_frac),
+                       "per_gpu": "whole mesh" if world == 1 else f"x-slab of {args.size}^3 cells + 1 ghost cell layer per interface; "
+                                  "assembly needs no communication; SpMV = halo send/recv with <= 2 neighbours; Krylov dots = all-reduce",
                        "l2": "inputs larger than L2 (element matrices + CSR >> 126 MB), no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": None, "peak_source": peak_src,
@@ -345,10 +384,10 @@ def main():
                          "algorithmic_bytes": b_asm, "kernel_ms": asm_kernel_ms,
                          "kernels_ms": {"element_kernel+gather_residual": t_elem, "apply_bc_vec": t_bc, "gather_csr": t_gather}},
             "roofline_spmv": {"bound": "hbm", "achieved": spmv_gbs, "peak": hbm, "unit": "GB/s", "frac": spmv_gbs / hbm,
-                              "algorithmic_bytes": b_spmv, "kernel_ms": spmv_ms, "kernel": "spmv_kernel (CSR, 8 lanes/row)"},
-            "e2e": {"value": world * n / (e2e_ms * 1e-3), "unit": "DOF/s", "h2d_bytes_per_step": n * 8,
-                    "d2h_bytes_per_step": n * 8, "ms_per_step": e2e_ms},
-            "gpu_launches": args.steps * 4, "clocks": clocks, "setup_s": setup_s,
+                              "algorithmic_bytes": b_spmv, "kernel_ms": spmv_ms, "kernel": "spmv_fused_kernel<8,0> (CSR, 8 lanes/row)" + (" + halo exchange" if world > 1 else "")},
+            "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": "DOF/s", "h2d_bytes_per_step": n_local * 8,
+                    "d2h_bytes_per_step": n_local * 8, "ms_per_step": e2e_ms},
+            "gpu_launches": args.steps * 4 * world, "clocks": clocks, "setup_s": setup_s,
         }
         if solve:
             line["cg_solve"] = solve

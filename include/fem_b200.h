@@ -129,6 +129,24 @@ int fem_pbicgstab(int64_t n, const int32_t* indptr, const int32_t* indices, cons
                   const double* diag, const double* b, double* x, double tol, double atol, int maxiter,
                   int check_every, double* workspace, double* info_host, void* stream);
 
+/* ---- (e) multi-GPU: one rank's share of the Jacobi-CG above (cells sharded across ranks).
+ *      Vectors hold the rank's owned dofs first, then its ghosts.  Every kernel leaves rank-local partial sums in
+ *      workspace[16..20); the caller all-reduces that slice (ncclAllReduce on the same stream) and exchanges the
+ *      ghost entries of p (ncclSend/ncclRecv) between the steps:
+ *        begin -> spmv_dot(x0, with_dot=0) -> init -> [allreduce] -> scalars(0)
+ *        loop:  [halo p] -> spmv_dot(p, 1) -> [allreduce] -> update -> [allreduce] -> direction -> scalars(1)
+ *      workspace[7] != 0 once converged (same stopping rule as fem_pcg); workspace[6] = iterations.            */
+int fem_dcg_begin(double* workspace, double tol, double atol, int maxiter, void* stream);
+int fem_dcg_spmv_dot(int64_t n_owned, int64_t n_local, const int32_t* indptr, const int32_t* indices,
+                     const double* data, const double* p, double* q, int with_dot, double* workspace, void* stream);
+int fem_dcg_init(int64_t n_owned, int64_t n_local, const double* b, const double* diag, const double* q,
+                 double* r, double* p, double* workspace, void* stream);
+int fem_dcg_scalars(int phase, double* workspace, void* stream);
+int fem_dcg_update(int64_t n_owned, int64_t n_local, const double* diag, const double* p, const double* q,
+                   double* x, double* r, double* workspace, void* stream);
+int fem_dcg_direction(int64_t n_owned, const double* diag, const double* r, double* p, double* workspace,
+                      void* stream);
+
 /* ---- (4) implicit adjoint: -lambda^T dc/dtheta per quadrature point
  *      (jax_fem/solver.py:1386-1394,1414-1416) for per-quad parameters; lambda must already be
  *      zero on Dirichlet rows (BC rows of c do not depend on theta).  grad: (n_cells, NQ).       */

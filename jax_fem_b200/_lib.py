@@ -33,6 +33,12 @@ _SIGNATURES = {
     "fem_pbicgstab": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _vp, _vp, _vp]),
     "fem_adjoint_param_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fem_dot": (_i, [_i64, _vp, _vp, _vp, _vp, _vp]),
+    "fem_dcg_begin": (_i, [_vp, _d, _d, _i, _vp]),
+    "fem_dcg_spmv_dot": (_i, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "fem_dcg_init": (_i, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fem_dcg_scalars": (_i, [_i, _vp, _vp]),
+    "fem_dcg_update": (_i, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fem_dcg_direction": (_i, [_i64, _vp, _vp, _vp, _vp, _vp]),
     "fem_axpy": (_i, [_i64, _d, _vp, _vp, _vp]),
 }
 

@@ -40,6 +40,10 @@ enum {
   S_TOL2 = 11,
   S_ATOLIN2 = 12,
   S_TMP = 13,
+  S_SUM0 = 16,   // distributed CG: rank-local partial sums, all-reduced by the caller between kernels
+  S_SUM1 = 17,
+  S_SUM2 = 18,
+  S_SUM3 = 19,
   S_TICKET = 32  // unsigned counter (reinterpreted)
 };
 
@@ -99,6 +103,7 @@ __device__ __forceinline__ bool solver_done(const double* S) { return __ldcg(S +
 // MODE 0: plain.  MODE 1 (CG): dot0 = d1[row]*y[row] -> alpha = gamma/dot0.
 // MODE 2 (BiCGSTAB q = A phat): dot0 = rhat.q -> alpha = rho_new/dot0.
 // MODE 3 (BiCGSTAB t = A shat): dot0 = t.s, dot1 = t.t -> omega = dot0/dot1.
+// MODE 4 (distributed CG): dot0 = d1.y over the rank's owned rows -> S[S_SUM0] (all-reduced by the caller).
 template <int LPR, int MODE>
 __global__ void __launch_bounds__(kThreads) spmv_fused_kernel(int64_t n, const int32_t* __restrict__ indptr,
                                                               const int32_t* __restrict__ indices,
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(kThreads) spmv_fused_kernel(int64_t n, const i
     for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (valid && sub == 0) {
       y[row] = acc;
-      if (MODE == 1 || MODE == 2) dots[0] = fma(d1[row], acc, dots[0]);
+      if (MODE == 1 || MODE == 2 || MODE == 4) dots[0] = fma(d1[row], acc, dots[0]);
       if (MODE == 3) {
         dots[0] = fma(acc, d1[row], dots[0]);
         dots[1] = fma(acc, acc, dots[1]);
@@ -147,6 +152,9 @@ __global__ void __launch_bounds__(kThreads) spmv_fused_kernel(int64_t n, const i
     reduce_and_finalize<1>(v, S, partial, [&](double (&t)[1]) { S[S_ALPHA] = S[S_RHO_NEW] / t[0]; });
   } else if constexpr (MODE == 3) {
     reduce_and_finalize<2>(dots, S, partial, [&](double (&t)[2]) { S[S_OMEGA] = t[0] / t[1]; });
+  } else if constexpr (MODE == 4) {   // distributed CG: rank-local p.Ap, all-reduced by the caller
+    double v[1] = {dots[0]};
+    reduce_and_finalize<1>(v, S, partial, [&](double (&t)[1]) { S[S_SUM0] = t[0]; });
   }
 }
 
@@ -213,6 +221,79 @@ __global__ void __launch_bounds__(kThreads) cg_direction_kernel(int64_t n, const
   const double beta = __ldcg(S + S_BETA);
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
     p[i] = fma(beta, p[i], precond(diag, i, r[i]));
+}
+
+// ------------------------------------------------ distributed CG (one rank's share) ---------------
+// Vectors hold the rank's owned dofs first, then its ghosts; kernels touch the owned range only.  Each kernel
+// leaves rank-local partial sums in S[S_SUM*]; the caller all-reduces that 4-double slice (NCCL, same stream)
+// before launching the next kernel, which derives alpha / beta from the reduced values on the device.
+__global__ void __launch_bounds__(kThreads) dcg_init_kernel(int64_t n, const double* __restrict__ b,
+                                                            const double* __restrict__ diag, const double* __restrict__ q,
+                                                            double* __restrict__ r, double* __restrict__ p,
+                                                            double* __restrict__ S, double* __restrict__ partial) {
+  double v[3] = {0.0, 0.0, 0.0};
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    const double bi = b[i], ri = bi - q[i];
+    const double zi = precond(diag, i, ri);
+    r[i] = ri;
+    p[i] = zi;
+    v[0] = fma(ri, zi, v[0]);
+    v[1] = fma(ri, ri, v[1]);
+    v[2] = fma(bi, bi, v[2]);
+  }
+  reduce_and_finalize<3>(v, S, partial, [&](double (&t)[3]) {
+    S[S_SUM0] = t[0];
+    S[S_SUM1] = t[1];
+    S[S_SUM2] = t[2];
+    S[S_SUM3] = 0.0;
+  });
+}
+
+__global__ void dcg_scalars_init_kernel(double* __restrict__ S) {
+  S[S_GAMMA] = S[S_SUM0];
+  S[S_RR] = S[S_SUM1];
+  const double atol2 = fmax(S[S_TOL2] * S[S_SUM2], S[S_ATOLIN2]);
+  S[S_ATOL2] = atol2;
+  S[S_K] = 0.0;
+  S[S_DONE] = (S[S_SUM1] > atol2 && 0.0 < S[S_MAXIT]) ? 0.0 : 1.0;
+}
+
+__global__ void __launch_bounds__(kThreads) dcg_update_kernel(int64_t n, const double* __restrict__ diag,
+                                                              const double* __restrict__ p, const double* __restrict__ q,
+                                                              double* __restrict__ x, double* __restrict__ r,
+                                                              double* __restrict__ S, double* __restrict__ partial) {
+  if (solver_done(S)) return;
+  const double alpha = __ldcg(S + S_GAMMA) / __ldcg(S + S_SUM0);
+  double v[2] = {0.0, 0.0};
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    x[i] = fma(alpha, p[i], x[i]);
+    const double ri = fma(-alpha, q[i], r[i]);
+    r[i] = ri;
+    v[0] = fma(ri, precond(diag, i, ri), v[0]);
+    v[1] = fma(ri, ri, v[1]);
+  }
+  reduce_and_finalize<2>(v, S, partial, [&](double (&t)[2]) {
+    S[S_SUM1] = t[0];
+    S[S_SUM2] = t[1];
+  });
+}
+
+__global__ void __launch_bounds__(kThreads) dcg_direction_kernel(int64_t n, const double* __restrict__ diag,
+                                                                 const double* __restrict__ r, double* __restrict__ p,
+                                                                 const double* __restrict__ S) {
+  if (solver_done(S)) return;
+  const double beta = __ldcg(S + S_SUM1) / __ldcg(S + S_GAMMA);
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+    p[i] = fma(beta, p[i], precond(diag, i, r[i]));
+}
+
+__global__ void dcg_scalars_step_kernel(double* __restrict__ S) {
+  if (S[S_DONE] != 0.0) return;
+  S[S_GAMMA] = S[S_SUM1];
+  S[S_RR] = S[S_SUM2];
+  const double k = S[S_K] + 1.0;
+  S[S_K] = k;
+  S[S_DONE] = (S[S_SUM2] > S[S_ATOL2] && k < S[S_MAXIT]) ? 0.0 : 1.0;
 }
 
 // ------------------------------------------------------------ BiCGSTAB ----------------------------
@@ -452,4 +533,68 @@ extern "C" int fem_pbicgstab(int64_t n, const int32_t* indptr, const int32_t* in
     if (int e = poll_done(w, &done, st)) return e;
   }
   return finish(n, indptr, indices, data, b, x, w, t, info_host, st);
+}
+
+// ---- distributed CG building blocks (the caller all-reduces workspace[16..20) between them) -------------
+extern "C" int fem_dcg_begin(double* workspace, double tol, double atol, int maxiter, void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(workspace, "null pointer");
+  Ws w;
+  w.s = workspace;
+  return init_scalars(w, tol, atol, maxiter, (cudaStream_t)stream);
+}
+
+extern "C" int fem_dcg_spmv_dot(int64_t n_owned, int64_t n_local, const int32_t* indptr, const int32_t* indices,
+                                const double* data, const double* p, double* q, int with_dot, double* workspace,
+                                void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(indptr && indices && data && p && q && workspace, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Ws w = carve(workspace, n_local);
+  if (with_dot) spmv_fused<4>(n_owned, indptr, indices, data, p, q, p, w, st);
+  else spmv_fused<0>(n_owned, indptr, indices, data, p, q, nullptr, w, st);
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
+}
+
+extern "C" int fem_dcg_init(int64_t n_owned, int64_t n_local, const double* b, const double* diag, const double* q,
+                            double* r, double* p, double* workspace, void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(b && q && r && p && workspace, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Ws w = carve(workspace, n_local);
+  dcg_init_kernel<<<FEM_PGRID(dcg_init_kernel)>>>(n_owned, b, diag, q, r, p, w.s, w.partial);
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
+}
+
+extern "C" int fem_dcg_scalars(int phase, double* workspace, void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(workspace, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (phase == 0) dcg_scalars_init_kernel<<<1, 1, 0, st>>>(workspace);
+  else dcg_scalars_step_kernel<<<1, 1, 0, st>>>(workspace);
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
+}
+
+extern "C" int fem_dcg_update(int64_t n_owned, int64_t n_local, const double* diag, const double* p, const double* q,
+                              double* x, double* r, double* workspace, void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(p && q && x && r && workspace, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Ws w = carve(workspace, n_local);
+  dcg_update_kernel<<<FEM_PGRID(dcg_update_kernel)>>>(n_owned, diag, p, q, x, r, w.s, w.partial);
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
+}
+
+extern "C" int fem_dcg_direction(int64_t n_owned, const double* diag, const double* r, double* p, double* workspace,
+                                 void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(r && p && workspace, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  dcg_direction_kernel<<<FEM_PGRID(dcg_direction_kernel)>>>(n_owned, diag, r, p, workspace);
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
 }

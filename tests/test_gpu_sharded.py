@@ -1,0 +1,66 @@
+"""Sharded (multi-rank) path on ONE GPU: ranks run as threads of this process (ThreadComm), each with its own local
+Problem, halo plan and share of the distributed Jacobi-CG.  The result must equal the single-domain solve and the oracle."""
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fem, laws as olaws
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_linear_elasticity_matches_single_domain_and_oracle(world):
+    import jax_fem_b200 as jf
+    from jax_fem_b200 import laws
+    from jax_fem_b200.distributed import ShardedProblem, ThreadComm
+
+    class Elasticity(jf.Problem):
+        def get_tensor_map(self):
+            return laws.LinearElasticity(70e3, 0.3)
+
+        def get_surface_maps(self):
+            return [lambda u, x: np.array([0., 0., 100.])]
+
+    m = jf.box_mesh(9, 4, 3, 3.0, 1.0, 0.8)
+    pts, cells = m.points, m.cells_dict['hexahedron']
+    left = lambda p: np.isclose(p[0], 0., atol=1e-5)
+    right = lambda p: np.isclose(p[0], 3., atol=1e-5)
+    kw = dict(dirichlet_bc_info=[[left] * 3, [0, 1, 2], [lambda p: 0.] * 3], location_fns=[right])
+
+    single = Elasticity(jf.Mesh(pts, cells), vec=3, dim=3, **kw)
+    ref = jf.solver(single, {'jax_solver': {'method': 'cg'}})[0].cpu().numpy()
+
+    out, errs = {}, []
+
+    def run(comm):
+        try:
+            torch.cuda.set_device(0)
+            sp = ShardedProblem(Elasticity, pts, cells, comm, vec=3, dim=3, **kw)
+            sol = sp.solve_linear()
+            out[comm.rank] = (sp.part, sol.cpu().numpy(), sp.last_info)
+        except Exception as e:                      # pragma: no cover
+            errs.append(e)
+            try:
+                comm.sh.barrier.abort()
+            except Exception:
+                pass
+
+    threads = [threading.Thread(target=run, args=(c,)) for c in ThreadComm.group(world)]
+    [t.start() for t in threads]
+    [t.join(300) for t in threads]
+    assert not errs, errs
+    glob = np.full_like(ref, np.nan)
+    for r in range(world):
+        part, sol, info = out[r]
+        glob[part.owned] = sol[:part.n_owned]
+        assert np.abs(sol[part.n_owned:] - ref[part.ghosts]).max() <= 1e-8 * np.abs(ref).max()   # ghosts up to date
+        assert 0 < info['iterations'] < 2000
+    assert np.abs(glob - ref).max() <= 1e-8 * np.abs(ref).max()
+
+    opb = fem.Problem(fem.Mesh(pts, cells), 3, 3, law=olaws.LinearElastic(70e3, 0.3), location_fns=[right],
+                      surface_maps=[lambda u, x: np.array([0., 0., 100.]) + 0. * u], **{'dirichlet_bc_info': kw['dirichlet_bc_info']})
+    osol = fem.solver(opb, method='cg')
+    assert np.abs(glob - osol).max() <= 1e-8 * np.abs(osol).max()
