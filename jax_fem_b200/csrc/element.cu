@@ -13,6 +13,7 @@
 //            the same address), closed-form tangents -- no AD, no per-cell (24x24) temporaries.
 //   output : one contiguous row block (NN blocks of VEC x VEC) per corner (cell, a), placed at the
 //            corner's position in the plan's node-sorted order.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace femb200 {
@@ -480,6 +481,169 @@ __global__ void __launch_bounds__(CPB* NN, (LAW == FEM_LAW_NEO_HOOKEAN ? 256 / (
   }
 }
 
+// ---- HEX8 isotropic elasticity on the FP64 tensor cores (DMMA) -------------------------------------
+// The DFMA kernel above is bounded by shared->register bandwidth: G_ab += (E w g_a) (x) g_b needs one loaded
+// double per 2.25 FMA while the SM sustains one per 4.  mma.sync.m8n8k4.f64 contracts over the quadrature points
+// with the operands DISTRIBUTED over the warp's registers: with the 24 element dofs ordered (component, node) the
+// 24x24 matrix  G = sum_q (E_q w_q g(q)) g(q)^T  is a 3x3 grid of 8x8 tiles T_IJ[a][b] = G_ab[I][J], every tile is
+// two k-steps (8 quadrature points), and lane l = (node n = l/4, t = l%4) supplies g_n(q=t) and g_n(q=t+4) as BOTH
+// the A row and the B column -- 8 shared loads per lane and cell instead of ~350.  DMMA and DFMA share one pipe on
+// B200 (tools/microbench.cu), so this saves operand bandwidth, not flops.  The element residual
+// r_a[i] = sum_{q,d} g_a(q)[d] S_q[i][d] reuses the same A fragments against S as the B operand (6 more DMMA).
+// One warp owns 4 cells: phase 1 (lane = (cell, q)) is the same geometry/stress code as above; then the warp
+// walks its cells one at a time: 18 + 6 DMMA, G -> K in registers (lane (n,t) holds K_{n,2t} and K_{n,2t+1}:
+// 18 contiguous doubles of row block n), staging in shared memory and a coalesced copy to the row block's
+// node-sorted position.
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+struct DmmaLayout {
+  static constexpr int NN = 8, NQ = 8, DIM = 3, VEC = 3;
+  static constexpr int TAB_STRIDE = 25, TAB_SIZE = NQ * TAB_STRIDE + NQ;      // 208
+  static constexpr int GS = 28;                    // per-q stride of g[n][d]: 12 (mod 16) => conflict-free fragments
+  static constexpr int OFF_X = 0, OFF_U = 24;      // per cell: X[8][3], U[8][3]
+  static constexpr int OFF_G = 48;                 // g[q][n][d]
+  static constexpr int OFF_S = OFF_G + NQ * GS;    // S[q][i][d] = sigma JxW        (272)
+  static constexpr int OFF_E = OFF_S + NQ * 9;     // E_q JxW                       (344)
+  static constexpr int CELL = 354;                 // 352 + 2: cell stride 2 (mod 16) spreads phase-1 stores
+  static constexpr int OUT = 576;                  // one cell's 8 row blocks
+  static constexpr int WARP = 4 * CELL + OUT + 16; // + 32 ints of corner positions
+  static constexpr int WARPS = 4;
+};
+
+template <int LAW>
+__global__ void __launch_bounds__(DmmaLayout::WARPS * 32, 3) element_dmma_kernel(const ElemArgs A) {
+  using L = DmmaLayout;
+  constexpr int NN = 8, NQ = 8, DIM = 3, VEC = 3, ND = 24;
+  extern __shared__ __align__(16) double sm[];
+  double* tab = sm;
+  const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
+  double* wb = sm + L::TAB_SIZE + warp * L::WARP;
+  double* out = wb + 4 * L::CELL;
+  int* pos = reinterpret_cast<int*>(out + L::OUT);
+  for (int i = threadIdx.x; i < NQ * NN * DIM; i += L::WARPS * 32)
+    tab[(i / (NN * DIM)) * L::TAB_STRIDE + i % (NN * DIM)] = A.ref[i];
+  if (threadIdx.x < NQ) tab[NQ * L::TAB_STRIDE + threadIdx.x] = A.ref[NQ * NN * DIM + threadIdx.x];
+
+  // ---- phase 0/1: lane = (cell j, q) ----
+  const int j1 = l >> 3, q = l & 7;
+  const int64_t c1 = ((int64_t)blockIdx.x * L::WARPS + warp) * 4 + j1;
+  const bool act1 = c1 < A.C;
+  double* cb = wb + j1 * L::CELL;
+  if (act1) {
+    const int64_t node = A.cells[c1 * NN + q];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) cb[L::OFF_X + q * DIM + d] = A.points[node * DIM + d];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) cb[L::OFF_U + q * VEC + i] = A.sol[node * VEC + i];
+    pos[l] = A.corner_pos ? A.corner_pos[c1 * NN + q] : (int)(c1 * NN + q);
+  }
+  __syncthreads();
+  if (act1) {
+    double g[NN][DIM];
+    const double w = qp_geometry<NN, DIM>(cb + L::OFF_X, tab + q * L::TAB_STRIDE, tab[NQ * L::TAB_STRIDE + q], g);
+    double ug[VEC][DIM];
+    qp_grad_u<NN, DIM, VEC>(cb + L::OFF_U, g, ug);
+    const double* ivq = A.iv ? A.iv + c1 * NQ + q : nullptr;
+    const double E = iso_modulus<LAW>(A.p, ivq, false), nu = iso_nu<LAW>(A.p);
+    const double mu = E / (2.0 * (1.0 + nu)), lam = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
+    double sig[DIM][DIM];
+    iso_stress<DIM>(lam, mu, ug, sig);
+#pragma unroll
+    for (int n = 0; n < NN; ++n)
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) cb[L::OFF_G + q * L::GS + n * DIM + d] = g[n][d];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) cb[L::OFF_S + q * 9 + i * DIM + d] = sig[i][d] * w;
+    cb[L::OFF_E + q] = E * w;
+  }
+  __syncwarp();
+
+  // ---- phase 2: the warp walks its 4 cells; lane = (node n, t) ----
+  const int n = l >> 2, t = l & 3;
+  const double nu = iso_nu<LAW>(A.p);
+  const double mu1 = 1.0 / (2.0 * (1.0 + nu)), lam1 = nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
+#pragma unroll 1
+  for (int j = 0; j < 4; ++j) {
+    const int64_t c = ((int64_t)blockIdx.x * L::WARPS + warp) * 4 + j;
+    if (c >= A.C) break;                                   // warp-uniform
+    const double* cj = wb + j * L::CELL;
+    double g0[3], g1[3], a0[3], a1[3];
+    const double e0 = cj[L::OFF_E + t], e1 = cj[L::OFF_E + t + 4];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      g0[d] = cj[L::OFF_G + t * L::GS + n * 3 + d];
+      g1[d] = cj[L::OFF_G + (t + 4) * L::GS + n * 3 + d];
+      a0[d] = e0 * g0[d];
+      a1[d] = e1 * g1[d];
+    }
+    double C[3][3][2];
+#pragma unroll
+    for (int I = 0; I < 3; ++I)
+#pragma unroll
+      for (int J = 0; J < 3; ++J) {
+        C[I][J][0] = C[I][J][1] = 0.0;
+        dmma884(C[I][J], a0[I], g0[J]);
+        dmma884(C[I][J], a1[I], g1[J]);
+      }
+    // residual: B[q][col] = S_q[i = col][d] for col < 3 (col = l/4), zero otherwise
+    double R[2] = {0.0, 0.0};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double b0 = (n < 3) ? cj[L::OFF_S + t * 9 + n * 3 + d] : 0.0;
+      const double b1 = (n < 3) ? cj[L::OFF_S + (t + 4) * 9 + n * 3 + d] : 0.0;
+      dmma884(R, g0[d], b0);
+      dmma884(R, g1[d], b1);
+    }
+    // R = r_n[2t], r_n[2t+1]: components 0,1 live in lanes t == 0, component 2 in lanes t == 1
+    if (t == 0) {
+      A.Re[c * ND + n * 3 + 0] = R[0];
+      A.Re[c * ND + n * 3 + 1] = R[1];
+    } else if (t == 1) {
+      A.Re[c * ND + n * 3 + 2] = R[0];
+    }
+    // G -> K for the lane's two column nodes b = 2t, 2t+1; 18 contiguous doubles of row block n
+    double* dst = out + n * 72 + t * 18;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const double tr = C[0][0][e] + C[1][1][e] + C[2][2][e];
+      double K[9];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) K[i * 3 + k] = lam1 * C[i][k][e] + mu1 * C[k][i][e] + (i == k ? mu1 * tr : 0.0);
+#pragma unroll
+      for (int m = 0; m < 9; ++m) dst[e * 9 + m] = K[m];
+    }
+    __syncwarp();
+    // coalesced copy-out: 8 row blocks x 36 double2
+#pragma unroll
+    for (int it = 0; it < 9; ++it) {
+      const int p2 = it * 32 + l;
+      const int row = p2 / 36, w2 = p2 % 36;
+      reinterpret_cast<double2*>(A.Ke + (int64_t)pos[j * 8 + row] * 72)[w2] = reinterpret_cast<const double2*>(out + row * 72)[w2];
+    }
+    __syncwarp();
+  }
+}
+
+template <int LAW>
+int launch_element_dmma(const ElemArgs& A, cudaStream_t st) {
+  using L = DmmaLayout;
+  const size_t smem = sizeof(double) * (L::TAB_SIZE + (size_t)L::WARPS * L::WARP);
+  const unsigned grid = (unsigned)((A.C + L::WARPS * 4 - 1) / (L::WARPS * 4));
+  auto k = element_dmma_kernel<LAW>;
+  FEM_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<grid, L::WARPS * 32, smem, st>>>(A);
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
+}
+
 // ---- adjoint: -lambda^T dc/dtheta per quadrature point (thread per (cell, q)) -------------------
 template <int NN, int DIM, int VEC, int LAW, int CPB>
 __global__ void __launch_bounds__(CPB* NN) param_grad_kernel(const ElemArgs A) {
@@ -576,6 +740,15 @@ int launch_param_grad(const ElemArgs& A, cudaStream_t st) {
 // Registry of (element, vec, law) combinations.  Anything else is an error, never a fallback.
 template <bool GRAD>
 int dispatch(int ele, int vec, int law, const ElemArgs& A, cudaStream_t st) {
+  if constexpr (!GRAD) {
+    // tensor-core path for the headline configuration (FEM_ELEMENT_PATH=dfma in the environment selects the
+    // CUDA-core kernel instead, for A/B measurements; both are parity-tested)
+    static const bool use_dmma = []() { const char* e = getenv("FEM_ELEMENT_PATH"); return !(e && e[0] == 'd' && e[1] == 'f'); }();
+    if (use_dmma && A.Ke && ele == FEM_ELE_HEX8 && vec == 3) {
+      if (law == FEM_LAW_LINEAR_ELASTIC) return launch_element_dmma<FEM_LAW_LINEAR_ELASTIC>(A, st);
+      if (law == FEM_LAW_SIMP) return launch_element_dmma<FEM_LAW_SIMP>(A, st);
+    }
+  }
 #define FEM_CASE(ELE, NN, DIM, VEC, LAW, CPB)                                     \
   if (ele == ELE && vec == VEC && law == LAW) {                                   \
     if constexpr (GRAD) return launch_param_grad<NN, DIM, VEC, LAW, CPB>(A, st);  \

@@ -45,89 +45,134 @@ constexpr int kGatherThreads = 128;
 constexpr int kGatherCorners = 32;      // corners per CTA (4 interior HEX8 nodes)
 constexpr int kGatherTail = 16;         // max corners of one node (checked when the plan is built)
 
+// Per-item metadata a thread keeps in registers (prefetched one work item ahead).
+template <int EPT, int SPT>
+struct GatherMeta {
+  int C0, C1, E0, E1, S0, S1;      // corner / entry / source ranges of the item
+  int soff[SPT];                   // raw block indices of the thread's sources
+  int sb[EPT], se[EPT], dst[EPT], info[EPT];
+};
+
 template <int VEC, int NN>
 __global__ void __launch_bounds__(kGatherThreads) gather_csr_kernel(
-    const int32_t* __restrict__ gdesc, const int32_t* __restrict__ eorder, const int32_t* __restrict__ src_ptr,
-    const int32_t* __restrict__ src, const int32_t* __restrict__ edst, const int32_t* __restrict__ einfo,
-    const double* __restrict__ Ke, double* __restrict__ data) {
+    int n_items, const int32_t* __restrict__ gdesc, const int32_t* __restrict__ eorder,
+    const int32_t* __restrict__ src_ptr, const int32_t* __restrict__ src, const int32_t* __restrict__ edst,
+    const int32_t* __restrict__ einfo, const double* __restrict__ Ke, double* __restrict__ data) {
   constexpr int VV = VEC * VEC;
   constexpr int ROW = NN * VV;                                    // doubles per corner row block
   constexpr int MAXC = kGatherCorners + kGatherTail;
-  constexpr int MAXS = MAXC * NN;                                 // sources (blocks) of the CTA
-  constexpr int EPT = (MAXS + kGatherThreads - 1) / kGatherThreads;   // entries per thread (worst case)
+  constexpr int MAXS = MAXC * NN;                                 // sources (blocks) of an item
+  constexpr int EPT = (MAXS + kGatherThreads - 1) / kGatherThreads;   // entries / sources per thread (worst case)
   static_assert(ROW % 2 == 0, "row blocks must be 16-byte multiples");
-  __shared__ __align__(128) double sh[MAXC * ROW];
-  __shared__ int s_off[MAXS];                                     // block offset (in blocks) inside sh
-  __shared__ __align__(8) uint64_t bar;
-  // descriptor: first corner / entry / source of this CTA and of the next one
-  const int C0 = gdesc[blockIdx.x * 4 + 0], C1 = gdesc[blockIdx.x * 4 + 4];
-  const int E0 = gdesc[blockIdx.x * 4 + 1], E1 = gdesc[blockIdx.x * 4 + 5];
-  const int S0 = gdesc[blockIdx.x * 4 + 2], S1 = gdesc[blockIdx.x * 4 + 6];
-  if (C0 >= C1) return;
-  const int nE = E1 - E0, nS = S1 - S0;
+  extern __shared__ __align__(128) double gsm[];
+  auto stage_ptr = [&](int stage) { return gsm + stage * (MAXC * ROW); };   // two TMA stages
+  int* s_off = reinterpret_cast<int*>(gsm + 2 * MAXC * ROW);      // block offset (in blocks) inside the stage
+  __shared__ __align__(8) uint64_t bar[2];
+  using Meta = GatherMeta<EPT, EPT>;
 
-  // phase A: the CTA's segment of row blocks is one contiguous, 16-byte aligned range: a single TMA bulk copy
-  // (cp.async.bulk) brings it in while the threads fetch the source offsets and their entries' metadata
-  if (threadIdx.x == 0) mbar_init(&bar, 1);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const uint32_t bytes = (uint32_t)(C1 - C0) * ROW * sizeof(double);
-    mbar_expect_tx(&bar, bytes);
-    bulk_g2s(sh, Ke + (int64_t)C0 * ROW, bytes, &bar);
-  }
-  for (int t = threadIdx.x; t < nS; t += kGatherThreads) s_off[t] = src[S0 + t] - C0 * NN;
-  // each thread owns up to EPT entries, taken in the plan's balanced order (entries of a CTA sorted by source
-  // count, so the lanes of a warp loop over the same number of sources)
-  int sb[EPT], se[EPT], dst[EPT], info[EPT];
+  auto load_desc = [&](int it, Meta& m) {
+    m.C0 = gdesc[it * 4 + 0]; m.C1 = gdesc[it * 4 + 4];
+    m.E0 = gdesc[it * 4 + 1]; m.E1 = gdesc[it * 4 + 5];
+    m.S0 = gdesc[it * 4 + 2]; m.S1 = gdesc[it * 4 + 6];
+  };
+  auto load_meta = [&](Meta& m) {          // global loads only; consumed one iteration later
 #pragma unroll
-  for (int r = 0; r < EPT; ++r) {
-    const int t = threadIdx.x + r * kGatherThreads;
-    sb[r] = se[r] = 0;
-    dst[r] = -1;
-    info[r] = 0;
-    if (t < nE) {
-      const int e = eorder[E0 + t];
-      sb[r] = src_ptr[e] - S0;
-      se[r] = src_ptr[e + 1] - S0;
-      dst[r] = edst[e] - VV * E0;
-      info[r] = einfo[e];
-    }
-  }
-  __syncthreads();
-  mbar_wait(&bar, 0);
-
-  // phase B: per entry, add its sources in ascending (cell, a, b) order -- fixed order => bit-reproducible
-  double res[EPT][VV];
-#pragma unroll
-  for (int r = 0; r < EPT; ++r) {
-#pragma unroll
-    for (int j = 0; j < VV; ++j) res[r][j] = 0.0;
-    for (int sidx = sb[r]; sidx < se[r]; ++sidx) {
-      const double* blk = sh + s_off[sidx] * VV;
-#pragma unroll
-      for (int j = 0; j < VV; ++j) res[r][j] += blk[j];
-    }
-  }
-  __syncthreads();
-
-  // phase C: results -> shared memory in CSR order (the CTA's rows are one contiguous range of `data`), then a
-  // coalesced copy.  einfo: bits 0..15 = VEC*len(row node), bit 16 = diagonal block, bits 17.. = Dirichlet rows.
-#pragma unroll
-  for (int r = 0; r < EPT; ++r) {
-    if (dst[r] >= 0) {
-      const int rowlen = info[r] & 0xffff;
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        const bool bc = (info[r] >> (17 + i)) & 1;
-#pragma unroll
-        for (int k = 0; k < VEC; ++k)
-          sh[dst[r] + i * rowlen + k] = bc ? ((((info[r] >> 16) & 1) && i == k) ? 1.0 : 0.0) : res[r][i * VEC + k];
+    for (int r = 0; r < EPT; ++r) {
+      const int t = threadIdx.x + r * kGatherThreads;
+      m.soff[r] = (t < m.S1 - m.S0) ? src[m.S0 + t] : 0;
+      m.sb[r] = m.se[r] = 0;
+      m.dst[r] = -1;
+      m.info[r] = 0;
+      if (t < m.E1 - m.E0) {
+        const int e = eorder[m.E0 + t];
+        m.sb[r] = src_ptr[e] - m.S0;
+        m.se[r] = src_ptr[e + 1] - m.S0;
+        m.dst[r] = edst[e] - VV * m.E0;
+        m.info[r] = einfo[e];
       }
     }
+  };
+  auto issue_tma = [&](const Meta& m, int stage) {   // one elected thread; the segment is contiguous and 16B-aligned
+    const uint32_t bytes = (uint32_t)(m.C1 - m.C0) * ROW * sizeof(double);
+    mbar_expect_tx(&bar[stage], bytes);            // also the (single) arrival: an empty item completes the phase at once
+    if (bytes) bulk_g2s(stage_ptr(stage), Ke + (int64_t)m.C0 * ROW, bytes, &bar[stage]);
+  };
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
   }
   __syncthreads();
-  double* __restrict__ out = data + (int64_t)VV * E0;
-  for (int t = threadIdx.x; t < nE * VV; t += kGatherThreads) out[t] = sh[t];
+  int it = blockIdx.x;
+  if (it >= n_items) return;
+  Meta cur, nxt;
+  load_desc(it, cur);
+  if (threadIdx.x == 0) issue_tma(cur, 0);
+  load_meta(cur);
+  const int it1 = it + gridDim.x;
+  if (it1 < n_items) load_desc(it1, nxt);
+
+  for (int k = 0; it < n_items; ++k, it += gridDim.x) {
+    const int stage = k & 1;
+    const bool has_next = it + (int)gridDim.x < n_items;
+    // prefetch the next item: its row blocks by TMA into the other stage (free since the end of iteration k-1),
+    // its metadata into registers; both are consumed in iteration k+1
+    if (has_next) {
+      if (threadIdx.x == 0) issue_tma(nxt, stage ^ 1);
+      load_meta(nxt);
+    }
+    Meta nn2;
+    const bool has_next2 = it + 2 * (int)gridDim.x < n_items;
+    if (has_next2) load_desc(it + 2 * gridDim.x, nn2);
+
+    const int nE = cur.E1 - cur.E0, nS = cur.S1 - cur.S0;
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) {
+      const int t = threadIdx.x + r * kGatherThreads;
+      if (t < nS) s_off[t] = cur.soff[r] - cur.C0 * NN;
+    }
+    __syncthreads();
+    mbar_wait(&bar[stage], (k >> 1) & 1);
+    const double* sh = stage_ptr(stage);
+
+    // phase B: per entry, add its sources in ascending (cell, a, b) order -- fixed order => bit-reproducible
+    double res[EPT][VV];
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) {
+#pragma unroll
+      for (int j = 0; j < VV; ++j) res[r][j] = 0.0;
+      for (int sidx = cur.sb[r]; sidx < cur.se[r]; ++sidx) {
+        const double* blk = sh + s_off[sidx] * VV;
+#pragma unroll
+        for (int j = 0; j < VV; ++j) res[r][j] += blk[j];
+      }
+    }
+    __syncthreads();
+
+    // phase C: results -> shared memory in CSR order (the item's rows are one contiguous range of `data`), then a
+    // coalesced copy.  einfo: bits 0..15 = VEC*len(row node), bit 16 = diagonal block, bits 17.. = Dirichlet rows.
+    double* so = stage_ptr(stage);
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) {
+      if (cur.dst[r] >= 0) {
+        const int rowlen = cur.info[r] & 0xffff;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const bool bc = (cur.info[r] >> (17 + i)) & 1;
+#pragma unroll
+          for (int kk = 0; kk < VEC; ++kk)
+            so[cur.dst[r] + i * rowlen + kk] =
+                bc ? ((((cur.info[r] >> 16) & 1) && i == kk) ? 1.0 : 0.0) : res[r][i * VEC + kk];
+        }
+      }
+    }
+    __syncthreads();
+    double* __restrict__ out = data + (int64_t)VV * cur.E0;
+    for (int t = threadIdx.x; t < nE * VV; t += kGatherThreads) out[t] = so[t];
+    __syncthreads();                       // stage is free for the TMA issued in the next iteration
+    cur = nxt;
+    nxt = nn2;
+  }
 }
 
 template <int VEC, int NN>
@@ -265,6 +310,30 @@ extern "C" int fem_device_count(void) {
   return n;
 }
 
+namespace femb200 {
+namespace {
+template <int VEC, int NN>
+int launch_gather(int n_items, const int32_t* gdesc, const int32_t* eorder, const int32_t* src_ptr, const int32_t* src,
+                  const int32_t* edst, const int32_t* einfo, const double* Ke, double* data, cudaStream_t st) {
+  constexpr int MAXC = kGatherCorners + kGatherTail;
+  const size_t smem = sizeof(double) * 2 * MAXC * NN * VEC * VEC + sizeof(int) * MAXC * NN;
+  auto k = gather_csr_kernel<VEC, NN>;
+  static int grid = 0;                      // persistent grid: resident CTAs x SMs (per template instance)
+  if (!grid) {
+    FEM_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0, dev = 0, sms = kNumSM;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kGatherThreads, smem);
+    grid = (per_sm < 1 ? 1 : per_sm) * sms;
+  }
+  k<<<grid < n_items ? grid : n_items, kGatherThreads, smem, st>>>(n_items, gdesc, eorder, src_ptr, src, edst, einfo, Ke, data);
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
+}
+}  // namespace
+}  // namespace femb200
+
 extern "C" int fem_gather_csr(int vec, int nn, int64_t n_blocks, const int32_t* gdesc, const int32_t* eorder,
                               const int32_t* src_ptr, const int32_t* src, const int32_t* edst, const int32_t* einfo,
                               const double* Ke, double* data, void* stream) {
@@ -274,9 +343,7 @@ extern "C" int fem_gather_csr(int vec, int nn, int64_t n_blocks, const int32_t* 
   cudaStream_t st = (cudaStream_t)stream;
 #define FEM_G(V, N)                                                                                                  \
   if (vec == V && nn == N) {                                                                                         \
-    gather_csr_kernel<V, N><<<(unsigned)n_blocks, kGatherThreads, 0, st>>>(gdesc, eorder, src_ptr, src, edst, einfo, Ke, data); \
-    FEM_LAUNCH_CHECK();                                                                                              \
-    return FEM_OK;                                                                                                   \
+    return launch_gather<V, N>((int)n_blocks, gdesc, eorder, src_ptr, src, edst, einfo, Ke, data, st);              \
   }
   FEM_G(3, 8) FEM_G(1, 8) FEM_G(1, 4) FEM_G(2, 4)
 #undef FEM_G
