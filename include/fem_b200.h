@@ -67,6 +67,15 @@ int fem_element_residual_jacobian(int ele_type, int vec, int law_id, const doubl
                                   const double* ref_tables, const int32_t* corner_pos, double* Ke, double* Re,
                                   void* stream);
 
+/* HEX27 (jax_fem/basis.py:58-65; 81x81 element tangents on FP64 DMMA tiles), isotropic elasticity (linear, SIMP).
+ * ref_tables: [n_quad*27*3] dN then [n_quad] weights; internal_var (n_cells, n_quad) or NULL.
+ * Ke: (n_cells*27, 244): row block of corner (c,a) = 27 blocks of 3x3 (+1 pad double) at corner_pos[c*27+a];
+ * NULL = residual only.  Re: (n_cells, 81).                                                                    */
+int fem_hex27_residual_jacobian(int law_id, const double* law_params_host, const double* points,
+                                const int32_t* cells, int64_t n_cells, const double* sol,
+                                const double* internal_var, const double* ref_tables, int n_quad,
+                                const int32_t* corner_pos, double* Ke, double* Re, void* stream);
+
 /* ---- (2) global assembly: _PetscTangentCache.update / get_A (jax_fem/solver.py:469-553)
  *      as a precomputed cell->CSR-slot permutation + deterministic segmented sum (no atomics).
  *
@@ -75,8 +84,9 @@ int fem_element_residual_jacobian(int ele_type, int vec, int law_id, const doubl
  * every (cell, local row node, local col node) contributing to it, in ascending (c,a,b) order (fixed
  * summation order => bit-reproducible).  Ke is the output of fem_element_residual_jacobian.
  * gdesc (4*(n_blocks+1)): work split.  CTA b owns the nodes whose first corner (in node-sorted order) lies in
- *              [32 b, 32 (b+1)); gdesc[4b..4b+2] = first corner, first entry, first source of CTA b (the next
- *              CTA's triple closes the ranges).  No node may have more than 16 corners.
+ *              [W b, W (b+1)), W = 32 corners (8 for 27-node cells); gdesc[4b..4b+2] = first corner, first entry,
+ *              first source of item b (the next item's triple closes the ranges).  No node may have more than
+ *              16 corners (8 for 27-node cells).  Row blocks are padded to an even number of doubles.
  * eorder (nnzb): processing order of the entries inside each CTA (a permutation of the CTA's entry range, sorted by
  *              descending source count so that the lanes of a warp loop equally long); results do not depend on it.
  * edst (nnzb): offset in `data` of element (row vec*n, col vec*m) of the scalar CSR pattern

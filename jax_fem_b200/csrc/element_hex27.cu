@@ -1,0 +1,281 @@
+// HEX27 (27-node, second-order hexahedron) element kernel: the dense 81x81 element tangent on the FP64 tensor
+// cores (DMMA, mma.sync.m8n8k4.f64), isotropic elasticity (linear / SIMP).
+//
+// Replaces, for ele_type='HEX27' (jax_fem/basis.py:58-65: degree 2, default quadrature degree 10 = 6x6x6 points),
+// the same reference functions as element.cu: get_laplace_kernel + value_and_jacfwd (jax_fem/problem.py:189-214,
+// 262-266) and FiniteElement.get_shape_grads (jax_fem/fe.py:112-141).  The reference would materialise
+// shape_grads (C,216,27,3) = 30 GB at 60^3; here geometry is recomputed per cell.
+//
+// One CTA (8 warps) per cell:
+//   phase 1  thread = quadrature point: J, J^-1, JxW, grad u, stress  ->  shared {J^-1, E w, S = sigma JxW}
+//   phase 2  for chunks of 32 quadrature points:
+//              all threads: g[q][n][:] = dN[q][n] J^-1(q)                     -> shared Gq[q][3n+d]
+//              DMMA: G(81x81) += sum_q (E_q w_q g(q)) g(q)^T as 8x8 tiles; only the 66 upper tiles of the 11x11
+//                    grid are computed (G is symmetric), 8-9 tiles per warp, accumulators in registers
+//              threads 0..80: r_(a,i) += sum_q S_q[i][:] . g_a(q)
+//   phase 3  tiles -> shared G (mirrored), in-place 3x3 conversion K_ab = lam' G_ab + mu' G_ab^T + mu' tr(G_ab) I,
+//            coalesced copy of the 27 row blocks to their node-sorted positions (row block = 27 blocks of 3x3,
+//            padded to 244 doubles so that every row block is a 16-byte multiple for the TMA gather).
+#include "common.cuh"
+
+namespace femb200 {
+namespace {
+
+constexpr int H27_NN = 27, H27_ND = 81, H27_T = 11;        // 11 x 11 tiles of 8 x 8 cover 81 x 81 (padded to 88)
+constexpr int H27_QC = 32;                                 // quadrature points per chunk (8 DMMA k-steps)
+constexpr int H27_GS = 100;                                // Gq row stride: 4 (mod 16) => conflict-free fragments
+constexpr int H27_GSS = 89;                                // G row stride (odd)
+constexpr int H27_QP = 19;                                 // per point: J^-1 (9), E w (1), S (9)
+constexpr int H27_THREADS = 256, H27_WARPS = 8;
+constexpr int H27_UPPER = H27_T * (H27_T + 1) / 2;         // 66
+constexpr int H27_TPW = (H27_UPPER + H27_WARPS - 1) / H27_WARPS;   // 9
+
+struct Hex27Args {
+  const double* points;
+  const int32_t* cells;
+  const double* sol;
+  const double* iv;          // (C, nq) or nullptr
+  const double* ref;         // [nq*27*3] dN, [nq] w
+  const int32_t* corner_pos;
+  double* Ke;                // (C*27, 244)
+  double* Re;                // (C, 81)
+  int64_t C;
+  int nq;
+  int law;
+  double p[8];
+};
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double det_inv3(const double (&J)[3][3], double (&inv)[3][3]) {
+  const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+  const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+  const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+  const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+  const double r = 1.0 / det;
+  inv[0][0] = c00 * r;
+  inv[1][0] = c01 * r;
+  inv[2][0] = c02 * r;
+  inv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * r;
+  inv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * r;
+  inv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * r;
+  inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * r;
+  inv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * r;
+  inv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * r;
+  return det;
+}
+
+__global__ void __launch_bounds__(H27_THREADS) hex27_kernel(const Hex27Args A) {
+  extern __shared__ __align__(16) double sm[];
+  const int nq = A.nq;
+  const int nq_pad = (nq + H27_QC - 1) / H27_QC * H27_QC;
+  double* X = sm;                          // [27][3]
+  double* U = X + H27_ND;                  // [27][3]
+  double* R = U + H27_ND;                  // [81] residual
+  double* work = R + H27_ND + 1;           // even offset (244) => 16-byte aligned
+  double* QP = work;                       // [nq_pad][19]
+  double* Gq = QP + nq_pad * H27_QP + (nq_pad * H27_QP) % 2;   // [32][100]
+  double* G = work;                        // [88][89] overlays QP + Gq after the main loop
+  __shared__ int pos[H27_NN];
+  const int64_t c = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
+
+  if (tid < H27_NN) {
+    const int64_t node = A.cells[c * H27_NN + tid];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      X[tid * 3 + d] = A.points[node * 3 + d];
+      U[tid * 3 + d] = A.sol[node * 3 + d];
+    }
+    pos[tid] = A.corner_pos ? A.corner_pos[c * H27_NN + tid] : (int)(c * H27_NN + tid);
+  }
+  __syncthreads();
+
+  const double nu = A.law == FEM_LAW_SIMP ? A.p[2] : A.p[1];
+  const double mu1 = 1.0 / (2.0 * (1.0 + nu)), lam1 = nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
+
+  // ---- phase 1: thread = quadrature point ----
+  for (int q = tid; q < nq_pad; q += H27_THREADS) {
+    double* rec = QP + q * H27_QP;
+    if (q >= nq) {                                        // padding points carry zero weight
+      for (int j = 0; j < H27_QP; ++j) rec[j] = 0.0;
+      continue;
+    }
+    const double* dN = A.ref + (int64_t)q * H27_ND;
+    double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int n = 0; n < H27_NN; ++n) {
+      const double d0 = __ldg(dN + n * 3), d1 = __ldg(dN + n * 3 + 1), d2 = __ldg(dN + n * 3 + 2);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const double x = X[n * 3 + d];
+        J[d][0] = fma(x, d0, J[d][0]);
+        J[d][1] = fma(x, d1, J[d][1]);
+        J[d][2] = fma(x, d2, J[d][2]);                    // fe.py:132
+      }
+    }
+    double inv[3][3];
+    const double det = det_inv3(J, inv);                  // fe.py:134-135
+    const double w = det * __ldg(A.ref + (int64_t)nq * H27_ND + q);        // fe.py:140
+    double ug[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int n = 0; n < H27_NN; ++n) {
+      const double d0 = __ldg(dN + n * 3), d1 = __ldg(dN + n * 3 + 1), d2 = __ldg(dN + n * 3 + 2);
+      double g[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) g[d] = d0 * inv[0][d] + d1 * inv[1][d] + d2 * inv[2][d];   // fe.py:138-139
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) ug[i][d] = fma(U[n * 3 + i], g[d], ug[i][d]);            // problem.py:204-205
+    }
+    double E;
+    if (A.law == FEM_LAW_SIMP) E = A.p[1] + (A.p[0] - A.p[1]) * pow(A.iv[c * nq + q], A.p[3]);
+    else E = A.p[0];
+    const double mu = E * mu1, lam = E * lam1;
+    const double tr = ug[0][0] + ug[1][1] + ug[2][2];
+#pragma unroll
+    for (int e = 0; e < 3; ++e)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) rec[e * 3 + d] = inv[e][d];
+    rec[9] = E * w;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) rec[10 + i * 3 + d] = (mu * (ug[i][d] + ug[d][i]) + (i == d ? lam * tr : 0.0)) * w;
+  }
+  // zero the padding columns 81..99 of Gq once
+  for (int j = tid; j < H27_QC * (H27_GS - H27_ND); j += H27_THREADS)
+    Gq[(j / (H27_GS - H27_ND)) * H27_GS + H27_ND + j % (H27_GS - H27_ND)] = 0.0;
+  __syncthreads();
+
+  // ---- phase 2: chunks of 32 points ----
+  // this warp's upper tiles u = warp, warp + 8, ...  ->  (I, J), I <= J
+  int tI[H27_TPW], tJ[H27_TPW];
+#pragma unroll
+  for (int k = 0; k < H27_TPW; ++k) {
+    int u = warp + k * H27_WARPS, I = 0;
+    if (u >= H27_UPPER) u = -1;
+    int rem = u;
+    while (u >= 0 && rem >= H27_T - I) { rem -= H27_T - I; ++I; }
+    tI[k] = u < 0 ? -1 : I;
+    tJ[k] = u < 0 ? -1 : I + rem;
+  }
+  double Cacc[H27_TPW][2];
+#pragma unroll
+  for (int k = 0; k < H27_TPW; ++k) Cacc[k][0] = Cacc[k][1] = 0.0;
+  double racc = 0.0;
+
+  for (int q0 = 0; q0 < nq_pad; q0 += H27_QC) {
+    // g[q][n][:] = dN[q][n] J^-1(q)
+    for (int j = tid; j < H27_QC * H27_NN; j += H27_THREADS) {
+      const int ql = j / H27_NN, n = j % H27_NN, q = q0 + ql;
+      double g[3] = {0.0, 0.0, 0.0};
+      if (q < nq) {
+        const double* dN = A.ref + ((int64_t)q * H27_NN + n) * 3;
+        const double d0 = __ldg(dN), d1 = __ldg(dN + 1), d2 = __ldg(dN + 2);
+        const double* inv = QP + q * H27_QP;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) g[d] = d0 * inv[d] + d1 * inv[3 + d] + d2 * inv[6 + d];
+      }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) Gq[ql * H27_GS + n * 3 + d] = g[d];
+    }
+    __syncthreads();
+    // DMMA: lane (row = l/4, col = l%4) holds A[row][k] = E w g[q = 4s + l%4][8I + l/4], B[k][col] = g[q][8J + l/4]
+#pragma unroll
+    for (int k = 0; k < H27_TPW; ++k) {
+      if (tI[k] < 0) continue;                            // warp-uniform
+      const double* ga = Gq + (l & 3) * H27_GS + 8 * tI[k] + (l >> 2);
+      const double* gb = Gq + (l & 3) * H27_GS + 8 * tJ[k] + (l >> 2);
+      const double* ew = QP + (q0 + (l & 3)) * H27_QP + 9;
+#pragma unroll
+      for (int s = 0; s < H27_QC / 4; ++s)
+        dmma884(Cacc[k], ew[4 * s * H27_QP] * ga[4 * s * H27_GS], gb[4 * s * H27_GS]);
+    }
+    // residual r_(a,i) += sum_q S_q[i][:] . g_a(q)
+    if (tid < H27_ND) {
+      const int a = tid / 3, i = tid % 3;
+      for (int ql = 0; ql < H27_QC; ++ql) {
+        const double* S = QP + (q0 + ql) * H27_QP + 10 + i * 3;
+        const double* g = Gq + ql * H27_GS + a * 3;
+        racc = fma(S[0], g[0], fma(S[1], g[1], fma(S[2], g[2], racc)));                   // problem.py:210
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < H27_ND) A.Re[c * H27_ND + tid] = racc;
+  if (A.Ke == nullptr) return;                             // residual only (block-uniform)
+
+  // ---- phase 3: tiles -> G (mirrored); fragment: row = l/4, cols = 2(l%4), 2(l%4)+1 ----
+#pragma unroll
+  for (int k = 0; k < H27_TPW; ++k) {
+    if (tI[k] < 0) continue;
+    const int r = 8 * tI[k] + (l >> 2), c0 = 8 * tJ[k] + 2 * (l & 3);
+    G[r * H27_GSS + c0] = Cacc[k][0];
+    G[r * H27_GSS + c0 + 1] = Cacc[k][1];
+    if (tI[k] != tJ[k]) {
+      G[c0 * H27_GSS + r] = Cacc[k][0];
+      G[(c0 + 1) * H27_GSS + r] = Cacc[k][1];
+    }
+  }
+  __syncthreads();
+  // in-place conversion of every 3x3 node-pair block
+  for (int j = tid; j < H27_NN * H27_NN; j += H27_THREADS) {
+    const int a = j / H27_NN, b = j % H27_NN;
+    double g[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) g[i][k] = G[(3 * a + i) * H27_GSS + 3 * b + k];
+    const double tr = g[0][0] + g[1][1] + g[2][2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        G[(3 * a + i) * H27_GSS + 3 * b + k] = lam1 * g[i][k] + mu1 * g[k][i] + (i == k ? mu1 * tr : 0.0);
+  }
+  __syncthreads();
+  // coalesced copy-out: row block a = [b][i][k], 243 doubles (+1 pad) at position pos[a]
+  for (int j = tid; j < H27_NN * 244; j += H27_THREADS) {
+    const int a = j / 244, rem = j % 244;
+    double v = 0.0;
+    if (rem < 243) {
+      const int b = rem / 9, i = (rem % 9) / 3, k = rem % 3;
+      v = G[(3 * a + i) * H27_GSS + 3 * b + k];
+    }
+    A.Ke[(int64_t)pos[a] * 244 + rem] = v;
+  }
+}
+
+}  // namespace
+}  // namespace femb200
+
+using namespace femb200;
+
+extern "C" int fem_hex27_residual_jacobian(int law_id, const double* law_params_host, const double* points,
+                                           const int32_t* cells, int64_t n_cells, const double* sol,
+                                           const double* internal_var, const double* ref_tables, int n_quad,
+                                           const int32_t* corner_pos, double* Ke, double* Re, void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(points && cells && sol && ref_tables && Re && law_params_host, "null pointer");
+  FEM_REQUIRE(law_id == FEM_LAW_LINEAR_ELASTIC || law_id == FEM_LAW_SIMP,
+              "HEX27 is registered for isotropic elasticity (linear, SIMP) only");
+  FEM_REQUIRE(!(law_id == FEM_LAW_SIMP && !internal_var), "SIMP needs the per-quadrature-point density");
+  FEM_REQUIRE(n_quad > 0 && n_quad <= 512, "unsupported number of quadrature points");
+  if (n_cells == 0) return FEM_OK;
+  Hex27Args A{};
+  A.points = points; A.cells = cells; A.sol = sol; A.iv = internal_var; A.ref = ref_tables;
+  A.corner_pos = corner_pos; A.Ke = Ke; A.Re = Re; A.C = n_cells; A.nq = n_quad; A.law = law_id;
+  for (int i = 0; i < 8; ++i) A.p[i] = law_params_host[i];
+  const int nq_pad = (n_quad + H27_QC - 1) / H27_QC * H27_QC;
+  const size_t work = (size_t)nq_pad * H27_QP + (nq_pad * H27_QP) % 2 + H27_QC * H27_GS;
+  const size_t gsz = (size_t)88 * H27_GSS;
+  const size_t smem = sizeof(double) * (3 * H27_ND + 1 + (work > gsz ? work : gsz));
+  FEM_CUDA_CHECK(cudaFuncSetAttribute(hex27_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  hex27_kernel<<<(unsigned)n_cells, H27_THREADS, smem, (cudaStream_t)stream>>>(A);
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
+}

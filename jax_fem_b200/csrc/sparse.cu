@@ -42,8 +42,8 @@ namespace {
 //            (cell, a, b) order -- the same fixed order on every run => bit-reproducible, no atomics.
 // Dirichlet rows become unit rows with the pattern kept (zeroRows, solver.py:527-528).
 constexpr int kGatherThreads = 128;
-constexpr int kGatherCorners = 32;      // corners per CTA (4 interior HEX8 nodes)
-constexpr int kGatherTail = 16;         // max corners of one node (checked when the plan is built)
+// corners per work item / max corners of one node (checked when the plan is built; mirrored by plan.py::gather_config)
+template <int NN> struct GatherCfg { static constexpr int CORNERS = NN <= 8 ? 32 : 8, TAIL = NN <= 8 ? 16 : 8; };
 
 // Per-item metadata a thread keeps in registers (prefetched one work item ahead).
 template <int EPT, int SPT>
@@ -59,8 +59,8 @@ __global__ void __launch_bounds__(kGatherThreads) gather_csr_kernel(
     const int32_t* __restrict__ src_ptr, const int32_t* __restrict__ src, const int32_t* __restrict__ edst,
     const int32_t* __restrict__ einfo, const double* __restrict__ Ke, double* __restrict__ data) {
   constexpr int VV = VEC * VEC;
-  constexpr int ROW = NN * VV;                                    // doubles per corner row block
-  constexpr int MAXC = kGatherCorners + kGatherTail;
+  constexpr int ROW = (NN * VV + 1) / 2 * 2;                      // doubles per corner row block (16-byte multiple)
+  constexpr int MAXC = GatherCfg<NN>::CORNERS + GatherCfg<NN>::TAIL;
   constexpr int MAXS = MAXC * NN;                                 // sources (blocks) of an item
   constexpr int EPT = (MAXS + kGatherThreads - 1) / kGatherThreads;   // entries / sources per thread (worst case)
   static_assert(ROW % 2 == 0, "row blocks must be 16-byte multiples");
@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(kGatherThreads) gather_csr_kernel(
 #pragma unroll
       for (int j = 0; j < VV; ++j) res[r][j] = 0.0;
       for (int sidx = cur.sb[r]; sidx < cur.se[r]; ++sidx) {
-        const double* blk = sh + s_off[sidx] * VV;
+        const int so = s_off[sidx];
+        const double* blk = (ROW == NN * VV) ? sh + so * VV : sh + (so / NN) * ROW + (so % NN) * VV;
 #pragma unroll
         for (int j = 0; j < VV; ++j) res[r][j] += blk[j];
       }
@@ -315,8 +316,9 @@ namespace {
 template <int VEC, int NN>
 int launch_gather(int n_items, const int32_t* gdesc, const int32_t* eorder, const int32_t* src_ptr, const int32_t* src,
                   const int32_t* edst, const int32_t* einfo, const double* Ke, double* data, cudaStream_t st) {
-  constexpr int MAXC = kGatherCorners + kGatherTail;
-  const size_t smem = sizeof(double) * 2 * MAXC * NN * VEC * VEC + sizeof(int) * MAXC * NN;
+  constexpr int MAXC = GatherCfg<NN>::CORNERS + GatherCfg<NN>::TAIL;
+  constexpr int ROW = (NN * VEC * VEC + 1) / 2 * 2;
+  const size_t smem = sizeof(double) * 2 * MAXC * ROW + sizeof(int) * MAXC * NN;
   auto k = gather_csr_kernel<VEC, NN>;
   static int grid = 0;                      // persistent grid: resident CTAs x SMs (per template instance)
   if (!grid) {
@@ -345,7 +347,7 @@ extern "C" int fem_gather_csr(int vec, int nn, int64_t n_blocks, const int32_t* 
   if (vec == V && nn == N) {                                                                                         \
     return launch_gather<V, N>((int)n_blocks, gdesc, eorder, src_ptr, src, edst, einfo, Ke, data, st);              \
   }
-  FEM_G(3, 8) FEM_G(1, 8) FEM_G(1, 4) FEM_G(2, 4)
+  FEM_G(3, 8) FEM_G(1, 8) FEM_G(1, 4) FEM_G(2, 4) FEM_G(3, 27)
 #undef FEM_G
   set_error("fem_gather_csr: unregistered (vec=%d, nodes/cell=%d)", vec, nn);
   return FEM_EINVAL;

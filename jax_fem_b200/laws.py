@@ -88,6 +88,7 @@ class SIMP(Law):
 REGISTERED = {
     ('HEX8', 1, Poisson), ('HEX8', 3, LinearElasticity), ('HEX8', 3, NeoHookean), ('HEX8', 3, SIMP),
     ('QUAD4', 1, Poisson), ('QUAD4', 2, LinearElasticity), ('QUAD4', 2, SIMP),
+    ('HEX27', 3, LinearElasticity), ('HEX27', 3, SIMP),
 }
 
 

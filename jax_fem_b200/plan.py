@@ -46,8 +46,15 @@ class AssemblyPlan:
     erow: torch.Tensor = None          # row node of every entry (int32)
     _tperm: torch.Tensor = None
 
-    GATHER_CORNERS = 32                # csrc/sparse.cu::kGatherCorners
-    GATHER_TAIL = 16                   # csrc/sparse.cu::kGatherTail
+    @staticmethod
+    def gather_config(nodes_per_cell):
+        """(corners per work item, max corners of one node) -- csrc/sparse.cu::GatherCfg."""
+        return (32, 16) if nodes_per_cell <= 8 else (8, 8)
+
+    @property
+    def row_block(self):
+        """Doubles per corner row block in the element-tangent buffer (padded to a 16-byte multiple)."""
+        return (self.nodes_per_cell * self.vec * self.vec + 1) // 2 * 2
 
     @property
     def n_items(self):
@@ -164,19 +171,20 @@ def build_plan(cells, num_nodes, vec):
     indptr, indices = expand_scalar_pattern(brow_ptr, bcol, vec)
     # gather work decomposition (csrc/sparse.cu::gather_csr_kernel): CTA b owns the nodes whose first corner is in
     # [32 b, 32 (b+1)); their corners / entries / sources are contiguous ranges
+    width, tail = AssemblyPlan.gather_config(N)
     deg = nc_ptr[1:] - nc_ptr[:-1]
-    if deg.numel() and int(deg.max()) > AssemblyPlan.GATHER_TAIL:
-        raise ValueError(f"a node belongs to {int(deg.max())} cells (> {AssemblyPlan.GATHER_TAIL}): mesh valence too high")
+    if deg.numel() and int(deg.max()) > tail:
+        raise ValueError(f"a node belongs to {int(deg.max())} cells (> {tail}): mesh valence too high")
     n_corners = int(nc.numel())
-    n_blocks = (n_corners + AssemblyPlan.GATHER_CORNERS - 1) // AssemblyPlan.GATHER_CORNERS
-    starts = torch.arange(n_blocks + 1, device=dev, dtype=torch.int64) * AssemblyPlan.GATHER_CORNERS
+    n_blocks = (n_corners + width - 1) // width
+    starts = torch.arange(n_blocks + 1, device=dev, dtype=torch.int64) * width
     node0 = torch.searchsorted(nc_ptr[:-1].long().contiguous(), starts)            # first node of every CTA
     ent0 = brow_ptr.long()[node0]
     gdesc = torch.stack([nc_ptr.long()[node0], ent0, src_ptr.long()[ent0], torch.zeros_like(ent0)], dim=1)
     gdesc = gdesc.reshape(-1).to(torch.int32)
     # balanced processing order: inside a CTA, entries sorted by descending source count (stable)
     cta_of_entry = torch.searchsorted(ent0[1:].contiguous(), torch.arange(bcol.numel(), device=dev), right=True)
-    key = cta_of_entry * (AssemblyPlan.GATHER_TAIL * 4) + (AssemblyPlan.GATHER_TAIL * 4 - 1 - counts)
+    key = cta_of_entry * 64 + (63 - counts.clamp(max=63))
     eorder = torch.sort(key, stable=True)[1].to(torch.int32)
     del cta_of_entry, key
     lens = (brow_ptr[1:] - brow_ptr[:-1]).long()

@@ -212,21 +212,31 @@ class Problem:
     def _run_element_kernel(self, sol, jac):
         fe = self.fes[0]
         if jac and self._Ke is None:
-            # one (N, vec, vec) row block per corner (cell, a), stored in the plan's node-sorted corner order
-            self._Ke = torch.empty((self.num_cells * fe.num_nodes, fe.num_nodes, fe.vec, fe.vec),
-                                   dtype=torch.float64, device=self.device)
+            # one row block (N blocks of vec x vec, padded to an even number of doubles) per corner (cell, a),
+            # stored in the plan's node-sorted corner order
+            self._Ke = torch.empty((self.num_cells * fe.num_nodes, self.plan.row_block), dtype=torch.float64,
+                                   device=self.device)
         iv = self._internal_var()
         lib = _lib.load()
-        _lib.check(lib.fem_element_residual_jacobian(
-            _lib.ELE[self.ele_type], fe.vec, self._law.law_id, _lib.host_doubles(self._law.params()),
-            _lib.ptr(self._points), _lib.ptr(self._cells), self.num_cells, _lib.ptr(sol), _lib.ptr(iv),
-            _lib.ptr(self._ref), _lib.ptr(self.plan.corner_pos), _lib.ptr(self._Ke) if jac else None,
-            _lib.ptr(self._Re), _lib.stream_ptr()))
+        if self.ele_type == 'HEX27':
+            _lib.check(lib.fem_hex27_residual_jacobian(
+                self._law.law_id, _lib.host_doubles(self._law.params()), _lib.ptr(self._points), _lib.ptr(self._cells),
+                self.num_cells, _lib.ptr(sol), _lib.ptr(iv), _lib.ptr(self._ref), fe.num_quads,
+                _lib.ptr(self.plan.corner_pos), _lib.ptr(self._Ke) if jac else None, _lib.ptr(self._Re), _lib.stream_ptr()))
+        else:
+            self._launch_element(lib, fe, sol, iv, jac)
         res = torch.empty((fe.num_total_nodes, fe.vec), dtype=torch.float64, device=self.device)
         p = self.plan
         _lib.check(lib.fem_gather_residual(fe.vec, fe.num_nodes, fe.num_total_nodes, _lib.ptr(p.nc_ptr), _lib.ptr(p.nc),
                                            _lib.ptr(self._Re), _lib.ptr(self._f_ext), _lib.ptr(res), _lib.stream_ptr()))
         return res
+
+    def _launch_element(self, lib, fe, sol, iv, jac):
+        _lib.check(lib.fem_element_residual_jacobian(
+            _lib.ELE[self.ele_type], fe.vec, self._law.law_id, _lib.host_doubles(self._law.params()),
+            _lib.ptr(self._points), _lib.ptr(self._cells), self.num_cells, _lib.ptr(sol), _lib.ptr(iv),
+            _lib.ptr(self._ref), _lib.ptr(self.plan.corner_pos), _lib.ptr(self._Ke) if jac else None,
+            _lib.ptr(self._Re), _lib.stream_ptr()))
 
     def compute_residual(self, sol_list):
         """sol_list: [ (num_total_nodes, vec) ] -> res_list of the same shapes (problem.py:462-475)."""
@@ -243,7 +253,7 @@ class Problem:
             raise AttributeError("element tangents are defined after newton_update()")
         fe = self.fes[0]
         N, v = fe.num_nodes, fe.vec
-        rows = self._Ke[self.plan.corner_pos.long()]                             # (C*N, N, v, v) in (c, a) order
+        rows = self._Ke[self.plan.corner_pos.long()][:, :N * v * v]              # (C*N, N*v*v) in (c, a) order
         return rows.reshape(self.num_cells, N, N, v, v).permute(0, 1, 3, 2, 4).reshape(self.num_cells, N * v, N * v)
 
     @property

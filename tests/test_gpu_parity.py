@@ -287,3 +287,46 @@ def test_unregistered_paths_raise():
         jf.solver(ok, {'petsc_solver': {}})
     with pytest.raises(NotImplementedError):
         jf.solver(ok, {'arc_length': {}})
+
+
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("order", [None, 4])
+def test_hex27_dmma_element_assembly_and_solve(order):
+    """BASELINE.json configs[3]: second-order HEX27 linear elasticity (81x81 element tangents on FP64 DMMA tiles);
+    default quadrature degree 10 (216 points, basis.py:64) and the 27-point variant."""
+    import jax_fem_b200 as jf
+    import gpu_problems as gp
+    m = jf.box_mesh_hex27(3, 2, 2, 1.5, 1.0, 0.8)
+    pts, cells = m.points.copy(), m.cells_dict['hexahedron27']
+    rng = np.random.default_rng(5)
+    pts += 0.02 * rng.uniform(-1, 1, pts.shape)                      # curved, non-affine cells
+    left = lambda p: p[0] < 0.03
+    right = lambda p: p[0] > 1.47
+    bc = [[left] * 3, [0, 1, 2], [lambda p: 0., lambda p: 0.01, lambda p: 0.]]
+
+    class Elast27(jf.Problem):
+        def get_tensor_map(self):
+            return jf.laws.LinearElasticity(70e3, 0.3)
+
+        def get_surface_maps(self):
+            return [lambda u, x: np.array([0., 0., -50.])]
+
+    prob = Elast27(jf.Mesh(pts, cells), vec=3, dim=3, ele_type='HEX27', quadrature_order=order,
+                   dirichlet_bc_info=bc, location_fns=[right])
+    opb = fem.Problem(fem.Mesh(pts, cells), 3, 3, ele_type='HEX27', quadrature_order=order, dirichlet_bc_info=bc,
+                      location_fns=[right], law=olaws.LinearElastic(70e3, 0.3),
+                      surface_maps=[lambda u, x: np.array([0., 0., -50.]) + 0. * u])
+    assert prob.fes[0].num_quads == (216 if order is None else 27)
+    sol = 1e-3 * rng.standard_normal((len(pts), 3))
+    res = prob.newton_update([torch.from_numpy(sol).cuda()])[0]
+    ores = opb.newton_update(sol)
+    assert relmax(host(prob.element_tangents()), opb.cell_jacobians(sol)) <= VAL_TOL
+    assert relmax(host(res), ores) <= VAL_TOL
+    A = jf.get_A(prob)
+    oA = fem.get_A(opb)
+    indptr, indices, data = [host(t) for t in A.getValuesCSR()]
+    assert np.array_equal(indptr, oA.indptr) and np.array_equal(indices, oA.indices)
+    assert relmax(data, oA.data) <= VAL_TOL
+    usol = host(jf.solver(prob, {'jax_solver': {'method': 'cg'}})[0])
+    osol = fem.solver(opb, method='cg')
+    assert relmax(usol, osol) <= SOL_TOL
