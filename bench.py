@@ -173,7 +173,7 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------
-def problem_class():
+def problem_class(workload="elasticity"):
     import jax_fem_b200 as jf
     from jax_fem_b200 import laws
 
@@ -184,22 +184,33 @@ def problem_class():
         def get_surface_maps(self):
             return [lambda u, x: np.array([0., 0., 100.])]
 
-    return Elasticity
+    class NeoHookean(jf.Problem):             # applications/scalability/hyperelastic3d_common.py:15-42 (cfg 3 law)
+        def get_tensor_map(self):
+            return laws.NeoHookean(10.0, 0.3)
+
+        def get_surface_maps(self):
+            return [lambda u, x: np.array([0., 1e-3, 0.])]
+
+    return NeoHookean if workload == "neohookean" else Elasticity
 
 
-def build_problem(size, world=1, comm=None):
+def build_problem(size, world=1, comm=None, workload="elasticity"):
     """cfg 2 on one GPU; for N GPUs the box is N times longer in x (weak scaling: size^3 cells per rank) and its
     cells are sharded in x-slabs with one ghost layer (jax_fem_b200/distributed.py).  Returns (problem, sharded)."""
     import jax_fem_b200 as jf
     Lx = float(world)
-    m = jf.box_mesh(size * world, size, size, Lx, 1., 1.)
+    hex27 = workload == "hex27"
+    m = (jf.box_mesh_hex27 if hex27 else jf.box_mesh)(size * world, size, size, Lx, 1., 1.)
+    cells = m.cells_dict['hexahedron27' if hex27 else 'hexahedron']
+    ele = 'HEX27' if hex27 else 'HEX8'
     left = lambda p: np.isclose(p[0], 0., atol=1e-5)
     right = lambda p: np.isclose(p[0], Lx, atol=1e-5)
-    kw = dict(dirichlet_bc_info=[[left] * 3, [0, 1, 2], [lambda p: 0.] * 3], location_fns=[right])
+    kw = dict(dirichlet_bc_info=[[left] * 3, [0, 1, 2], [lambda p: 0.] * 3], location_fns=[right], ele_type=ele)
+    cls = problem_class(workload)
     if world == 1:
-        return problem_class()(jf.Mesh(m.points, m.cells_dict['hexahedron']), vec=3, dim=3, **kw), None
+        return cls(jf.Mesh(m.points, cells), vec=3, dim=3, **kw), None
     from jax_fem_b200.distributed import ShardedProblem
-    sp = ShardedProblem(problem_class(), m.points, m.cells_dict['hexahedron'], comm, vec=3, dim=3, **kw)
+    sp = ShardedProblem(cls, m.points, cells, comm, vec=3, dim=3, **kw)
     return sp.problem, sp
 
 
@@ -213,6 +224,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--solve", action="store_true", help="also time a full Jacobi-CG solve")
+    ap.add_argument("--workload", default="elasticity", choices=["elasticity", "neohookean", "hex27"],
+                    help="elasticity = cfg 2 (the headline, default); neohookean = cfg 3's law on the same mesh; "
+                         "hex27 = cfg 4 (use --size 60)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -241,14 +255,15 @@ def main():
     if world > 1:
         from jax_fem_b200.distributed import TorchDistComm
         comm = TorchDistComm()
-    prob, sharded = build_problem(args.size, world, comm)
+    prob, sharded = build_problem(args.size, world, comm, args.workload)
     setup_s = time.perf_counter() - t0
     fe = prob.fes[0]
     n_local, nnz = prob.num_total_dofs_all_vars, prob.plan.nnz
     n = sharded.n_owned if sharded else n_local               # dofs this rank owns (what it is credited for)
     log(f"problem built in {setup_s:.1f}s: {n} owned dofs (+{n_local - n} ghost), local nnz {prob.plan.nnz}")
     own_frac = n / n_local
-    b_asm, b_spmv = algorithmic_bytes(n, int(nnz * own_frac), int(prob.num_cells * own_frac), int(fe.num_total_nodes * own_frac))
+    b_asm, b_spmv = algorithmic_bytes(n, int(nnz * own_frac), int(prob.num_cells * own_frac), int(fe.num_total_nodes * own_frac),
+                                      nodes_per_cell=fe.num_nodes)
     rng = np.random.default_rng(rank)
     sol_host = torch.from_numpy(1e-3 * rng.standard_normal((fe.num_total_nodes, 3))).pin_memory()
     sol = sol_host.to(dev)
@@ -372,7 +387,9 @@ def main():
             "metric": "assembled DOFs/s (residual+Jacobian), HEX8 linear elasticity", "value": value, "unit": "DOF/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"HEX8 box {args.size * world}x{args.size}x{args.size} linear elasticity E=70e3 nu=0.3, u=0 on x=0, "
+            "config": {"workload": {"neohookean": "[NON-HEADLINE: Neo-Hookean E=10 nu=0.3] ", "hex27": "[NON-HEADLINE: HEX27, 216-point quadrature] ",
+                                    "elasticity": ""}[args.workload] +
+                                   f"HEX8 box {args.size * world}x{args.size}x{args.size} linear elasticity E=70e3 nu=0.3, u=0 on x=0, "
                                    f"traction on x=Lx (cfg 2{'' if world == 1 else ' extended in x: weak scaling'})",
                        "n_dofs_total": n_total, "n_dofs_per_gpu": n, "nnz_per_gpu": int(nnz * own_frac), "cells_per_gpu": int(prob.num_cells * own_frac),
                        "per_gpu": "whole mesh" if world == 1 else f"x-slab of {args.size}^3 cells + 1 ghost cell layer per interface; "
