@@ -113,8 +113,11 @@ int fem_bc_initial_guess(int64_t n, int64_t n_bc, const int32_t* bc_rows, const 
                          const double* dofs, double* x0, void* stream);
 
 /* ---- (3) sparse kernels and Krylov solvers: jax_solve (jax_fem/solver.py:63-92)               */
-int fem_spmv(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
-             const double* x, double* y, void* stream);
+/* Optional node-block structure (vec, brow_ptr, bcol) of the FE matrix: when given (vec = 2 or 3) the kernels walk
+ * the neighbour list of a mesh node once for its vec scalar rows and read one column index per vec x vec block
+ * instead of `indices` (same result up to summation order); pass vec = 1 / NULL for a general CSR matrix.       */
+int fem_spmv(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data, int vec,
+             const int32_t* brow_ptr, const int32_t* bcol, const double* x, double* y, void* stream);
 /* diag[i] = A[i,i] (jacobi = A.diagonal(), solver.py:68)                                          */
 int fem_csr_diagonal(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
                      double* diag, void* stream);
@@ -132,12 +135,13 @@ int64_t fem_krylov_workspace(int64_t n);
  * info_host[0] = iterations (negative on breakdown as in JAX), info_host[1] = final ||r||^2,
  * info_host[2] = ||A x - b|| (the reference's post-check, solver.py:87).
  * check_every: iterations between host polls of the device-side convergence flag.               */
-int fem_pcg(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
-            const double* diag, const double* b, double* x, double tol, double atol, int maxiter,
-            int check_every, double* workspace, double* info_host, void* stream);
-int fem_pbicgstab(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
-                  const double* diag, const double* b, double* x, double tol, double atol, int maxiter,
-                  int check_every, double* workspace, double* info_host, void* stream);
+int fem_pcg(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data, int vec,
+            const int32_t* brow_ptr, const int32_t* bcol, const double* diag, const double* b, double* x,
+            double tol, double atol, int maxiter, int check_every, double* workspace, double* info_host, void* stream);
+int fem_pbicgstab(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data, int vec,
+                  const int32_t* brow_ptr, const int32_t* bcol, const double* diag, const double* b, double* x,
+                  double tol, double atol, int maxiter, int check_every, double* workspace, double* info_host,
+                  void* stream);
 
 /* ---- (e) multi-GPU: one rank's share of the Jacobi-CG above (cells sharded across ranks).
  *      Vectors hold the rank's owned dofs first, then its ghosts.  Every kernel leaves rank-local partial sums in
@@ -148,7 +152,8 @@ int fem_pbicgstab(int64_t n, const int32_t* indptr, const int32_t* indices, cons
  *      workspace[7] != 0 once converged (same stopping rule as fem_pcg); workspace[6] = iterations.            */
 int fem_dcg_begin(double* workspace, double tol, double atol, int maxiter, void* stream);
 int fem_dcg_spmv_dot(int64_t n_owned, int64_t n_local, const int32_t* indptr, const int32_t* indices,
-                     const double* data, const double* p, double* q, int with_dot, double* workspace, void* stream);
+                     const double* data, int vec, const int32_t* brow_ptr, const int32_t* bcol,
+                     const double* p, double* q, int with_dot, double* workspace, void* stream);
 int fem_dcg_init(int64_t n_owned, int64_t n_local, const double* b, const double* diag, const double* q,
                  double* r, double* p, double* workspace, void* stream);
 int fem_dcg_scalars(int phase, double* workspace, void* stream);

@@ -26,16 +26,16 @@ _SIGNATURES = {
     "fem_gather_residual": (_i, [_i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fem_apply_bc_vec": (_i, [_i64, _vp, _vp, _d, _vp, _vp, _vp]),
     "fem_bc_initial_guess": (_i, [_i64, _i64, _vp, _vp, _vp, _vp, _vp]),
-    "fem_spmv": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fem_spmv": (_i, [_i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "fem_csr_diagonal": (_i, [_i64, _vp, _vp, _vp, _vp, _vp]),
     "fem_csr_transpose_values": (_i, [_i, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fem_krylov_workspace": (_i64, [_i64]),
-    "fem_pcg": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _vp, _vp, _vp]),
-    "fem_pbicgstab": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _vp, _vp, _vp]),
+    "fem_pcg": (_i, [_i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _vp, _vp, _vp]),
+    "fem_pbicgstab": (_i, [_i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _vp, _vp, _vp]),
     "fem_adjoint_param_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fem_dot": (_i, [_i64, _vp, _vp, _vp, _vp, _vp]),
     "fem_dcg_begin": (_i, [_vp, _d, _d, _i, _vp]),
-    "fem_dcg_spmv_dot": (_i, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "fem_dcg_spmv_dot": (_i, [_i64, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "fem_dcg_init": (_i, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fem_dcg_scalars": (_i, [_i, _vp, _vp]),
     "fem_dcg_update": (_i, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -19,7 +19,7 @@ int launch_spmv(int64_t n, const int32_t* indptr, const int32_t* indices, const 
 
 namespace {
 
-constexpr int kBlocks = kNumSM * 8;   // upper bound of any persistent grid (sizes the partial buffer)
+constexpr int kBlocks = kNumSM * 16;  // upper bound of any persistent grid (sizes the partial buffer)
 constexpr int kThreads = 256;
 constexpr int kScalars = 64;
 constexpr int kMaxDots = 4;
@@ -153,6 +153,78 @@ __global__ void __launch_bounds__(kThreads) spmv_fused_kernel(int64_t n, const i
   } else if constexpr (MODE == 3) {
     reduce_and_finalize<2>(dots, S, partial, [&](double (&t)[2]) { S[S_OMEGA] = t[0] / t[1]; });
   } else if constexpr (MODE == 4) {   // distributed CG: rank-local p.Ap, all-reduced by the caller
+    double v[1] = {dots[0]};
+    reduce_and_finalize<1>(v, S, partial, [&](double (&t)[1]) { S[S_SUM0] = t[0]; });
+  }
+}
+
+
+// Same contract on the NODE-BLOCK structure of the FE matrix: the VEC scalar rows of a mesh node share one column
+// pattern (VEC consecutive columns per neighbour node), so LPN lanes walk the node's neighbour list once, read ONE
+// column index per VEC x VEC block (4/9 instead of 4 index bytes per nonzero for VEC = 3), gather VEC consecutive
+// entries of x and stream the VEC row segments at full width.  `indices` is not read at all.
+template <int VEC, int LPN, int MODE>
+__global__ void __launch_bounds__(kThreads) spmv_block_fused_kernel(int64_t n_nodes, const int32_t* __restrict__ brow_ptr,
+                                                                    const int32_t* __restrict__ bcol,
+                                                                    const double* __restrict__ data,
+                                                                    const double* __restrict__ x, double* __restrict__ y,
+                                                                    const double* __restrict__ d1, double* __restrict__ S,
+                                                                    double* __restrict__ partial) {
+  if (MODE != 0 && solver_done(S)) return;
+  constexpr int NPB = kThreads / LPN;
+  constexpr int VV = VEC * VEC;
+  const int sub = threadIdx.x % LPN;
+  double dots[2] = {0.0, 0.0};
+  for (int64_t base = (int64_t)blockIdx.x * NPB; base < n_nodes; base += (int64_t)gridDim.x * NPB) {
+    const int64_t nd = base + threadIdx.x / LPN;
+    const bool valid = nd < n_nodes;
+    double acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.0;
+    if (valid) {
+      const int e0 = brow_ptr[nd], len = brow_ptr[nd + 1] - e0;
+      const double* rowp = data + (int64_t)VV * e0;
+      const int32_t* colp = bcol + e0;
+#pragma unroll 2
+      for (int s = sub; s < len; s += LPN) {
+        const int64_t m = colp[s];
+        double xv[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) xv[k] = __ldg(x + VEC * m + k);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const double* d = rowp + (int64_t)i * VEC * len + VEC * s;
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) acc[i] = fma(d[k], xv[k], acc[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+#pragma unroll
+      for (int o = LPN / 2; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    if (valid && sub == 0) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const int64_t row = VEC * nd + i;
+        y[row] = acc[i];
+        if (MODE == 1 || MODE == 2 || MODE == 4) dots[0] = fma(d1[row], acc[i], dots[0]);
+        if (MODE == 3) {
+          dots[0] = fma(acc[i], d1[row], dots[0]);
+          dots[1] = fma(acc[i], acc[i], dots[1]);
+        }
+      }
+    }
+  }
+  if constexpr (MODE == 1) {
+    double v[1] = {dots[0]};
+    reduce_and_finalize<1>(v, S, partial, [&](double (&t)[1]) { S[S_ALPHA] = S[S_GAMMA] / t[0]; });
+  } else if constexpr (MODE == 2) {
+    double v[1] = {dots[0]};
+    reduce_and_finalize<1>(v, S, partial, [&](double (&t)[1]) { S[S_ALPHA] = S[S_RHO_NEW] / t[0]; });
+  } else if constexpr (MODE == 3) {
+    reduce_and_finalize<2>(dots, S, partial, [&](double (&t)[2]) { S[S_OMEGA] = t[0] / t[1]; });
+  } else if constexpr (MODE == 4) {
     double v[1] = {dots[0]};
     reduce_and_finalize<1>(v, S, partial, [&](double (&t)[1]) { S[S_SUM0] = t[0]; });
   }
@@ -427,10 +499,30 @@ int persistent_grid(K kernel) {
 }
 #define FEM_PGRID(kernel) persistent_grid(kernel), kThreads, 0, st
 
+// CSR operand; with vec > 1 and the node-block graph (brow_ptr, bcol) the block kernel is used and `indices` is unread.
+struct Mat {
+  int64_t n;
+  const int32_t* indptr;
+  const int32_t* indices;
+  const double* data;
+  int vec;
+  const int32_t* brow_ptr;
+  const int32_t* bcol;
+};
+
 template <int MODE>
-void spmv_fused(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data, const double* x,
-                double* y, const double* d1, const Ws& w, cudaStream_t st) {
-  spmv_fused_kernel<kLPR, MODE><<<FEM_PGRID((spmv_fused_kernel<kLPR, MODE>))>>>(n, indptr, indices, data, x, y, d1, w.s, w.partial);
+void spmv_fused(const Mat& A, const double* x, double* y, const double* d1, const Ws& w, cudaStream_t st) {
+  constexpr int LPN = 8;
+  if (A.brow_ptr && A.bcol && A.vec == 3) {
+    spmv_block_fused_kernel<3, LPN, MODE><<<FEM_PGRID((spmv_block_fused_kernel<3, LPN, MODE>))>>>(
+        A.n / 3, A.brow_ptr, A.bcol, A.data, x, y, d1, w.s, w.partial);
+  } else if (A.brow_ptr && A.bcol && A.vec == 2) {
+    spmv_block_fused_kernel<2, LPN, MODE><<<FEM_PGRID((spmv_block_fused_kernel<2, LPN, MODE>))>>>(
+        A.n / 2, A.brow_ptr, A.bcol, A.data, x, y, d1, w.s, w.partial);
+  } else {
+    spmv_fused_kernel<kLPR, MODE><<<FEM_PGRID((spmv_fused_kernel<kLPR, MODE>))>>>(A.n, A.indptr, A.indices, A.data, x, y,
+                                                                                 d1, w.s, w.partial);
+  }
 }
 
 int init_scalars(const Ws& w, double tol, double atol, int maxiter, cudaStream_t st) {
@@ -443,14 +535,15 @@ int init_scalars(const Ws& w, double tol, double atol, int maxiter, cudaStream_t
   return FEM_OK;
 }
 
-int finish(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data, const double* b,
-           const double* x, const Ws& w, double* scratch, double* info_host, cudaStream_t st) {
+int finish(const Mat& A, const double* b, const double* x, const Ws& w, double* scratch, double* info_host,
+           cudaStream_t st) {
+  const int64_t n = A.n;
   double h[kScalars];
   FEM_CUDA_CHECK(cudaMemcpyAsync(h, w.s, sizeof(h), cudaMemcpyDeviceToHost, st));
   FEM_CUDA_CHECK(cudaStreamSynchronize(st));
   info_host[0] = h[S_K];
   info_host[1] = h[S_RR];
-  spmv_fused<0>(n, indptr, indices, data, x, scratch, nullptr, w, st);
+  spmv_fused<0>(A, x, scratch, nullptr, w, st);
   resnorm_kernel<<<FEM_PGRID(resnorm_kernel)>>>(n, scratch, b, w.s, w.partial);
   FEM_LAUNCH_CHECK();
   FEM_CUDA_CHECK(cudaMemcpyAsync(h, w.s, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -470,53 +563,73 @@ int poll_done(const Ws& w, bool* done, cudaStream_t st) {
 }  // namespace
 }  // namespace femb200
 
+namespace femb200 {
+// plain y = A x on the node-block structure (non-persistent: one node row block per LPN lanes)
+int launch_spmv_block(int64_t n, int vec, const int32_t* brow_ptr, const int32_t* bcol, const double* data,
+                      const double* x, double* y, cudaStream_t st) {
+  constexpr int LPN = 8;
+  const int64_t n_nodes = n / vec;
+  const unsigned grid = (unsigned)((n_nodes * LPN + kThreads - 1) / kThreads);
+  if (vec == 3)
+    spmv_block_fused_kernel<3, LPN, 0><<<grid, kThreads, 0, st>>>(n_nodes, brow_ptr, bcol, data, x, y, nullptr, nullptr, nullptr);
+  else
+    spmv_block_fused_kernel<2, LPN, 0><<<grid, kThreads, 0, st>>>(n_nodes, brow_ptr, bcol, data, x, y, nullptr, nullptr, nullptr);
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
+}
+}  // namespace femb200
+
 using namespace femb200;
 
 extern "C" int64_t fem_krylov_workspace(int64_t n) {
   return kScalars + (int64_t)kBlocks * kMaxDots + 8 * pad_n(n);
 }
 
-extern "C" int fem_pcg(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
-                       const double* diag, const double* b, double* x, double tol, double atol, int maxiter,
-                       int check_every, double* workspace, double* info_host, void* stream) {
+extern "C" int fem_pcg(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data, int vec,
+                       const int32_t* brow_ptr, const int32_t* bcol, const double* diag, const double* b, double* x,
+                       double tol, double atol, int maxiter, int check_every, double* workspace, double* info_host,
+                       void* stream) {
   if (int e = check_device()) return e;
   FEM_REQUIRE(indptr && indices && data && b && x && workspace && info_host, "null pointer");
   FEM_REQUIRE(n > 0 && maxiter >= 0, "bad size");
   cudaStream_t st = (cudaStream_t)stream;
   if (check_every <= 0) check_every = 25;
   const Ws w = carve(workspace, n);
+  const Mat A{n, indptr, indices, data, vec, brow_ptr, bcol};
   double *r = w.v[0], *p = w.v[1], *q = w.v[2];
   if (int e = init_scalars(w, tol, atol, maxiter, st)) return e;
-  spmv_fused<0>(n, indptr, indices, data, x, q, nullptr, w, st);
+  spmv_fused<0>(A, x, q, nullptr, w, st);
   cg_init_kernel<<<FEM_PGRID(cg_init_kernel)>>>(n, b, diag, q, r, p, w.s, w.partial);
   FEM_LAUNCH_CHECK();
   bool done = false;
   if (int e = poll_done(w, &done, st)) return e;
   for (int it = 0; !done && it < maxiter; it += check_every) {
     for (int j = 0; j < check_every; ++j) {
-      spmv_fused<1>(n, indptr, indices, data, p, q, p, w, st);                 // q = A p ; alpha
+      spmv_fused<1>(A, p, q, p, w, st);                                        // q = A p ; alpha
       cg_update_kernel<<<FEM_PGRID(cg_update_kernel)>>>(n, diag, p, q, x, r, w.s, w.partial);
       cg_direction_kernel<<<FEM_PGRID(cg_direction_kernel)>>>(n, diag, r, p, w.s);
     }
     FEM_LAUNCH_CHECK();
     if (int e = poll_done(w, &done, st)) return e;
   }
-  return finish(n, indptr, indices, data, b, x, w, q, info_host, st);
+  return finish(A, b, x, w, q, info_host, st);
 }
 
-extern "C" int fem_pbicgstab(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
-                             const double* diag, const double* b, double* x, double tol, double atol, int maxiter,
-                             int check_every, double* workspace, double* info_host, void* stream) {
+extern "C" int fem_pbicgstab(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data, int vec,
+                             const int32_t* brow_ptr, const int32_t* bcol, const double* diag, const double* b, double* x,
+                             double tol, double atol, int maxiter, int check_every, double* workspace,
+                             double* info_host, void* stream) {
   if (int e = check_device()) return e;
   FEM_REQUIRE(indptr && indices && data && b && x && workspace && info_host, "null pointer");
   FEM_REQUIRE(n > 0 && maxiter >= 0, "bad size");
   cudaStream_t st = (cudaStream_t)stream;
   if (check_every <= 0) check_every = 25;
   const Ws w = carve(workspace, n);
+  const Mat A{n, indptr, indices, data, vec, brow_ptr, bcol};
   double *r = w.v[0], *rhat = w.v[1], *p = w.v[2], *q = w.v[3], *s = w.v[4], *t = w.v[5], *phat = w.v[6],
          *shat = w.v[7];
   if (int e = init_scalars(w, tol, atol, maxiter, st)) return e;
-  spmv_fused<0>(n, indptr, indices, data, x, t, nullptr, w, st);
+  spmv_fused<0>(A, x, t, nullptr, w, st);
   bicg_init_kernel<<<FEM_PGRID(bicg_init_kernel)>>>(n, b, t, r, rhat, p, q, w.s, w.partial);
   FEM_LAUNCH_CHECK();
   bool done = false;
@@ -524,15 +637,15 @@ extern "C" int fem_pbicgstab(int64_t n, const int32_t* indptr, const int32_t* in
   for (int it = 0; !done && it < maxiter; it += check_every) {
     for (int j = 0; j < check_every; ++j) {
       bicg_p_kernel<<<FEM_PGRID(bicg_p_kernel)>>>(n, diag, r, q, p, phat, w.s);
-      spmv_fused<2>(n, indptr, indices, data, phat, q, rhat, w, st);           // q = A phat ; alpha
+      spmv_fused<2>(A, phat, q, rhat, w, st);                                  // q = A phat ; alpha
       bicg_s_kernel<<<FEM_PGRID(bicg_s_kernel)>>>(n, diag, r, q, s, shat, w.s, w.partial);
-      spmv_fused<3>(n, indptr, indices, data, shat, t, s, w, st);              // t = A shat ; omega
+      spmv_fused<3>(A, shat, t, s, w, st);                                     // t = A shat ; omega
       bicg_x_kernel<<<FEM_PGRID(bicg_x_kernel)>>>(n, phat, shat, s, t, rhat, x, r, w.s, w.partial);
     }
     FEM_LAUNCH_CHECK();
     if (int e = poll_done(w, &done, st)) return e;
   }
-  return finish(n, indptr, indices, data, b, x, w, t, info_host, st);
+  return finish(A, b, x, w, t, info_host, st);
 }
 
 // ---- distributed CG building blocks (the caller all-reduces workspace[16..20) between them) -------------
@@ -545,14 +658,15 @@ extern "C" int fem_dcg_begin(double* workspace, double tol, double atol, int max
 }
 
 extern "C" int fem_dcg_spmv_dot(int64_t n_owned, int64_t n_local, const int32_t* indptr, const int32_t* indices,
-                                const double* data, const double* p, double* q, int with_dot, double* workspace,
-                                void* stream) {
+                                const double* data, int vec, const int32_t* brow_ptr, const int32_t* bcol,
+                                const double* p, double* q, int with_dot, double* workspace, void* stream) {
   if (int e = check_device()) return e;
   FEM_REQUIRE(indptr && indices && data && p && q && workspace, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const Ws w = carve(workspace, n_local);
-  if (with_dot) spmv_fused<4>(n_owned, indptr, indices, data, p, q, p, w, st);
-  else spmv_fused<0>(n_owned, indptr, indices, data, p, q, nullptr, w, st);
+  const Mat A{n_owned, indptr, indices, data, vec, brow_ptr, bcol};
+  if (with_dot) spmv_fused<4>(A, p, q, p, w, st);
+  else spmv_fused<0>(A, p, q, nullptr, w, st);
   FEM_LAUNCH_CHECK();
   return FEM_OK;
 }

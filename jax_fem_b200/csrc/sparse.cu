@@ -404,11 +404,17 @@ int launch_spmv(int64_t n, const int32_t* indptr, const int32_t* indices, const 
 }
 }  // namespace femb200
 
-extern "C" int fem_spmv(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
-                        const double* x, double* y, void* stream) {
+namespace femb200 {
+int launch_spmv_block(int64_t n, int vec, const int32_t* brow_ptr, const int32_t* bcol, const double* data,
+                      const double* x, double* y, cudaStream_t st);
+}
+
+extern "C" int fem_spmv(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data, int vec,
+                        const int32_t* brow_ptr, const int32_t* bcol, const double* x, double* y, void* stream) {
   if (int e = check_device()) return e;
   FEM_REQUIRE(indptr && indices && data && x && y, "null pointer");
   if (n == 0) return FEM_OK;
+  if (brow_ptr && bcol && (vec == 2 || vec == 3)) return launch_spmv_block(n, vec, brow_ptr, bcol, data, x, y, (cudaStream_t)stream);
   return launch_spmv(n, indptr, indices, data, x, y, (cudaStream_t)stream);
 }
 

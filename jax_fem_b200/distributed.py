@@ -211,8 +211,8 @@ def distributed_cg(A, b, x0, part, halo, comm, vec, tol=1e-10, atol=1e-10, maxit
     P = _lib.ptr
 
     def spmv_dot(vec_in, with_dot):
-        _lib.check(lib.fem_dcg_spmv_dot(n_owned, n_local, P(indptr), P(indices), P(data), P(vec_in), P(q),
-                                        int(with_dot), P(ws), st()))
+        _lib.check(lib.fem_dcg_spmv_dot(n_owned, n_local, P(indptr), P(indices), P(data), A.plan.vec, P(A.plan.brow_ptr),
+                                        P(A.plan.bcol), P(vec_in), P(q), int(with_dot), P(ws), st()))
 
     _lib.check(lib.fem_dcg_begin(P(ws), float(tol), float(atol), int(maxiter), st()))
     halo.update(x)

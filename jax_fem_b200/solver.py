@@ -156,8 +156,11 @@ def jax_solve(A, b, x0, precond, method='bicgstab', tol=1e-10, atol=1e-10, maxit
     ws = _krylov_workspace(n, b.device)
     info = (_lib.ctypes.c_double * 4)()
     fn = {'bicgstab': _lib.load().fem_pbicgstab, 'cg': _lib.load().fem_pcg}[method]
-    _lib.check(fn(n, _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(data), _lib.ptr(diag), _lib.ptr(b), _lib.ptr(x),
-                  float(tol), float(atol), int(maxiter), int(check_every), _lib.ptr(ws), info, _lib.stream_ptr()))
+    plan = getattr(A, 'plan', None)             # FE matrices carry their node-block structure; others use plain CSR
+    vec, brow_ptr, bcol = (plan.vec, plan.brow_ptr, plan.bcol) if plan is not None else (1, None, None)
+    _lib.check(fn(n, _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(data), vec, _lib.ptr(brow_ptr), _lib.ptr(bcol),
+                  _lib.ptr(diag), _lib.ptr(b), _lib.ptr(x), float(tol), float(atol), int(maxiter), int(check_every),
+                  _lib.ptr(ws), info, _lib.stream_ptr()))
     iters, err = int(info[0]), float(info[2])
     logger.debug("jax_solver(%s) - %d iterations, linear solve res = %.3g", method, iters, err)
     assert err < 0.1, f"JAX linear solver failed to converge with err = {err}"

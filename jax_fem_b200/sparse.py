@@ -42,8 +42,9 @@ class CSRMatrix:
     def mult(self, x, y=None):
         y = torch.empty_like(x) if y is None else y
         p = self.plan
-        _lib.check(_lib.load().fem_spmv(p.n, _lib.ptr(p.indptr), _lib.ptr(p.indices), _lib.ptr(self.data),
-                                        _lib.ptr(x), _lib.ptr(y), _lib.stream_ptr()))
+        _lib.check(_lib.load().fem_spmv(p.n, _lib.ptr(p.indptr), _lib.ptr(p.indices), _lib.ptr(self.data), p.vec,
+                                        _lib.ptr(p.brow_ptr), _lib.ptr(p.bcol), _lib.ptr(x), _lib.ptr(y),
+                                        _lib.stream_ptr()))
         return y
 
     def __matmul__(self, x):

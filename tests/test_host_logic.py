@@ -152,7 +152,7 @@ def test_library_exports_every_declared_symbol_and_has_no_cpu_fallback():
     assert lib.fem_version() >= 100
     if not torch.cuda.is_available():
         assert lib.fem_device_count() == -3                                      # FEM_ENODEV
-        assert lib.fem_spmv(0, None, None, None, None, None, None) == -3         # refuses to compute without a GPU
+        assert lib.fem_spmv(0, None, None, None, 1, None, None, None, None, None) == -3         # refuses to compute without a GPU
         assert b"no CUDA device" in lib.fem_last_error()
         m = jf.box_mesh(2, 2, 2, 1, 1, 1)
         with pytest.raises(RuntimeError):
