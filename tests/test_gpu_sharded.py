@@ -64,3 +64,47 @@ def test_sharded_linear_elasticity_matches_single_domain_and_oracle(world):
                       surface_maps=[lambda u, x: np.array([0., 0., 100.]) + 0. * u], **{'dirichlet_bc_info': kw['dirichlet_bc_info']})
     osol = fem.solver(opb, method='cg')
     assert np.abs(glob - osol).max() <= 1e-8 * np.abs(osol).max()
+
+
+def test_sharded_newton_neohookean_matches_single_domain():
+    """BASELINE.json configs[2] in miniature: Neo-Hookean cube (hyperelastic3d_common.py:15-42, 83-103), Newton with
+    per-iteration tangent re-assembly, cells sharded across 2 ranks."""
+    import jax_fem_b200 as jf
+    from jax_fem_b200 import laws
+    from jax_fem_b200.distributed import ShardedProblem, ThreadComm
+
+    class Hyper(jf.Problem):
+        def get_tensor_map(self):
+            return laws.NeoHookean(10.0, 0.3)
+
+        def get_surface_maps(self):
+            return [lambda u, x: np.array([0., 1e-3, 0.])]
+
+    m = jf.box_mesh(6, 4, 4, 1., 1., 1.)
+    pts, cells = m.points, m.cells_dict['hexahedron']
+    left = lambda p: np.isclose(p[0], 0., atol=1e-5)
+    right = lambda p: np.isclose(p[0], 1., atol=1e-5)
+    ymax = lambda p: np.isclose(p[1], 1., atol=1e-5)
+    kw = dict(dirichlet_bc_info=[[left] * 3 + [right] * 3, [0, 1, 2] * 2,
+                                 [lambda p: 0.] * 3 + [lambda p: 0.02] + [lambda p: 0.] * 2], location_fns=[ymax])
+    single = Hyper(jf.Mesh(pts, cells), vec=3, dim=3, **kw)
+    ref = jf.solver(single, {'jax_solver': {'method': 'cg'}})[0].cpu().numpy()
+    out, errs = {}, []
+
+    def run(comm):
+        try:
+            torch.cuda.set_device(0)
+            sp = ShardedProblem(Hyper, pts, cells, comm, vec=3, dim=3, **kw)
+            out[comm.rank] = (sp.part, sp.solve().cpu().numpy(), sp.last_info)
+        except Exception as e:                      # pragma: no cover
+            errs.append(e)
+            comm.sh.barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(c,)) for c in ThreadComm.group(2)]
+    [t.start() for t in threads]
+    [t.join(300) for t in threads]
+    assert not errs, errs
+    for r in range(2):
+        part, sol, info = out[r]
+        assert info['newton_iterations'] == single.last_newton_info['iterations']
+        assert np.abs(sol - ref[part.l2g]).max() <= 1e-8 * np.abs(ref).max()
