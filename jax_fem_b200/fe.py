@@ -126,6 +126,16 @@ class FiniteElement:
         inv = np.linalg.inv(J)
         return np.einsum('qne,cqed->cqnd', self.shape_grads_ref, inv), np.linalg.det(J) * self.quad_weights[None, :]
 
+    def get_JxW(self, points=None, chunk=1 << 17):
+        """JxW (C,Q) alone, in cell chunks (the load-vector assembly needs it for every cell but must not materialise
+        the (C,Q,N,dim) gradients)."""
+        out = np.empty((self.num_cells, self.num_quads))
+        pts = self.points if points is None else np.asarray(points)
+        for s in range(0, self.num_cells, chunk):
+            J = np.einsum('cnd,qne->cqde', pts[self.cells[s:s + chunk]], self.shape_grads_ref)
+            out[s:s + chunk] = np.linalg.det(J) * self.quad_weights[None, :]
+        return out
+
     def get_face_shape_grads(self, boundary_inds, points=None):
         """-> face_shape_grads_physical (S,FQ,N,dim), nanson_scale (S,FQ)."""
         boundary_inds = np.asarray(boundary_inds)

@@ -133,7 +133,7 @@ class Problem:
         used = False
         if hasattr(self, 'get_mass_map'):
             x = fe.get_physical_quad_points()                                      # (C,Q,dim)
-            _, JxW = fe.get_shape_grads()
+            JxW = fe.get_JxW()
             val = _eval_load_map(self.get_mass_map(), None, x.reshape(-1, self.dim), fe.vec).reshape(*x.shape[:2], fe.vec)
             contrib = np.einsum('cqv,qn,cq->cnv', val, fe.shape_vals, JxW)
             for i in range(fe.vec):

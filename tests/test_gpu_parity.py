@@ -330,3 +330,31 @@ def test_hex27_dmma_element_assembly_and_solve(order):
     usol = host(jf.solver(prob, {'jax_solver': {'method': 'cg'}})[0])
     osol = fem.solver(opb, method='cg')
     assert relmax(usol, osol) <= SOL_TOL
+
+
+def test_cuda_core_element_path_for_elasticity_in_subprocess():
+    """The HEX8 elasticity tangent has two kernels (FP64 tensor-core tiles by default, CUDA cores with
+    FEM_ELEMENT_PATH=dfma); the choice is read once per process, so the second one is checked in a child process."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import numpy as np, torch, sys
+sys.path.insert(0, 'tests')
+import jax_fem_b200 as jf, gpu_problems as gp
+from oracle import fem, laws as olaws
+m = jf.box_mesh(4, 3, 3, 1.0, 0.8, 0.9)
+pts = m.points + 0.02 * np.random.default_rng(0).uniform(-1, 1, m.points.shape)
+cells = m.cells_dict['hexahedron']
+sol = 0.01 * np.random.default_rng(1).standard_normal(pts.shape)
+prob = gp.PlainElasticity(jf.Mesh(pts, cells), vec=3, dim=3)
+prob.newton_update([torch.from_numpy(sol).cuda()])
+opb = fem.Problem(fem.Mesh(pts, cells), 3, 3, law=olaws.LinearElastic(70e3, 0.3))
+K, Ko = prob.element_tangents().cpu().numpy(), opb.cell_jacobians(sol)
+print('RELMAX', np.abs(K - Ko).max() / np.abs(Ko).max())
+"""
+    env = dict(os.environ, FEM_ELEMENT_PATH="dfma")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=200)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert float(out.stdout.split("RELMAX")[1]) <= VAL_TOL
