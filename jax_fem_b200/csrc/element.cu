@@ -509,21 +509,20 @@ struct DmmaLayout {
   static constexpr int OFF_S = OFF_G + NQ * GS;    // S[q][i][d] = sigma JxW        (272)
   static constexpr int OFF_E = OFF_S + NQ * 9;     // E_q JxW                       (344)
   static constexpr int CELL = 354;                 // 352 + 2: cell stride 2 (mod 16) spreads phase-1 stores
-  static constexpr int OUT = 576;                  // one cell's 8 row blocks
-  static constexpr int WARP = 4 * CELL + OUT + 16; // + 32 ints of corner positions
+  static constexpr int WARP = 4 * CELL + 16;       // + 32 ints of corner positions; the row blocks of a cell are
+                                                   // staged in the cell's own (by then dead) area, 4 rows at a time
   static constexpr int WARPS = 4;
 };
 
 template <int LAW>
-__global__ void __launch_bounds__(DmmaLayout::WARPS * 32, 3) element_dmma_kernel(const ElemArgs A) {
+__global__ void __launch_bounds__(DmmaLayout::WARPS * 32, 4) element_dmma_kernel(const ElemArgs A) {
   using L = DmmaLayout;
   constexpr int NN = 8, NQ = 8, DIM = 3, VEC = 3, ND = 24;
   extern __shared__ __align__(16) double sm[];
   double* tab = sm;
   const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
   double* wb = sm + L::TAB_SIZE + warp * L::WARP;
-  double* out = wb + 4 * L::CELL;
-  int* pos = reinterpret_cast<int*>(out + L::OUT);
+  int* pos = reinterpret_cast<int*>(wb + 4 * L::CELL);
   for (int i = threadIdx.x; i < NQ * NN * DIM; i += L::WARPS * 32)
     tab[(i / (NN * DIM)) * L::TAB_STRIDE + i % (NN * DIM)] = A.ref[i];
   if (threadIdx.x < NQ) tab[NQ * L::TAB_STRIDE + threadIdx.x] = A.ref[NQ * NN * DIM + threadIdx.x];
@@ -607,28 +606,38 @@ __global__ void __launch_bounds__(DmmaLayout::WARPS * 32, 3) element_dmma_kernel
     } else if (t == 1) {
       A.Re[c * ND + n * 3 + 2] = R[0];
     }
-    // G -> K for the lane's two column nodes b = 2t, 2t+1; 18 contiguous doubles of row block n
-    double* dst = out + n * 72 + t * 18;
+    // G -> K for the lane's two column nodes b = 2t, 2t+1: 18 contiguous doubles of row block n
+    double K[2][9];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const double tr = C[0][0][e] + C[1][1][e] + C[2][2][e];
-      double K[9];
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) K[i * 3 + k] = lam1 * C[i][k][e] + mu1 * C[k][i][e] + (i == k ? mu1 * tr : 0.0);
-#pragma unroll
-      for (int m = 0; m < 9; ++m) dst[e * 9 + m] = K[m];
+        for (int k = 0; k < 3; ++k) K[e][i * 3 + k] = lam1 * C[i][k][e] + mu1 * C[k][i][e] + (i == k ? mu1 * tr : 0.0);
     }
-    __syncwarp();
-    // coalesced copy-out: 8 row blocks x 36 double2
+    // stage 4 row blocks at a time in the cell's own area (its g / S / E are in registers by now), then copy them
+    // to their node-sorted positions with coalesced 16-byte stores
+    double* out = wb + j * L::CELL;
 #pragma unroll
-    for (int it = 0; it < 9; ++it) {
-      const int p2 = it * 32 + l;
-      const int row = p2 / 36, w2 = p2 % 36;
-      reinterpret_cast<double2*>(A.Ke + (int64_t)pos[j * 8 + row] * 72)[w2] = reinterpret_cast<const double2*>(out + row * 72)[w2];
+    for (int half = 0; half < 2; ++half) {
+      __syncwarp();
+      if ((n >> 2) == half) {
+        double* dst = out + (n & 3) * 72 + t * 18;
+#pragma unroll
+        for (int m = 0; m < 9; ++m) reinterpret_cast<double2*>(dst)[m] = make_double2(K[(2 * m) / 9][(2 * m) % 9], K[(2 * m + 1) / 9][(2 * m + 1) % 9]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 5; ++it) {
+        const int p2 = it * 32 + l;                     // 4 rows x 36 double2
+        if (p2 < 144) {
+          const int row = p2 / 36, w2 = p2 % 36;
+          reinterpret_cast<double2*>(A.Ke + (int64_t)pos[j * 8 + half * 4 + row] * 72)[w2] =
+              reinterpret_cast<const double2*>(out + row * 72)[w2];
+        }
+      }
     }
-    __syncwarp();
   }
 }
 
