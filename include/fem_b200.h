@@ -76,6 +76,31 @@ int fem_hex27_residual_jacobian(int law_id, const double* law_params_host, const
                                 const double* internal_var, const double* ref_tables, int n_quad,
                                 const int32_t* corner_pos, double* Ke, double* Re, void* stream);
 
+/* ---- (1)+(2) fused: compute_newton_vars (jax_fem/problem.py:447-460) + _PetscTangentCache.update / get_A
+ *      (jax_fem/solver.py:469-553) + compute_residual_vars_helper (jax_fem/problem.py:426-437) in one kernel for
+ *      HEX8 / vec 3 / isotropic elasticity (linear, SIMP): the element tangents never reach HBM.
+ *
+ * The mesh nodes are partitioned into patches of <= 64 owned nodes; one CTA evaluates every cell touching its
+ * patch, accumulates the rows of its own nodes in shared memory in ascending cell order (deterministic, no atomics)
+ * and writes each CSR value once.  Tables (jax_fem_b200/patch_plan.py documents the bit layouts):
+ *   phdr (n_patches+1, 8): first owned node / local node / patch-cell / chunk, accumulator doubles
+ *   pn_node, pn_out, pn_acc, pn_info: per owned node: global id, offset of its rows in `data` (= 9 brow_ptr[n]),
+ *            offset in the patch accumulator, len(n) | diagonal slot << 8
+ *   lnodes: per patch the global ids of its local nodes (owned first);  pc_cell / pc_ln: per (patch, cell) the
+ *            global cell id and the 8 local node numbers (uint8 x 8)
+ *   ck_lane / ck_rnd: per chunk of 32 cells the first lane and the number of accumulation rounds
+ *   ln_desc / ln_slot: per owned corner: cell-in-chunk | a<<5 | owned index<<8 | round<<16, and the 8 column slots
+ * bc_flag: (3 n_nodes) bytes, 1 = Dirichlet row (zeroed, unit diagonal, pattern kept; solver.py:477,527-528).
+ * f_ext: (n_nodes, 3) constant load vector or NULL.  Outputs: data (nnz) CSR values, res (n_nodes, 3).          */
+int fem_assemble_fused(int ele_type, int vec, int law_id, const double* law_params_host,
+                       const double* points, const double* sol, const double* internal_var,
+                       const double* ref_tables, int64_t n_patches, const int32_t* phdr,
+                       const int32_t* pn_node, const int32_t* pn_out, const int32_t* pn_acc,
+                       const int32_t* pn_info, const int32_t* lnodes, const int32_t* pc_cell,
+                       const int32_t* pc_ln, const int32_t* ck_lane, const int32_t* ck_rnd,
+                       const int32_t* ln_desc, const int32_t* ln_slot, const uint8_t* bc_flag,
+                       const double* f_ext, double* data, double* res, void* stream);
+
 /* ---- (2) global assembly: _PetscTangentCache.update / get_A (jax_fem/solver.py:469-553)
  *      as a precomputed cell->CSR-slot permutation + deterministic segmented sum (no atomics).
  *

@@ -1,0 +1,322 @@
+// Fused owner-computes assembly: element evaluation + global CSR assembly + Dirichlet rows + nodal residual in ONE
+// kernel, without the element tangents ever touching HBM.
+//
+// Replaces, for HEX8 isotropic elasticity (linear, SIMP), the chain
+//   Problem.compute_newton_vars (jax_fem/problem.py:447-460: get_laplace_kernel :189-214 + value_and_jacfwd :262-266)
+//   -> problem.V -> _PetscTangentCache.update / get_A (jax_fem/solver.py:469-553: setValuesCOO + zeroRows)
+//   and compute_residual_vars_helper (jax_fem/problem.py:426-437)
+// which the two-kernel path (element.cu + sparse.cu::gather_csr_kernel) runs through a C*8 x 8 x 3 x 3 staging
+// buffer (4.6 GB written and read again at 100^3).
+//
+// One persistent CTA per SM walks over *patches* (jax_fem_b200/patch_plan.py): <= 64 mesh nodes owned by the CTA
+// (4x4x4 on a structured grid) together with every cell touching them.  Per patch:
+//   prologue : coordinates and solution of the patch's local nodes (owned + halo) -> shared memory
+//   per chunk of 32 cells
+//     phase 1: thread = (cell, quadrature point): J, J^-1, physical gradients g, JxW, grad u, stress -> record
+//              (same arithmetic as element.cu, fe.py:112-141 / problem.py:204-210)
+//     phase 2: thread = (owned corner (cell, a), column half): G_ab = sum_q E_q w_q g_a (x) g_b for 4 column nodes
+//              from 16-byte broadcast shared loads, K_ab = lam' G + mu' G^T + mu' tr(G) I, element residual r_a
+//     rounds : the row blocks are added into the patch's shared-memory accumulator, which is laid out exactly like
+//              the CSR rows of the owned nodes; lanes that hit the same row are serialised by their plan-computed
+//              round (= rank of the cell among the node's cells) => ascending cell order, bit-reproducible, no atomics
+//   epilogue : Dirichlet rows -> unit rows (pattern kept, Mat.zeroRows), rows copied to `data` with coalesced
+//              stores, residual (+ constant load vector) written; every CSR value is written exactly once.
+// Cells on a patch surface are evaluated by every patch they touch (phase 1 only: 125 cells per 64 owned nodes on
+// a structured grid); phase 2 is done once per (cell, corner) by the corner's owner.
+#include "common.cuh"
+#include "element_math.cuh"
+
+namespace femb200 {
+namespace {
+
+struct FusedCfg {
+  static constexpr int THREADS = 256;
+  static constexpr int CHUNK = 32;            // cells per chunk               (patch_plan.CHUNK)
+  static constexpr int MAX_OWNED = 64;        //                               (patch_plan.MAX_OWNED)
+  static constexpr int MAX_LOCAL = 256;       //                               (patch_plan.MAX_LOCAL + 1)
+  static constexpr int ACC = 64 * 27 * 9;     // accumulator doubles           (patch_plan.ACC_DOUBLES)
+  static constexpr int NN = 8, NQ = 8, DIM = 3, VEC = 3;
+  static constexpr int TAB_STRIDE = 25, TAB_SIZE = NQ * TAB_STRIDE + NQ;
+  // record of (cell, q): g[8][3] | E w | pad | S[3][3] = sigma JxW | pad  -- 16-byte aligned pieces
+  static constexpr int OFF_G = 0, OFF_E = 24, OFF_S = 26, QREC = 36;
+  static constexpr int CELLREC = NQ * QREC + 2;   // +16 B: neighbouring cells broadcast from different banks
+  static constexpr int OFF_TAB = 0;
+  static constexpr int OFF_ACC = OFF_TAB + TAB_SIZE;
+  static constexpr int OFF_RACC = OFF_ACC + ACC;
+  static constexpr int OFF_XU = OFF_RACC + MAX_OWNED * VEC;
+  static constexpr int OFF_REC = OFF_XU + MAX_LOCAL * (DIM + VEC);
+  static constexpr int OFF_INT = OFF_REC + CHUNK * CELLREC;
+  static constexpr int SMEM_DOUBLES = OFF_INT + (4 * MAX_OWNED) / 2;
+};
+
+struct FusedArgs {
+  const double* points;
+  const double* sol;
+  const double* iv;
+  const double* ref;
+  const int32_t *phdr, *pn_node, *pn_out, *pn_acc, *pn_info, *lnodes, *pc_cell, *pc_ln, *ck_lane, *ck_rnd, *ln_desc, *ln_slot;
+  const uint8_t* bc_flag;
+  const double* f_ext;
+  double* data;
+  double* res;
+  int n_patches;
+  double p[8];
+};
+
+template <int LAW>
+__global__ void __launch_bounds__(FusedCfg::THREADS, 1) fused_assembly_kernel(const FusedArgs A) {
+  using L = FusedCfg;
+  constexpr int NN = L::NN, NQ = L::NQ, DIM = L::DIM, VEC = L::VEC;
+  extern __shared__ __align__(16) double sm[];
+  double* tab = sm + L::OFF_TAB;
+  double* acc = sm + L::OFF_ACC;
+  double* racc = sm + L::OFF_RACC;
+  double* xu = sm + L::OFF_XU;
+  double* recs = sm + L::OFF_REC;
+  int* s_node = reinterpret_cast<int*>(sm + L::OFF_INT);
+  int* s_out = s_node + L::MAX_OWNED;
+  int* s_acc = s_out + L::MAX_OWNED;
+  int* s_info = s_acc + L::MAX_OWNED;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < NQ * NN * DIM; i += L::THREADS) tab[(i / (NN * DIM)) * L::TAB_STRIDE + i % (NN * DIM)] = A.ref[i];
+  if (tid < NQ) tab[NQ * L::TAB_STRIDE + tid] = A.ref[NQ * NN * DIM + tid];
+  for (int i = tid; i < L::ACC + L::MAX_OWNED * VEC; i += L::THREADS) acc[i] = 0.0;   // acc and racc are adjacent
+
+  const double nu = iso_nu<LAW>(A.p);
+  const double mu1 = 1.0 / (2.0 * (1.0 + nu)), lam1 = nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
+
+#pragma unroll 1
+  for (int patch = blockIdx.x; patch < A.n_patches; patch += gridDim.x) {
+    const int* h0 = A.phdr + (int64_t)patch * 8;
+    const int node0 = h0[0], lnode0 = h0[1], cell0 = h0[2], chunk0 = h0[3];
+    const int n_owned = h0[8] - node0, n_local = h0[9] - lnode0, n_cells = h0[10] - cell0, n_chunks = h0[11] - chunk0;
+    __syncthreads();            // previous patch: epilogue done with s_*, xu
+    if (tid < n_owned) {
+      s_node[tid] = A.pn_node[node0 + tid];
+      s_out[tid] = A.pn_out[node0 + tid];
+      s_acc[tid] = A.pn_acc[node0 + tid];
+      s_info[tid] = A.pn_info[node0 + tid];
+    }
+    for (int i = tid; i < n_local; i += L::THREADS) {
+      const int64_t node = A.lnodes[lnode0 + i];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) xu[i * 6 + d] = A.points[node * DIM + d];
+#pragma unroll
+      for (int d = 0; d < VEC; ++d) xu[i * 6 + 3 + d] = A.sol[node * VEC + d];
+    }
+    __syncthreads();
+
+#pragma unroll 1
+    for (int k = 0; k < n_chunks; ++k) {
+      const int ncell = min(L::CHUNK, n_cells - k * L::CHUNK);
+      // ---------------- phase 1: thread = (cell, q) ----------------
+      if (tid < ncell * NQ) {
+        const int cl = tid >> 3, q = tid & 7;
+        const int pc = cell0 + k * L::CHUNK + cl;
+        const int2 lw = reinterpret_cast<const int2*>(A.pc_ln)[pc];
+        double X[NN * DIM], U[NN * VEC];
+#pragma unroll
+        for (int n = 0; n < NN; ++n) {
+          const int ln = ((n < 4 ? lw.x : lw.y) >> (8 * (n & 3))) & 255;
+          const double2* src = reinterpret_cast<const double2*>(xu + ln * 6);
+          const double2 v0 = src[0], v1 = src[1], v2 = src[2];
+          X[n * 3 + 0] = v0.x; X[n * 3 + 1] = v0.y; X[n * 3 + 2] = v1.x;
+          U[n * 3 + 0] = v1.y; U[n * 3 + 1] = v2.x; U[n * 3 + 2] = v2.y;
+        }
+        double g[NN][DIM];
+        const double w = qp_geometry<NN, DIM>(X, tab + q * L::TAB_STRIDE, tab[NQ * L::TAB_STRIDE + q], g);
+        double ug[VEC][DIM];
+        qp_grad_u<NN, DIM, VEC>(U, g, ug);
+        const double* ivq = A.iv ? A.iv + (int64_t)A.pc_cell[pc] * NQ + q : nullptr;
+        const double E = iso_modulus<LAW>(A.p, ivq, false);
+        const double mu = E / (2.0 * (1.0 + nu)), lam = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
+        double sig[DIM][DIM];
+        iso_stress<DIM>(lam, mu, ug, sig);
+        double* rq = recs + cl * L::CELLREC + q * L::QREC;
+#pragma unroll
+        for (int t = 0; t < 12; ++t)
+          reinterpret_cast<double2*>(rq + L::OFF_G)[t] = make_double2(g[(2 * t) / 3][(2 * t) % 3], g[(2 * t + 1) / 3][(2 * t + 1) % 3]);
+        rq[L::OFF_E] = E * w;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) rq[L::OFF_S + i * DIM + d] = sig[i][d] * w;
+      }
+      __syncthreads();
+
+      // ---------------- phase 2: thread = (owned corner, column half) ----------------
+      const int l0 = A.ck_lane[chunk0 + k], l1 = A.ck_lane[chunk0 + k + 1];
+      const int rounds = A.ck_rnd[chunk0 + k];
+      const int ntask = 2 * (l1 - l0);
+#pragma unroll 1
+      for (int t0 = 0; t0 < ntask; t0 += L::THREADS) {
+        const int t = t0 + tid;
+        const bool valid = t < ntask;
+        const int li = l0 + (t >> 1), h = t & 1;
+        int desc = 0, slots = 0;
+        if (valid) {
+          desc = A.ln_desc[li];
+          slots = A.ln_slot[2 * (int64_t)li + h];
+        }
+        const int cl = desc & 31, a = (desc >> 5) & 7, nl = (desc >> 8) & 255, rk = (desc >> 16) & 255;
+        double K[4][3][3];
+        double r[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) K[j][i][c] = 0.0;
+        if (valid) {
+          const double* rec = recs + cl * L::CELLREC;
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            const double* rq = rec + q * L::QREC;
+            const double ew = rq[L::OFF_E];
+            double ga[3], gw[3], gb[12];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              ga[d] = rq[L::OFF_G + a * 3 + d];
+              gw[d] = ga[d] * ew;
+            }
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+              const double2 v = reinterpret_cast<const double2*>(rq + L::OFF_G + h * 12)[u];
+              gb[2 * u] = v.x;
+              gb[2 * u + 1] = v.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) K[j][i][c] = fma(gw[i], gb[j * 3 + c], K[j][i][c]);
+            // element residual r_a = sum_q S_q g_a(q): this half takes the quadrature points q = 4h .. 4h+3
+            if ((q >> 2) == h) {
+#pragma unroll
+              for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) r[i] = fma(rq[L::OFF_S + i * 3 + d], ga[d], r[i]);   // problem.py:210
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            double G[3][3];
+            double tr = 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              tr += K[j][i][i];
+#pragma unroll
+              for (int c = 0; c < 3; ++c) G[i][c] = K[j][i][c];
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) K[j][i][c] = lam1 * G[i][c] + mu1 * G[c][i] + (i == c ? mu1 * tr : 0.0);
+          }
+        }
+        // the two halves of a corner sit in adjacent lanes: r = r(q<4) + r(q>=4), kept by the half-0 lane
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const double o = __shfl_xor_sync(0xffffffffu, r[i], 1);
+          r[i] = (h == 0) ? r[i] + o : o + r[i];
+        }
+        // ---- ordered accumulation into the patch's CSR-shaped rows ----
+        const int len3 = valid ? 3 * (s_info[nl] & 255) : 0;
+        double* rowp = acc + (valid ? s_acc[nl] : 0);
+#pragma unroll 1
+        for (int rd = 0; rd < rounds; ++rd) {
+          if (valid && rk == rd) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              double* p = rowp + 3 * ((slots >> (8 * j)) & 255);
+#pragma unroll
+              for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) p[i * len3 + c] += K[j][i][c];
+            }
+            if (h == 0) {
+#pragma unroll
+              for (int i = 0; i < 3; ++i) racc[nl * 3 + i] += r[i];
+            }
+          }
+          __syncthreads();
+        }
+      }
+      if (ntask == 0) __syncthreads();     // records may not be overwritten before every thread left phase 2
+    }
+
+    // ---------------- epilogue: Dirichlet rows, coalesced copy-out, re-zero ----------------
+    for (int i = warp; i < n_owned; i += L::THREADS / 32) {
+      const int n = s_node[i], info = s_info[i];
+      const int len = info & 255, dg = info >> 8;
+      const int tot = 9 * len, len3 = 3 * len;
+      double* src = acc + s_acc[i];
+      double* dst = A.data + s_out[i];
+      const uint8_t* f = A.bc_flag + 3 * (int64_t)n;
+      const int f0 = f[0], f1 = f[1], f2 = f[2];
+      for (int e = lane; e < tot; e += 32) {
+        double v = src[e];
+        src[e] = 0.0;
+        if (f0 | f1 | f2) {
+          const int row = e / len3, col = e - row * len3;
+          const int fl = row == 0 ? f0 : (row == 1 ? f1 : f2);
+          if (fl) v = (col == 3 * dg + row) ? 1.0 : 0.0;
+        }
+        dst[e] = v;
+      }
+      if (lane < 3) {
+        A.res[3 * (int64_t)n + lane] = racc[i * 3 + lane] + (A.f_ext ? A.f_ext[3 * (int64_t)n + lane] : 0.0);
+        racc[i * 3 + lane] = 0.0;
+      }
+    }
+  }
+}
+
+template <int LAW>
+int launch_fused(const FusedArgs& A, cudaStream_t st) {
+  using L = FusedCfg;
+  const size_t smem = sizeof(double) * L::SMEM_DOUBLES;
+  auto k = fused_assembly_kernel<LAW>;
+  FEM_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = A.n_patches < kNumSM ? A.n_patches : kNumSM;
+  k<<<grid, L::THREADS, smem, st>>>(A);
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
+}
+
+}  // namespace
+}  // namespace femb200
+
+using namespace femb200;
+
+extern "C" int fem_assemble_fused(int ele_type, int vec, int law_id, const double* law_params_host,
+                                  const double* points, const double* sol, const double* internal_var,
+                                  const double* ref_tables, int64_t n_patches, const int32_t* phdr,
+                                  const int32_t* pn_node, const int32_t* pn_out, const int32_t* pn_acc,
+                                  const int32_t* pn_info, const int32_t* lnodes, const int32_t* pc_cell,
+                                  const int32_t* pc_ln, const int32_t* ck_lane, const int32_t* ck_rnd,
+                                  const int32_t* ln_desc, const int32_t* ln_slot, const uint8_t* bc_flag,
+                                  const double* f_ext, double* data, double* res, void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(points && sol && ref_tables && law_params_host && phdr && pn_node && pn_out && pn_acc && pn_info &&
+                  lnodes && pc_cell && pc_ln && ck_lane && ck_rnd && ln_desc && ln_slot && bc_flag && data && res,
+              "null pointer");
+  FEM_REQUIRE(n_patches >= 0 && n_patches < (1ll << 31), "n_patches out of range");
+  if (!(ele_type == FEM_ELE_HEX8 && vec == 3 && (law_id == FEM_LAW_LINEAR_ELASTIC || law_id == FEM_LAW_SIMP))) {
+    set_error("fused assembly is registered for HEX8 / vec 3 / isotropic elasticity only (element=%d, vec=%d, law=%d)",
+              ele_type, vec, law_id);
+    return FEM_EINVAL;
+  }
+  FEM_REQUIRE(!(law_id == FEM_LAW_SIMP && !internal_var), "SIMP needs the per-quadrature-point density");
+  if (n_patches == 0) return FEM_OK;
+  FusedArgs A{};
+  A.points = points; A.sol = sol; A.iv = internal_var; A.ref = ref_tables;
+  A.phdr = phdr; A.pn_node = pn_node; A.pn_out = pn_out; A.pn_acc = pn_acc; A.pn_info = pn_info; A.lnodes = lnodes;
+  A.pc_cell = pc_cell; A.pc_ln = pc_ln; A.ck_lane = ck_lane; A.ck_rnd = ck_rnd; A.ln_desc = ln_desc; A.ln_slot = ln_slot;
+  A.bc_flag = bc_flag; A.f_ext = f_ext; A.data = data; A.res = res; A.n_patches = (int)n_patches;
+  for (int i = 0; i < 8; ++i) A.p[i] = law_params_host[i];
+  if (law_id == FEM_LAW_SIMP) return launch_fused<FEM_LAW_SIMP>(A, (cudaStream_t)stream);
+  return launch_fused<FEM_LAW_LINEAR_ELASTIC>(A, (cudaStream_t)stream);
+}

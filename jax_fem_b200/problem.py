@@ -26,6 +26,7 @@ import torch
 from . import _lib, laws, logger
 from .fe import FiniteElement, evaluate_point_fn
 from .generate_mesh import Mesh
+from .patch_plan import build_patch_plan
 from .plan import build_plan
 
 
@@ -94,7 +95,11 @@ class Problem:
         self._ref = torch.from_numpy(np.concatenate([fe.shape_grads_ref.reshape(-1), fe.quad_weights])).to(dev)
         self.plan = build_plan(self._cells, fe.num_total_nodes, fe.vec)
         self._Ke = None
-        self._Re = torch.empty((self.num_cells, fe.num_nodes * fe.vec), dtype=torch.float64, device=dev)
+        self._Re = None
+        self._patch_plan = None
+        self._A_data = None            # CSR values left by the fused assembly of the last newton_update
+        self._A_bc_key = None
+        self._last_sol = None
         self._bc_cache = None
         self._law = None
 
@@ -209,8 +214,49 @@ class Problem:
             sol = torch.as_tensor(np.asarray(sol), dtype=torch.float64)
         return sol.detach().to(device=self.device, dtype=torch.float64).contiguous()
 
+    # ---- fused owner-computes assembly (csrc/fused.cu) ------------------------------------------------------
+    def fused_assembly_enabled(self):
+        """HEX8 / vec 3 / isotropic elasticity runs element evaluation + CSR assembly + Dirichlet rows in one kernel
+        (FEM_ASSEMBLY=staged in the environment selects the two-kernel path, for A/B measurements and tests)."""
+        import os
+        return (os.environ.get('FEM_ASSEMBLY', 'fused') != 'staged' and self.ele_type == 'HEX8' and self.fes[0].vec == 3
+                and self._law.law_id in (laws.LinearElasticity.law_id, laws.SIMP.law_id))
+
+    @property
+    def patch_plan(self):
+        if self._patch_plan is None:
+            self._patch_plan = build_patch_plan(self._points, self._cells, self.fes[0].num_total_nodes, self.fes[0].vec,
+                                                self.plan.brow_ptr, self.plan.bcol)
+        return self._patch_plan
+
+    def _run_fused(self, sol):
+        fe = self.fes[0]
+        pp, p = self.patch_plan, self.plan
+        _, _, flag = self.bc_data()
+        iv = self._internal_var()
+        data = torch.empty(p.nnz, dtype=torch.float64, device=self.device)
+        res = torch.empty((fe.num_total_nodes, fe.vec), dtype=torch.float64, device=self.device)
+        P = _lib.ptr
+        _lib.check(_lib.load().fem_assemble_fused(
+            _lib.ELE[self.ele_type], fe.vec, self._law.law_id, _lib.host_doubles(self._law.params()),
+            P(self._points), P(sol), P(iv), P(self._ref), pp.n_patches, P(pp.phdr), P(pp.pn_node), P(pp.pn_out),
+            P(pp.pn_acc), P(pp.pn_info), P(pp.lnodes), P(pp.pc_cell), P(pp.pc_ln), P(pp.ck_lane), P(pp.ck_rnd),
+            P(pp.ln_desc), P(pp.ln_slot), P(flag), P(self._f_ext), P(data), P(res), _lib.stream_ptr()))
+        self._A_data, self._A_bc_key = data, self._bc_cache[0]
+        return res
+
+    def assembled_values(self):
+        """CSR values of the last newton_update for get_A: the fused kernel's output when it ran with the current
+        Dirichlet sets, otherwise None (get_A then gathers the staged element tangents)."""
+        if self._A_data is None:
+            return None
+        self.bc_data()
+        return self._A_data if self._A_bc_key == self._bc_cache[0] else None
+
     def _run_element_kernel(self, sol, jac):
         fe = self.fes[0]
+        if self._Re is None:
+            self._Re = torch.empty((self.num_cells, fe.num_nodes * fe.vec), dtype=torch.float64, device=self.device)
         if jac and self._Ke is None:
             # one row block (N blocks of vec x vec, padded to an even number of doubles) per corner (cell, a),
             # stored in the plan's node-sorted corner order
@@ -243,17 +289,34 @@ class Problem:
         return [self._run_element_kernel(self._as_sol(sol_list), jac=False)]
 
     def newton_update(self, sol_list):
-        """Residual list; the element tangents stay on the device for get_A (problem.py:477-491)."""
-        return [self._run_element_kernel(self._as_sol(sol_list), jac=True)]
+        """Residual list; the tangent stays on the device for get_A (problem.py:477-491): as finished CSR values when
+        the fused assembly is registered for this problem, as element tangents otherwise."""
+        sol = self._as_sol(sol_list)
+        self._last_sol = sol
+        self._A_data = None
+        if self.fused_assembly_enabled():
+            self._Ke_valid = False
+            return [self._run_fused(sol)]
+        self._Ke_valid = True
+        return [self._run_element_kernel(sol, jac=True)]
+
+    def staged_tangents(self):
+        """Element tangents of the last newton_update in the staging layout of the two-kernel path; after a fused
+        assembly they are produced on demand (problem.V, changed Dirichlet sets)."""
+        if self._last_sol is None:
+            raise AttributeError("element tangents are defined after newton_update()")
+        if not getattr(self, '_Ke_valid', False):
+            self._run_element_kernel(self._last_sol, jac=True)
+            self._Ke_valid = True
+        return self._Ke
 
     # ---- reference attributes, materialised on demand ---------------------------------------------------
     def element_tangents(self):
         """(num_cells, ndof, ndof) element tangents in the reference's layout (row = test dof)."""
-        if self._Ke is None:
-            raise AttributeError("element tangents are defined after newton_update()")
+        Ke = self.staged_tangents()
         fe = self.fes[0]
         N, v = fe.num_nodes, fe.vec
-        rows = self._Ke[self.plan.corner_pos.long()][:, :N * v * v]              # (C*N, N*v*v) in (c, a) order
+        rows = Ke[self.plan.corner_pos.long()][:, :N * v * v]              # (C*N, N*v*v) in (c, a) order
         return rows.reshape(self.num_cells, N, N, v, v).permute(0, 1, 3, 2, 4).reshape(self.num_cells, N * v, N * v)
 
     @property

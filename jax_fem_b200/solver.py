@@ -118,15 +118,19 @@ def get_A(problem):
     diagonal and the full pattern kept (solver.py:469-553).  Returns a device CSRMatrix."""
     if hasattr(problem, 'P_mat'):
         raise NotImplementedError("P_mat (multipoint constraints) is outside the B200 hot path")
-    if problem._Ke is None:
+    if problem._last_sol is None:
         raise RuntimeError("get_A() needs problem.newton_update(sol_list) first")
     p = problem.plan
     fe = problem.fes[0]
+    data = problem.assembled_values()          # fused owner-computes assembly already produced the CSR values
+    if data is not None:
+        return CSRMatrix(p, data)
+    Ke = problem.staged_tangents()
     einfo = problem.entry_info()
     data = torch.empty(p.nnz, dtype=torch.float64, device=problem.device)
     _lib.check(_lib.load().fem_gather_csr(fe.vec, fe.num_nodes, p.n_gather_blocks, _lib.ptr(p.gdesc), _lib.ptr(p.eorder),
                                           _lib.ptr(p.src_ptr), _lib.ptr(p.src), _lib.ptr(p.edst), _lib.ptr(einfo),
-                                          _lib.ptr(problem._Ke), _lib.ptr(data), _lib.stream_ptr()))
+                                          _lib.ptr(Ke), _lib.ptr(data), _lib.stream_ptr()))
     return CSRMatrix(p, data)
 
 

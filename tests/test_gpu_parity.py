@@ -358,3 +358,82 @@ print('RELMAX', np.abs(K - Ko).max() / np.abs(Ko).max())
     out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=200)
     assert out.returncode == 0, out.stderr[-2000:]
     assert float(out.stdout.split("RELMAX")[1]) <= VAL_TOL
+
+
+# ---- fused owner-computes assembly (csrc/fused.cu) ------------------------------------------------------
+def _assemble_both_ways(prob, sol, monkeypatch):
+    import jax_fem_b200 as jf
+    out = {}
+    for mode in ("fused", "staged"):
+        monkeypatch.setenv("FEM_ASSEMBLY", mode)
+        assert prob.fused_assembly_enabled() == (mode == "fused")
+        res = prob.newton_update([torch.from_numpy(sol).cuda()])[0]
+        A = jf.get_A(prob)
+        out[mode] = (host(res), host(A.data))
+    return out
+
+
+@pytest.mark.parametrize("case", ["perturbed_box", "cylinder", "simp"])
+def test_fused_assembly_matches_oracle_and_staged_path(case, monkeypatch):
+    """One-kernel assembly (element evaluation + CSR rows + Dirichlet rows + nodal residual) against the oracle's
+    get_A / compute_residual and against the two-kernel path, on non-affine and unstructured meshes."""
+    import jax_fem_b200 as jf
+    import gpu_problems as gp
+    rng = np.random.default_rng(11)
+    iv = None
+    if case == "cylinder":
+        g = cases.load_golden("linear_elasticity_cylinder")
+        pts, cells = g["points"], g["cells"]
+        prob = gp.LinearElasticityCylinder(jf.Mesh(pts, cells), vec=3, dim=3, dirichlet_bc_info=cases.CYL_BC,
+                                           location_fns=[cases.top])
+        opb = fem.Problem(fem.Mesh(pts, cells), 3, 3, dirichlet_bc_info=cases.CYL_BC, location_fns=[cases.top],
+                          law=olaws.LinearElastic(70e3, 0.3), mass_map=cases.cyl_mass, surface_maps=[cases.cyl_traction])
+    else:
+        pts, cells = perturbed_box(9, seed=5)
+        bc = [[lambda p: np.isclose(p[0], 0., atol=0.03)] * 2 + [lambda p: np.isclose(p[2], 0.9, atol=0.03)], [0, 2, 1],
+              [lambda p: 0.01, lambda p: 0., lambda p: -0.02]]
+        if case == "simp":
+            iv = 0.2 + 0.7 * rng.uniform(0, 1, (len(cells), 8))
+            prob = gp.SIMPElasticity(jf.Mesh(pts, cells), vec=3, dim=3, dirichlet_bc_info=bc,
+                                     location_fns=[lambda p: np.isclose(p[0], 1.0, atol=0.03)])
+            prob.internal_vars = [torch.from_numpy(iv).cuda()]
+            opb = fem.Problem(fem.Mesh(pts, cells), 3, 3, dirichlet_bc_info=bc, law=olaws.SIMP(70e3, 70.0, 0.3, 3.0),
+                              internal_vars=[iv])
+        else:
+            prob = gp.PlainElasticity(jf.Mesh(pts, cells), vec=3, dim=3, dirichlet_bc_info=bc)
+            opb = fem.Problem(fem.Mesh(pts, cells), 3, 3, dirichlet_bc_info=bc, law=olaws.LinearElastic(70e3, 0.3))
+    sol = 0.01 * rng.standard_normal((len(pts), 3))
+    out = _assemble_both_ways(prob, sol, monkeypatch)
+    law_only = fem.Problem(fem.Mesh(pts, cells), 3, 3, law=opb.law, internal_vars=() if iv is None else [iv])
+    ores = np.zeros((len(pts), 3))
+    np.add.at(ores, cells.reshape(-1), law_only.cell_residuals(sol).reshape(-1, 3))
+    f_ext = host(prob._f_ext) if prob._f_ext is not None else 0.0
+    opb.newton_update(sol)
+    oA = fem.get_A(opb)
+    for mode in ("fused", "staged"):
+        res, data = out[mode]
+        assert relmax(data, oA.data) <= VAL_TOL, mode
+        assert relmax(res, ores + f_ext) <= VAL_TOL, mode
+    assert relmax(out["fused"][1], out["staged"][1]) <= 1e-14
+    # Dirichlet rows are exact unit rows in both
+    rows = host(prob.bc_data()[0])
+    indptr, indices = host(prob.plan.indptr), host(prob.plan.indices)
+    for r in rows[:: max(1, len(rows) // 50)]:
+        seg = out["fused"][1][indptr[r]:indptr[r + 1]]
+        assert np.array_equal(seg, (indices[indptr[r]:indptr[r + 1]] == r).astype(float))
+    # bit-reproducible, and reference attributes stay available after a fused assembly
+    monkeypatch.setenv("FEM_ASSEMBLY", "fused")
+    prob.newton_update([torch.from_numpy(sol).cuda()])
+    assert np.array_equal(host(jf.get_A(prob).data), out["fused"][1])
+    assert relmax(host(prob.element_tangents()), opb.cell_jacobians(sol)) <= VAL_TOL
+
+
+def test_fused_assembly_rejects_unregistered_combination():
+    from jax_fem_b200 import _lib
+    lib = _lib.load()
+    z = torch.zeros(64, dtype=torch.float64, device='cuda')
+    zi = torch.zeros(64, dtype=torch.int32, device='cuda')
+    P = _lib.ptr
+    code = lib.fem_assemble_fused(0, 3, 2, _lib.host_doubles([1., .3]), P(z), P(z), None, P(z), 1, *([P(zi)] * 12),
+                                  P(zi), None, P(z), P(z), None)
+    assert code == -1 and b"fused assembly is registered" in lib.fem_last_error()
