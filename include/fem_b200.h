@@ -88,18 +88,28 @@ int fem_hex27_residual_jacobian(int law_id, const double* law_params_host, const
  *            offset in the patch accumulator, len(n) | diagonal slot << 8
  *   lnodes: per patch the global ids of its local nodes (owned first);  pc_cell / pc_ln: per (patch, cell) the
  *            global cell id and the 8 local node numbers (uint8 x 8)
- *   ck_lane / ck_rnd: per chunk of 32 cells the first lane and the number of accumulation rounds
+ *   ck_cell / ck_lane / ck_rnd: per chunk (<= 32 or 16 cells, see config) the first patch-cell, the first lane and
+ *            the number of accumulation rounds
  *   ln_desc / ln_slot: per owned corner: cell-in-chunk | a<<5 | owned index<<8 | round<<16, and the 8 column slots
  * bc_flag: (3 n_nodes) bytes, 1 = Dirichlet row (zeroed, unit diagonal, pattern kept; solver.py:477,527-528).
- * f_ext: (n_nodes, 3) constant load vector or NULL.  Outputs: data (nnz) CSR values, res (n_nodes, 3).          */
+ * f_ext: (n_nodes, 3) constant load vector or NULL.  Outputs: data (nnz) CSR values, res (n_nodes, 3).
+ * config: which (patch size, chunk size) the tables were built for (patch_plan.CONFIGS index).                  */
 int fem_assemble_fused(int ele_type, int vec, int law_id, const double* law_params_host,
                        const double* points, const double* sol, const double* internal_var,
                        const double* ref_tables, int64_t n_patches, const int32_t* phdr,
                        const int32_t* pn_node, const int32_t* pn_out, const int32_t* pn_acc,
                        const int32_t* pn_info, const int32_t* lnodes, const int32_t* pc_cell,
-                       const int32_t* pc_ln, const int32_t* ck_lane, const int32_t* ck_rnd,
+                       const int32_t* pc_ln, const int32_t* ck_cell, const int32_t* ck_lane, const int32_t* ck_rnd,
                        const int32_t* ln_desc, const int32_t* ln_slot, const uint8_t* bc_flag,
-                       const double* f_ext, double* data, double* res, void* stream);
+                       const double* f_ext, double* data, double* res, int config, void* stream);
+
+/* Plan construction helper (HOST pointers, no CUDA): greedy split of every patch's cells into chunks of <= chunk
+ * cells in which no owned node occurs more than rmax times.  cell_ptr (n_patches+1); owned_idx (M, nodes_per_cell):
+ * owned-node index of the corner or 255; outputs: chunk of every patch-cell (inside its patch), round of every
+ * corner (255 = not owned), chunks per patch.                                                                    */
+int fem_patch_chunks_host(int64_t n_patches, const int64_t* cell_ptr_host, const uint8_t* owned_idx_host,
+                          int nodes_per_cell, int max_owned, int chunk, int rmax,
+                          int32_t* cell_chunk_host, uint8_t* rank_host, int32_t* n_chunks_host);
 
 /* ---- (2) global assembly: _PetscTangentCache.update / get_A (jax_fem/solver.py:469-553)
  *      as a precomputed cell->CSR-slot permutation + deterministic segmented sum (no atomics).

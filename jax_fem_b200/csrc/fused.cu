@@ -29,13 +29,15 @@
 namespace femb200 {
 namespace {
 
+// MAX_OWNED / CHUNK / RMAX mirror jax_fem_b200/patch_plan.py::CONFIGS; SPLIT = tasks per owned corner in phase 2
+// (8 / SPLIT column nodes each); CTAS = resident CTAs per SM the shared-memory footprint is sized for.
+template <int MAX_OWNED_, int CHUNK_, int THREADS_, int SPLIT_, int CTAS_>
 struct FusedCfg {
-  static constexpr int THREADS = 256;
-  static constexpr int CHUNK = 32;            // cells per chunk               (patch_plan.CHUNK)
-  static constexpr int MAX_OWNED = 64;        //                               (patch_plan.MAX_OWNED)
-  static constexpr int MAX_LOCAL = 256;       //                               (patch_plan.MAX_LOCAL + 1)
-  static constexpr int ACC = 64 * 27 * 9;     // accumulator doubles           (patch_plan.ACC_DOUBLES)
+  static constexpr int THREADS = THREADS_, CHUNK = CHUNK_, MAX_OWNED = MAX_OWNED_, SPLIT = SPLIT_, CTAS = CTAS_;
+  static constexpr int MAX_LOCAL = MAX_OWNED == 64 ? 256 : 160;   // (patch_plan max_local + 1)
+  static constexpr int ACC = MAX_OWNED * 27 * 9;                  // accumulator doubles (patch_plan acc_doubles)
   static constexpr int NN = 8, NQ = 8, DIM = 3, VEC = 3;
+  static constexpr int CPT = NN / SPLIT;                          // column nodes per task
   static constexpr int TAB_STRIDE = 25, TAB_SIZE = NQ * TAB_STRIDE + NQ;
   // record of (cell, q): g[8][3] | E w | pad | S[3][3] = sigma JxW | pad  -- 16-byte aligned pieces
   static constexpr int OFF_G = 0, OFF_E = 24, OFF_S = 26, QREC = 36;
@@ -43,10 +45,13 @@ struct FusedCfg {
   static constexpr int OFF_TAB = 0;
   static constexpr int OFF_ACC = OFF_TAB + TAB_SIZE;
   static constexpr int OFF_RACC = OFF_ACC + ACC;
-  static constexpr int OFF_XU = OFF_RACC + MAX_OWNED * VEC;
+  static constexpr int OFF_FEXT = OFF_RACC + MAX_OWNED * VEC;
+  static constexpr int OFF_XU = OFF_FEXT + MAX_OWNED * VEC;
   static constexpr int OFF_REC = OFF_XU + MAX_LOCAL * (DIM + VEC);
   static constexpr int OFF_INT = OFF_REC + CHUNK * CELLREC;
-  static constexpr int SMEM_DOUBLES = OFF_INT + (4 * MAX_OWNED) / 2;
+  static constexpr int SMEM_DOUBLES = OFF_INT + (5 * MAX_OWNED) / 2;
+  static_assert(CHUNK * NQ <= THREADS, "phase 1 needs one thread per (cell, q)");
+  static_assert(SPLIT == 2 || SPLIT == 4, "column split");
 };
 
 struct FusedArgs {
@@ -54,7 +59,7 @@ struct FusedArgs {
   const double* sol;
   const double* iv;
   const double* ref;
-  const int32_t *phdr, *pn_node, *pn_out, *pn_acc, *pn_info, *lnodes, *pc_cell, *pc_ln, *ck_lane, *ck_rnd, *ln_desc, *ln_slot;
+  const int32_t *phdr, *pn_node, *pn_out, *pn_acc, *pn_info, *lnodes, *pc_cell, *pc_ln, *ck_cell, *ck_lane, *ck_rnd, *ln_desc, *ln_slot;
   const uint8_t* bc_flag;
   const double* f_ext;
   double* data;
@@ -63,20 +68,20 @@ struct FusedArgs {
   double p[8];
 };
 
-template <int LAW>
-__global__ void __launch_bounds__(FusedCfg::THREADS, 1) fused_assembly_kernel(const FusedArgs A) {
-  using L = FusedCfg;
-  constexpr int NN = L::NN, NQ = L::NQ, DIM = L::DIM, VEC = L::VEC;
+template <int LAW, class L>
+__global__ void __launch_bounds__(L::THREADS, L::CTAS) fused_assembly_kernel(const FusedArgs A) {
+  constexpr int NN = L::NN, NQ = L::NQ, DIM = L::DIM, VEC = L::VEC, SPLIT = L::SPLIT, CPT = L::CPT;
   extern __shared__ __align__(16) double sm[];
   double* tab = sm + L::OFF_TAB;
   double* acc = sm + L::OFF_ACC;
   double* racc = sm + L::OFF_RACC;
+  double* fext = sm + L::OFF_FEXT;
   double* xu = sm + L::OFF_XU;
   double* recs = sm + L::OFF_REC;
   int* s_node = reinterpret_cast<int*>(sm + L::OFF_INT);
   int* s_out = s_node + L::MAX_OWNED;
   int* s_acc = s_out + L::MAX_OWNED;
-  int* s_info = s_acc + L::MAX_OWNED;
+  int* s_info = s_acc + L::MAX_OWNED;      // len | diagonal slot << 8 | Dirichlet flags << 16
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   for (int i = tid; i < NQ * NN * DIM; i += L::THREADS) tab[(i / (NN * DIM)) * L::TAB_STRIDE + i % (NN * DIM)] = A.ref[i];
@@ -89,14 +94,18 @@ __global__ void __launch_bounds__(FusedCfg::THREADS, 1) fused_assembly_kernel(co
 #pragma unroll 1
   for (int patch = blockIdx.x; patch < A.n_patches; patch += gridDim.x) {
     const int* h0 = A.phdr + (int64_t)patch * 8;
-    const int node0 = h0[0], lnode0 = h0[1], cell0 = h0[2], chunk0 = h0[3];
-    const int n_owned = h0[8] - node0, n_local = h0[9] - lnode0, n_cells = h0[10] - cell0, n_chunks = h0[11] - chunk0;
-    __syncthreads();            // previous patch: epilogue done with s_*, xu
+    const int node0 = h0[0], lnode0 = h0[1], chunk0 = h0[3];
+    const int n_owned = h0[8] - node0, n_local = h0[9] - lnode0, n_chunks = h0[11] - chunk0;
+    __syncthreads();            // previous patch: epilogue done with s_*, xu, fext
     if (tid < n_owned) {
-      s_node[tid] = A.pn_node[node0 + tid];
+      const int n = A.pn_node[node0 + tid];
+      const uint8_t* f = A.bc_flag + 3 * (int64_t)n;
+      s_node[tid] = n;
       s_out[tid] = A.pn_out[node0 + tid];
       s_acc[tid] = A.pn_acc[node0 + tid];
-      s_info[tid] = A.pn_info[node0 + tid];
+      s_info[tid] = A.pn_info[node0 + tid] | ((f[0] ? 1 : 0) << 16) | ((f[1] ? 1 : 0) << 17) | ((f[2] ? 1 : 0) << 18);
+#pragma unroll
+      for (int d = 0; d < VEC; ++d) fext[tid * 3 + d] = A.f_ext ? A.f_ext[3 * (int64_t)n + d] : 0.0;
     }
     for (int i = tid; i < n_local; i += L::THREADS) {
       const int64_t node = A.lnodes[lnode0 + i];
@@ -109,12 +118,23 @@ __global__ void __launch_bounds__(FusedCfg::THREADS, 1) fused_assembly_kernel(co
 
 #pragma unroll 1
     for (int k = 0; k < n_chunks; ++k) {
-      const int ncell = min(L::CHUNK, n_cells - k * L::CHUNK);
+      const int c0 = A.ck_cell[chunk0 + k], ncell = A.ck_cell[chunk0 + k + 1] - c0;
+      // phase-2 metadata of this chunk: issued before phase 1 so that the loads overlap it
+      const int l0 = A.ck_lane[chunk0 + k], l1 = A.ck_lane[chunk0 + k + 1];
+      const int rounds = A.ck_rnd[chunk0 + k];
+      const int ntask = SPLIT * (l1 - l0);
+      int desc0 = 0, slot0 = 0;
+      if (tid < ntask) {
+        desc0 = A.ln_desc[l0 + tid / SPLIT];
+        slot0 = A.ln_slot[2 * (int64_t)(l0 + tid / SPLIT) + ((tid % SPLIT) * CPT) / 4];
+      }
       // ---------------- phase 1: thread = (cell, q) ----------------
       if (tid < ncell * NQ) {
         const int cl = tid >> 3, q = tid & 7;
-        const int pc = cell0 + k * L::CHUNK + cl;
+        const int pc = c0 + cl;
         const int2 lw = reinterpret_cast<const int2*>(A.pc_ln)[pc];
+        const double* ivq = A.iv ? A.iv + (int64_t)A.pc_cell[pc] * NQ + q : nullptr;
+        const double E = iso_modulus<LAW>(A.p, ivq, false);
         double X[NN * DIM], U[NN * VEC];
 #pragma unroll
         for (int n = 0; n < NN; ++n) {
@@ -128,8 +148,6 @@ __global__ void __launch_bounds__(FusedCfg::THREADS, 1) fused_assembly_kernel(co
         const double w = qp_geometry<NN, DIM>(X, tab + q * L::TAB_STRIDE, tab[NQ * L::TAB_STRIDE + q], g);
         double ug[VEC][DIM];
         qp_grad_u<NN, DIM, VEC>(U, g, ug);
-        const double* ivq = A.iv ? A.iv + (int64_t)A.pc_cell[pc] * NQ + q : nullptr;
-        const double E = iso_modulus<LAW>(A.p, ivq, false);
         const double mu = E / (2.0 * (1.0 + nu)), lam = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
         double sig[DIM][DIM];
         iso_stress<DIM>(lam, mu, ug, sig);
@@ -145,25 +163,23 @@ __global__ void __launch_bounds__(FusedCfg::THREADS, 1) fused_assembly_kernel(co
       }
       __syncthreads();
 
-      // ---------------- phase 2: thread = (owned corner, column half) ----------------
-      const int l0 = A.ck_lane[chunk0 + k], l1 = A.ck_lane[chunk0 + k + 1];
-      const int rounds = A.ck_rnd[chunk0 + k];
-      const int ntask = 2 * (l1 - l0);
+      // ---------------- phase 2: thread = (owned corner, column part) ----------------
 #pragma unroll 1
       for (int t0 = 0; t0 < ntask; t0 += L::THREADS) {
         const int t = t0 + tid;
         const bool valid = t < ntask;
-        const int li = l0 + (t >> 1), h = t & 1;
-        int desc = 0, slots = 0;
-        if (valid) {
-          desc = A.ln_desc[li];
-          slots = A.ln_slot[2 * (int64_t)li + h];
+        const int h = t % SPLIT;
+        int desc = desc0, slots = slot0;
+        if (t0 > 0 && valid) {
+          desc = A.ln_desc[l0 + t / SPLIT];
+          slots = A.ln_slot[2 * (int64_t)(l0 + t / SPLIT) + (h * CPT) / 4];
         }
+        slots >>= 8 * ((h * CPT) % 4);
         const int cl = desc & 31, a = (desc >> 5) & 7, nl = (desc >> 8) & 255, rk = (desc >> 16) & 255;
-        double K[4][3][3];
+        double K[CPT][3][3];
         double r[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < CPT; ++j)
 #pragma unroll
           for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -174,26 +190,26 @@ __global__ void __launch_bounds__(FusedCfg::THREADS, 1) fused_assembly_kernel(co
           for (int q = 0; q < NQ; ++q) {
             const double* rq = rec + q * L::QREC;
             const double ew = rq[L::OFF_E];
-            double ga[3], gw[3], gb[12];
+            double ga[3], gw[3], gb[CPT * 3];
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
               ga[d] = rq[L::OFF_G + a * 3 + d];
               gw[d] = ga[d] * ew;
             }
 #pragma unroll
-            for (int u = 0; u < 6; ++u) {
-              const double2 v = reinterpret_cast<const double2*>(rq + L::OFF_G + h * 12)[u];
+            for (int u = 0; u < CPT * 3 / 2; ++u) {
+              const double2 v = reinterpret_cast<const double2*>(rq + L::OFF_G + h * (CPT * 3))[u];
               gb[2 * u] = v.x;
               gb[2 * u + 1] = v.y;
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < CPT; ++j)
 #pragma unroll
               for (int i = 0; i < 3; ++i)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) K[j][i][c] = fma(gw[i], gb[j * 3 + c], K[j][i][c]);
-            // element residual r_a = sum_q S_q g_a(q): this half takes the quadrature points q = 4h .. 4h+3
-            if ((q >> 2) == h) {
+            // element residual r_a = sum_q S_q g_a(q): part h takes the quadrature points q = h NQ/SPLIT ...
+            if (q / (NQ / SPLIT) == h) {
 #pragma unroll
               for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -201,7 +217,7 @@ __global__ void __launch_bounds__(FusedCfg::THREADS, 1) fused_assembly_kernel(co
             }
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < CPT; ++j) {
             double G[3][3];
             double tr = 0.0;
 #pragma unroll
@@ -216,12 +232,12 @@ __global__ void __launch_bounds__(FusedCfg::THREADS, 1) fused_assembly_kernel(co
               for (int c = 0; c < 3; ++c) K[j][i][c] = lam1 * G[i][c] + mu1 * G[c][i] + (i == c ? mu1 * tr : 0.0);
           }
         }
-        // the two halves of a corner sit in adjacent lanes: r = r(q<4) + r(q>=4), kept by the half-0 lane
+        // the SPLIT parts of a corner sit in adjacent lanes: butterfly sum of the partial residuals (commutative =>
+        // every lane of the group holds the same bits); the part-0 lane adds it to the node
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const double o = __shfl_xor_sync(0xffffffffu, r[i], 1);
-          r[i] = (h == 0) ? r[i] + o : o + r[i];
-        }
+        for (int o = 1; o < SPLIT; o <<= 1)
+#pragma unroll
+          for (int i = 0; i < 3; ++i) r[i] += __shfl_xor_sync(0xffffffffu, r[i], o);
         // ---- ordered accumulation into the patch's CSR-shaped rows ----
         const int len3 = valid ? 3 * (s_info[nl] & 255) : 0;
         double* rowp = acc + (valid ? s_acc[nl] : 0);
@@ -229,7 +245,7 @@ __global__ void __launch_bounds__(FusedCfg::THREADS, 1) fused_assembly_kernel(co
         for (int rd = 0; rd < rounds; ++rd) {
           if (valid && rk == rd) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < CPT; ++j) {
               double* p = rowp + 3 * ((slots >> (8 * j)) & 255);
 #pragma unroll
               for (int i = 0; i < 3; ++i)
@@ -250,40 +266,43 @@ __global__ void __launch_bounds__(FusedCfg::THREADS, 1) fused_assembly_kernel(co
     // ---------------- epilogue: Dirichlet rows, coalesced copy-out, re-zero ----------------
     for (int i = warp; i < n_owned; i += L::THREADS / 32) {
       const int n = s_node[i], info = s_info[i];
-      const int len = info & 255, dg = info >> 8;
+      const int len = info & 255, dg = (info >> 8) & 255, fl = info >> 16;
       const int tot = 9 * len, len3 = 3 * len;
       double* src = acc + s_acc[i];
       double* dst = A.data + s_out[i];
-      const uint8_t* f = A.bc_flag + 3 * (int64_t)n;
-      const int f0 = f[0], f1 = f[1], f2 = f[2];
       for (int e = lane; e < tot; e += 32) {
         double v = src[e];
         src[e] = 0.0;
-        if (f0 | f1 | f2) {
+        if (fl) {
           const int row = e / len3, col = e - row * len3;
-          const int fl = row == 0 ? f0 : (row == 1 ? f1 : f2);
-          if (fl) v = (col == 3 * dg + row) ? 1.0 : 0.0;
+          if ((fl >> row) & 1) v = (col == 3 * dg + row) ? 1.0 : 0.0;
         }
         dst[e] = v;
       }
       if (lane < 3) {
-        A.res[3 * (int64_t)n + lane] = racc[i * 3 + lane] + (A.f_ext ? A.f_ext[3 * (int64_t)n + lane] : 0.0);
+        A.res[3 * (int64_t)n + lane] = racc[i * 3 + lane] + fext[i * 3 + lane];
         racc[i * 3 + lane] = 0.0;
       }
     }
   }
 }
 
-template <int LAW>
+template <int LAW, class L>
 int launch_fused(const FusedArgs& A, cudaStream_t st) {
-  using L = FusedCfg;
   const size_t smem = sizeof(double) * L::SMEM_DOUBLES;
-  auto k = fused_assembly_kernel<LAW>;
+  auto k = fused_assembly_kernel<LAW, L>;
   FEM_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = A.n_patches < kNumSM ? A.n_patches : kNumSM;
+  const int want = kNumSM * L::CTAS;
+  const int grid = A.n_patches < want ? A.n_patches : want;
   k<<<grid, L::THREADS, smem, st>>>(A);
   FEM_LAUNCH_CHECK();
   return FEM_OK;
+}
+
+template <class L>
+int launch_fused_law(int law_id, const FusedArgs& A, cudaStream_t st) {
+  if (law_id == FEM_LAW_SIMP) return launch_fused<FEM_LAW_SIMP, L>(A, st);
+  return launch_fused<FEM_LAW_LINEAR_ELASTIC, L>(A, st);
 }
 
 }  // namespace
@@ -296,12 +315,12 @@ extern "C" int fem_assemble_fused(int ele_type, int vec, int law_id, const doubl
                                   const double* ref_tables, int64_t n_patches, const int32_t* phdr,
                                   const int32_t* pn_node, const int32_t* pn_out, const int32_t* pn_acc,
                                   const int32_t* pn_info, const int32_t* lnodes, const int32_t* pc_cell,
-                                  const int32_t* pc_ln, const int32_t* ck_lane, const int32_t* ck_rnd,
+                                  const int32_t* pc_ln, const int32_t* ck_cell, const int32_t* ck_lane, const int32_t* ck_rnd,
                                   const int32_t* ln_desc, const int32_t* ln_slot, const uint8_t* bc_flag,
-                                  const double* f_ext, double* data, double* res, void* stream) {
+                                  const double* f_ext, double* data, double* res, int config, void* stream) {
   if (int e = check_device()) return e;
   FEM_REQUIRE(points && sol && ref_tables && law_params_host && phdr && pn_node && pn_out && pn_acc && pn_info &&
-                  lnodes && pc_cell && pc_ln && ck_lane && ck_rnd && ln_desc && ln_slot && bc_flag && data && res,
+                  lnodes && pc_cell && pc_ln && ck_cell && ck_lane && ck_rnd && ln_desc && ln_slot && bc_flag && data && res,
               "null pointer");
   FEM_REQUIRE(n_patches >= 0 && n_patches < (1ll << 31), "n_patches out of range");
   if (!(ele_type == FEM_ELE_HEX8 && vec == 3 && (law_id == FEM_LAW_LINEAR_ELASTIC || law_id == FEM_LAW_SIMP))) {
@@ -314,9 +333,16 @@ extern "C" int fem_assemble_fused(int ele_type, int vec, int law_id, const doubl
   FusedArgs A{};
   A.points = points; A.sol = sol; A.iv = internal_var; A.ref = ref_tables;
   A.phdr = phdr; A.pn_node = pn_node; A.pn_out = pn_out; A.pn_acc = pn_acc; A.pn_info = pn_info; A.lnodes = lnodes;
-  A.pc_cell = pc_cell; A.pc_ln = pc_ln; A.ck_lane = ck_lane; A.ck_rnd = ck_rnd; A.ln_desc = ln_desc; A.ln_slot = ln_slot;
+  A.pc_cell = pc_cell; A.pc_ln = pc_ln; A.ck_cell = ck_cell; A.ck_lane = ck_lane; A.ck_rnd = ck_rnd; A.ln_desc = ln_desc; A.ln_slot = ln_slot;
   A.bc_flag = bc_flag; A.f_ext = f_ext; A.data = data; A.res = res; A.n_patches = (int)n_patches;
   for (int i = 0; i < 8; ++i) A.p[i] = law_params_host[i];
-  if (law_id == FEM_LAW_SIMP) return launch_fused<FEM_LAW_SIMP>(A, (cudaStream_t)stream);
-  return launch_fused<FEM_LAW_LINEAR_ELASTIC>(A, (cudaStream_t)stream);
+  // config == index into jax_fem_b200/patch_plan.py::CONFIGS (the tables must have been built for it)
+  switch (config) {
+    case 0: return launch_fused_law<FusedCfg<64, 32, 256, 2, 1>>(law_id, A, (cudaStream_t)stream);
+    case 1: return launch_fused_law<FusedCfg<32, 16, 256, 4, 2>>(law_id, A, (cudaStream_t)stream);
+    case 2: return launch_fused_law<FusedCfg<32, 16, 128, 2, 2>>(law_id, A, (cudaStream_t)stream);
+    case 3: return launch_fused_law<FusedCfg<32, 16, 256, 2, 2>>(law_id, A, (cudaStream_t)stream);
+  }
+  set_error("unknown fused-assembly configuration %d", config);
+  return FEM_EINVAL;
 }

@@ -26,7 +26,7 @@ import torch
 from . import _lib, laws, logger
 from .fe import FiniteElement, evaluate_point_fn
 from .generate_mesh import Mesh
-from .patch_plan import build_patch_plan
+from .patch_plan import DEFAULT_CONFIG, build_patch_plan
 from .plan import build_plan
 
 
@@ -225,8 +225,10 @@ class Problem:
     @property
     def patch_plan(self):
         if self._patch_plan is None:
+            import os
             self._patch_plan = build_patch_plan(self._points, self._cells, self.fes[0].num_total_nodes, self.fes[0].vec,
-                                                self.plan.brow_ptr, self.plan.bcol)
+                                                self.plan.brow_ptr, self.plan.bcol,
+                                                config=int(os.environ.get('FEM_FUSED_CONFIG', DEFAULT_CONFIG)))
         return self._patch_plan
 
     def _run_fused(self, sol):
@@ -240,8 +242,9 @@ class Problem:
         _lib.check(_lib.load().fem_assemble_fused(
             _lib.ELE[self.ele_type], fe.vec, self._law.law_id, _lib.host_doubles(self._law.params()),
             P(self._points), P(sol), P(iv), P(self._ref), pp.n_patches, P(pp.phdr), P(pp.pn_node), P(pp.pn_out),
-            P(pp.pn_acc), P(pp.pn_info), P(pp.lnodes), P(pp.pc_cell), P(pp.pc_ln), P(pp.ck_lane), P(pp.ck_rnd),
-            P(pp.ln_desc), P(pp.ln_slot), P(flag), P(self._f_ext), P(data), P(res), _lib.stream_ptr()))
+            P(pp.pn_acc), P(pp.pn_info), P(pp.lnodes), P(pp.pc_cell), P(pp.pc_ln), P(pp.ck_cell), P(pp.ck_lane),
+            P(pp.ck_rnd), P(pp.ln_desc), P(pp.ln_slot), P(flag), P(self._f_ext), P(data), P(res), pp.config,
+            _lib.stream_ptr()))
         self._A_data, self._A_bc_key = data, self._bc_cache[0]
         return res
 

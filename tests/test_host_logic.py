@@ -171,8 +171,8 @@ def test_product_never_imports_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
 
 
-def _patch_plan_case(points, cells, bc_info, law):
-    from jax_fem_b200.patch_plan import build_patch_plan, emulate
+def _patch_plan_case(points, cells, bc_info, law, config):
+    from jax_fem_b200.patch_plan import CONFIGS, build_patch_plan, emulate
     pb = fem.Problem(fem.Mesh(points, cells), 3, 3, dirichlet_bc_info=bc_info, law=law)
     nn = len(points)
     sol = np.random.default_rng(1).standard_normal((nn, 3)) * 1e-3
@@ -181,7 +181,9 @@ def _patch_plan_case(points, cells, bc_info, law):
     pb.newton_update(sol)
     A = fem.get_A(pb)
     plan = build_plan(torch.from_numpy(cells), nn, 3)
-    pp = build_patch_plan(torch.from_numpy(points), torch.from_numpy(cells), nn, 3, plan.brow_ptr, plan.bcol)
+    pp = build_patch_plan(torch.from_numpy(points), torch.from_numpy(cells), nn, 3, plan.brow_ptr, plan.bcol, config=config)
+    cfg = CONFIGS[config]
+    assert pp.ck_rnd.max() <= cfg.rmax and np.diff(pp.ck_cell.numpy()).max() <= cfg.chunk
     flag = np.zeros(3 * nn, dtype=np.uint8)
     for rows in pb.bc_rows():
         flag[rows] = 1
@@ -196,19 +198,23 @@ def _patch_plan_case(points, cells, bc_info, law):
     return pp
 
 
-def test_patch_plan_structured_box():
+@pytest.mark.parametrize("config", [0, 1])
+def test_patch_plan_structured_box(config):
     """Fused owner-computes assembly tables: walking them in the kernel's order reproduces the oracle's CSR
     (Dirichlet rows included) and nodal residual on a box whose sides are not multiples of the patch edge."""
     m = fem.box_mesh(6, 9, 5, 1., 1.5, 1.)
-    pp = _patch_plan_case(m.points, m.cells, cases.CUBE_BC, olaws.LinearElastic(70e3, 0.3))
-    assert pp.n_patches == 2 * 3 * 2                       # 7 x 10 x 6 nodes in bricks of 4 layers
+    pp = _patch_plan_case(m.points, m.cells, cases.CUBE_BC, olaws.LinearElastic(70e3, 0.3), config)
+    assert pp.n_patches == (2, 4)[config] * 3 * 2          # 7 x 10 x 6 nodes in bricks of 4 (2) x 4 x 4 layers
     hdr = pp.phdr.numpy()
-    assert np.diff(hdr[:, 0]).max() == 64 and np.diff(hdr[:, 1]).max() <= 216
+    assert np.diff(hdr[:, 0]).max() == (64, 32)[config] and np.diff(hdr[:, 1]).max() <= (216, 144)[config]
     assert np.array_equal(np.sort(pp.pn_node.numpy()), np.arange(len(m.points)))
 
 
-def test_patch_plan_unstructured_golden_mesh():
+@pytest.mark.parametrize("config", [0, 1])
+def test_patch_plan_unstructured_golden_mesh(config):
+    from jax_fem_b200.patch_plan import CONFIGS
     g = cases.load_golden("linear_elasticity_cylinder")
-    pp = _patch_plan_case(g["points"], g["cells"], cases.CYL_BC, olaws.LinearElastic(70e3, 0.3))
-    hdr = pp.phdr.numpy()
-    assert np.diff(hdr[:, 0]).max() <= 64 and np.diff(hdr[:, 1]).max() <= 255 and hdr[:-1, 4].max() <= 64 * 27 * 9
+    pp = _patch_plan_case(g["points"], g["cells"], cases.CYL_BC, olaws.LinearElastic(70e3, 0.3), config)
+    hdr, cfg = pp.phdr.numpy(), CONFIGS[config]
+    assert np.diff(hdr[:, 0]).max() <= cfg.max_owned and np.diff(hdr[:, 1]).max() <= cfg.max_local
+    assert hdr[:-1, 4].max() <= cfg.acc_doubles
