@@ -87,7 +87,8 @@ int fem_hex27_residual_jacobian(int law_id, const double* law_params_host, const
  *   pn_node, pn_out, pn_acc, pn_info: per owned node: global id, offset of its rows in `data` (= 9 brow_ptr[n]),
  *            offset in the patch accumulator, len(n) | diagonal slot << 8
  *   lnodes: per patch the global ids of its local nodes (owned first);  pc_cell / pc_ln: per (patch, cell) the
- *            global cell id and the 8 local node numbers (uint8 x 8)
+ *            global cell id and the 8 local node numbers (uint8 x 8);  pc_lm: per (patch, cell) its first lane and
+ *            the mask of corners the patch owns
  *   ck_cell / ck_lane / ck_rnd: per chunk (<= 32 or 16 cells, see config) the first patch-cell, the first lane and
  *            the number of accumulation rounds
  *   ln_desc / ln_slot: per owned corner: cell-in-chunk | a<<5 | owned index<<8 | round<<16, and the 8 column slots
@@ -99,7 +100,7 @@ int fem_assemble_fused(int ele_type, int vec, int law_id, const double* law_para
                        const double* ref_tables, int64_t n_patches, const int32_t* phdr,
                        const int32_t* pn_node, const int32_t* pn_out, const int32_t* pn_acc,
                        const int32_t* pn_info, const int32_t* lnodes, const int32_t* pc_cell,
-                       const int32_t* pc_ln, const int32_t* ck_cell, const int32_t* ck_lane, const int32_t* ck_rnd,
+                       const int32_t* pc_ln, const int32_t* pc_lm, const int32_t* ck_cell, const int32_t* ck_lane, const int32_t* ck_rnd,
                        const int32_t* ln_desc, const int32_t* ln_slot, const uint8_t* bc_flag,
                        const double* f_ext, double* data, double* res, int config, void* stream);
 

@@ -22,7 +22,7 @@ _SIGNATURES = {
     "fem_device_count": (_i, []),
     "fem_element_residual_jacobian": (_i, [_i, _i, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fem_hex27_residual_jacobian": (_i, [_i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
-    "fem_assemble_fused": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64] + [_vp] * 17 + [_i, _vp]),
+    "fem_assemble_fused": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64] + [_vp] * 18 + [_i, _vp]),
     "fem_patch_chunks_host": (_i, [_i64, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "fem_gather_csr": (_i, [_i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fem_gather_residual": (_i, [_i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -59,7 +59,7 @@ struct FusedArgs {
   const double* sol;
   const double* iv;
   const double* ref;
-  const int32_t *phdr, *pn_node, *pn_out, *pn_acc, *pn_info, *lnodes, *pc_cell, *pc_ln, *ck_cell, *ck_lane, *ck_rnd, *ln_desc, *ln_slot;
+  const int32_t *phdr, *pn_node, *pn_out, *pn_acc, *pn_info, *lnodes, *pc_cell, *pc_ln, *pc_lm, *ck_cell, *ck_lane, *ck_rnd, *ln_desc, *ln_slot;
   const uint8_t* bc_flag;
   const double* f_ext;
   double* data;
@@ -299,6 +299,250 @@ int launch_fused(const FusedArgs& A, cudaStream_t st) {
   return FEM_OK;
 }
 
+// ---- DMMA variant ----------------------------------------------------------------------------------------------
+// The CUDA-core phase 2 above is bound by shared-memory bandwidth (one wavefront per operand double and lane, plus
+// the read-modify-write of the accumulator).  Here the element tangent of a cell is formed by ONE warp on the FP64
+// tensor cores exactly as in element.cu::element_dmma_kernel (G = sum_q (E_q w_q g(q)) g(q)^T as a 3x3 grid of 8x8
+// tiles, 18 + 6 mma.sync.m8n8k4.f64, 8 + 6 operand loads per lane and cell), lane (n, t) ends up with the blocks
+// K[n][2t], K[n][2t+1] of row corner n and adds them into the patch accumulator if the patch owns that corner.
+// Inside a cell no two lanes touch the same accumulator word; the plan's chunks hold <= 8 cells (one per warp) that
+// share no owned node (rmax = 1), so a barrier between chunks is the only ordering needed.  Cells on the patch
+// surface pay the full tile for the few rows that are kept (125 cells per 64 owned nodes).
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+struct FusedDmmaCfg {
+  static constexpr int THREADS = 256, WARPS = 8, MAX_OWNED = 64, MAX_LOCAL = 256;
+  static constexpr int SUB = 8;                    // cells per chunk (patch_plan CONFIGS[4].chunk) = warps
+  static constexpr int NSUB = 4;                   // chunks per phase-1 batch
+  static constexpr int BATCH = SUB * NSUB;
+  static constexpr int ACC = MAX_OWNED * 27 * 9;
+  static constexpr int NN = 8, NQ = 8, DIM = 3, VEC = 3;
+  static constexpr int TAB_STRIDE = 25, TAB_SIZE = NQ * TAB_STRIDE + NQ;
+  static constexpr int GS = 28;                    // per-q stride of g[n][d]: 12 (mod 16) => conflict-free fragments
+  static constexpr int OFF_G = 0, OFF_S = NQ * GS, OFF_E = OFF_S + NQ * 9;
+  static constexpr int CELL = OFF_E + NQ + 2;      // 306: cell stride 2 (mod 16) spreads the phase-1 stores
+  static constexpr int OFF_TAB = 0;
+  static constexpr int OFF_ACC = OFF_TAB + TAB_SIZE;
+  static constexpr int OFF_RACC = OFF_ACC + ACC;
+  static constexpr int OFF_FEXT = OFF_RACC + MAX_OWNED * VEC;
+  static constexpr int OFF_XU = OFF_FEXT + MAX_OWNED * VEC;
+  static constexpr int OFF_CELLS = OFF_XU + MAX_LOCAL * (DIM + VEC);
+  static constexpr int OFF_INT = OFF_CELLS + BATCH * CELL;
+  static constexpr int SMEM_DOUBLES = OFF_INT + (5 * MAX_OWNED) / 2;
+};
+
+template <int LAW>
+__global__ void __launch_bounds__(FusedDmmaCfg::THREADS, 1) fused_dmma_kernel(const FusedArgs A) {
+  using L = FusedDmmaCfg;
+  constexpr int NN = L::NN, NQ = L::NQ, DIM = L::DIM, VEC = L::VEC;
+  extern __shared__ __align__(16) double sm[];
+  double* tab = sm + L::OFF_TAB;
+  double* acc = sm + L::OFF_ACC;
+  double* racc = sm + L::OFF_RACC;
+  double* fext = sm + L::OFF_FEXT;
+  double* xu = sm + L::OFF_XU;
+  double* cellsm = sm + L::OFF_CELLS;
+  int* s_node = reinterpret_cast<int*>(sm + L::OFF_INT);
+  int* s_out = s_node + L::MAX_OWNED;
+  int* s_acc = s_out + L::MAX_OWNED;
+  int* s_info = s_acc + L::MAX_OWNED;      // len | diagonal slot << 8 | Dirichlet flags << 16
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < NQ * NN * DIM; i += L::THREADS) tab[(i / (NN * DIM)) * L::TAB_STRIDE + i % (NN * DIM)] = A.ref[i];
+  if (tid < NQ) tab[NQ * L::TAB_STRIDE + tid] = A.ref[NQ * NN * DIM + tid];
+  for (int i = tid; i < L::ACC + L::MAX_OWNED * VEC; i += L::THREADS) acc[i] = 0.0;   // acc and racc are adjacent
+
+  const double nu = iso_nu<LAW>(A.p);
+  const double mu1 = 1.0 / (2.0 * (1.0 + nu)), lam1 = nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
+  const int n = lane >> 2, t = lane & 3;     // phase 2: row corner n, column pair t
+
+#pragma unroll 1
+  for (int patch = blockIdx.x; patch < A.n_patches; patch += gridDim.x) {
+    const int* h0 = A.phdr + (int64_t)patch * 8;
+    const int node0 = h0[0], lnode0 = h0[1], chunk0 = h0[3];
+    const int n_owned = h0[8] - node0, n_local = h0[9] - lnode0, n_chunks = h0[11] - chunk0;
+    __syncthreads();            // previous patch: epilogue done with s_*, xu, fext
+    if (tid < n_owned) {
+      const int nd = A.pn_node[node0 + tid];
+      const uint8_t* f = A.bc_flag + 3 * (int64_t)nd;
+      s_node[tid] = nd;
+      s_out[tid] = A.pn_out[node0 + tid];
+      s_acc[tid] = A.pn_acc[node0 + tid];
+      s_info[tid] = A.pn_info[node0 + tid] | ((f[0] ? 1 : 0) << 16) | ((f[1] ? 1 : 0) << 17) | ((f[2] ? 1 : 0) << 18);
+#pragma unroll
+      for (int d = 0; d < VEC; ++d) fext[tid * 3 + d] = A.f_ext ? A.f_ext[3 * (int64_t)nd + d] : 0.0;
+    }
+    for (int i = tid; i < n_local; i += L::THREADS) {
+      const int64_t node = A.lnodes[lnode0 + i];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) xu[i * 6 + d] = A.points[node * DIM + d];
+#pragma unroll
+      for (int d = 0; d < VEC; ++d) xu[i * 6 + 3 + d] = A.sol[node * VEC + d];
+    }
+    __syncthreads();
+
+#pragma unroll 1
+    for (int k0 = 0; k0 < n_chunks; k0 += L::NSUB) {
+      const int nsub = min(L::NSUB, n_chunks - k0);
+      const int cbase = A.ck_cell[chunk0 + k0];
+      const int ncell = A.ck_cell[chunk0 + k0 + nsub] - cbase;
+      // phase-2 metadata of the warp's cells (one per chunk of the batch), fetched ahead of phase 1:
+      // cw[s] = cell index inside the batch or -1, desc/slots of the lane's corner if the patch owns it
+      int cw[L::NSUB], desc[L::NSUB], slots[L::NSUB];
+#pragma unroll
+      for (int s = 0; s < L::NSUB; ++s) {
+        cw[s] = -1;
+        desc[s] = -1;
+        slots[s] = 0;
+        if (s < nsub) {
+          const int c0 = A.ck_cell[chunk0 + k0 + s], c1 = A.ck_cell[chunk0 + k0 + s + 1];
+          if (c0 + warp < c1) {
+            cw[s] = c0 + warp - cbase;
+            const int2 lm = reinterpret_cast<const int2*>(A.pc_lm)[c0 + warp];      // first lane, owned-corner mask
+            if ((lm.y >> n) & 1) {
+              const int li = lm.x + __popc(lm.y & ((1 << n) - 1));
+              desc[s] = A.ln_desc[li];
+              slots[s] = A.ln_slot[2 * (int64_t)li + (t >> 1)] >> (16 * (t & 1));
+            }
+          }
+        }
+      }
+      // ---------------- phase 1: thread = (cell, q) ----------------
+      if (tid < ncell * NQ) {
+        const int cl = tid >> 3, q = tid & 7;
+        const int pc = cbase + cl;
+        const int2 lw = reinterpret_cast<const int2*>(A.pc_ln)[pc];
+        const double* ivq = A.iv ? A.iv + (int64_t)A.pc_cell[pc] * NQ + q : nullptr;
+        const double E = iso_modulus<LAW>(A.p, ivq, false);
+        double X[NN * DIM], U[NN * VEC];
+#pragma unroll
+        for (int m = 0; m < NN; ++m) {
+          const int ln = ((m < 4 ? lw.x : lw.y) >> (8 * (m & 3))) & 255;
+          const double2* src = reinterpret_cast<const double2*>(xu + ln * 6);
+          const double2 v0 = src[0], v1 = src[1], v2 = src[2];
+          X[m * 3 + 0] = v0.x; X[m * 3 + 1] = v0.y; X[m * 3 + 2] = v1.x;
+          U[m * 3 + 0] = v1.y; U[m * 3 + 1] = v2.x; U[m * 3 + 2] = v2.y;
+        }
+        double g[NN][DIM];
+        const double w = qp_geometry<NN, DIM>(X, tab + q * L::TAB_STRIDE, tab[NQ * L::TAB_STRIDE + q], g);
+        double ug[VEC][DIM];
+        qp_grad_u<NN, DIM, VEC>(U, g, ug);
+        const double mu = E / (2.0 * (1.0 + nu)), lam = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
+        double sig[DIM][DIM];
+        iso_stress<DIM>(lam, mu, ug, sig);
+        double* cb = cellsm + cl * L::CELL;
+#pragma unroll
+        for (int u = 0; u < 12; ++u)
+          reinterpret_cast<double2*>(cb + L::OFF_G + q * L::GS)[u] = make_double2(g[(2 * u) / 3][(2 * u) % 3], g[(2 * u + 1) / 3][(2 * u + 1) % 3]);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) cb[L::OFF_S + q * 9 + i * DIM + d] = sig[i][d] * w;
+        cb[L::OFF_E + q] = E * w;
+      }
+      __syncthreads();
+
+      // ---------------- phase 2: one warp per cell of a chunk; lane = (row corner n, column pair t) ----------------
+#pragma unroll
+      for (int s = 0; s < L::NSUB; ++s) {
+        if (s < nsub) {
+          if (cw[s] >= 0) {                                       // warp-uniform
+            const double* cj = cellsm + cw[s] * L::CELL;
+            double g0[3], g1[3], a0[3], a1[3];
+            const double e0 = cj[L::OFF_E + t], e1 = cj[L::OFF_E + t + 4];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              g0[d] = cj[L::OFF_G + t * L::GS + n * 3 + d];
+              g1[d] = cj[L::OFF_G + (t + 4) * L::GS + n * 3 + d];
+              a0[d] = e0 * g0[d];
+              a1[d] = e1 * g1[d];
+            }
+            double C[3][3][2];
+#pragma unroll
+            for (int I = 0; I < 3; ++I)
+#pragma unroll
+              for (int J = 0; J < 3; ++J) {
+                C[I][J][0] = C[I][J][1] = 0.0;
+                dmma884(C[I][J], a0[I], g0[J]);
+                dmma884(C[I][J], a1[I], g1[J]);
+              }
+            // residual: B[q][col] = S_q[i = col][d] for col < 3 (col = lane / 4), zero otherwise
+            double R[2] = {0.0, 0.0};
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              const double b0 = (n < 3) ? cj[L::OFF_S + t * 9 + n * 3 + d] : 0.0;
+              const double b1 = (n < 3) ? cj[L::OFF_S + (t + 4) * 9 + n * 3 + d] : 0.0;
+              dmma884(R, g0[d], b0);
+              dmma884(R, g1[d], b1);
+            }
+            if (desc[s] >= 0) {                                   // the patch owns corner n of this cell
+              const int nl = (desc[s] >> 8) & 255;
+              const int len3 = 3 * (s_info[nl] & 255);
+              double* rowp = acc + s_acc[nl];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const double tr = C[0][0][e] + C[1][1][e] + C[2][2][e];
+                double* p = rowp + 3 * ((slots[s] >> (8 * e)) & 255);
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                  for (int c = 0; c < 3; ++c)
+                    p[i * len3 + c] += lam1 * C[i][c][e] + mu1 * C[c][i][e] + (i == c ? mu1 * tr : 0.0);
+              }
+              // R = r_n[2t], r_n[2t+1]: components 0,1 live in lanes t == 0, component 2 in lanes t == 1
+              if (t == 0) {
+                racc[nl * 3 + 0] += R[0];
+                racc[nl * 3 + 1] += R[1];
+              } else if (t == 1) {
+                racc[nl * 3 + 2] += R[0];
+              }
+            }
+          }
+          __syncthreads();      // the next chunk may touch the same owned nodes; after the last one: cell areas free
+        }
+      }
+    }
+
+    // ---------------- epilogue: Dirichlet rows, coalesced copy-out, re-zero ----------------
+    for (int i = warp; i < n_owned; i += L::THREADS / 32) {
+      const int nd = s_node[i], info = s_info[i];
+      const int len = info & 255, dg = (info >> 8) & 255, fl = info >> 16;
+      const int tot = 9 * len, len3 = 3 * len;
+      double* src = acc + s_acc[i];
+      double* dst = A.data + s_out[i];
+      for (int e = lane; e < tot; e += 32) {
+        double v = src[e];
+        src[e] = 0.0;
+        if (fl) {
+          const int row = e / len3, col = e - row * len3;
+          if ((fl >> row) & 1) v = (col == 3 * dg + row) ? 1.0 : 0.0;
+        }
+        dst[e] = v;
+      }
+      if (lane < 3) {
+        A.res[3 * (int64_t)nd + lane] = racc[i * 3 + lane] + fext[i * 3 + lane];
+        racc[i * 3 + lane] = 0.0;
+      }
+    }
+  }
+}
+
+template <int LAW>
+int launch_fused_dmma(const FusedArgs& A, cudaStream_t st) {
+  using L = FusedDmmaCfg;
+  const size_t smem = sizeof(double) * L::SMEM_DOUBLES;
+  auto k = fused_dmma_kernel<LAW>;
+  FEM_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = A.n_patches < kNumSM ? A.n_patches : kNumSM;
+  k<<<grid, L::THREADS, smem, st>>>(A);
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
+}
+
 template <class L>
 int launch_fused_law(int law_id, const FusedArgs& A, cudaStream_t st) {
   if (law_id == FEM_LAW_SIMP) return launch_fused<FEM_LAW_SIMP, L>(A, st);
@@ -315,12 +559,12 @@ extern "C" int fem_assemble_fused(int ele_type, int vec, int law_id, const doubl
                                   const double* ref_tables, int64_t n_patches, const int32_t* phdr,
                                   const int32_t* pn_node, const int32_t* pn_out, const int32_t* pn_acc,
                                   const int32_t* pn_info, const int32_t* lnodes, const int32_t* pc_cell,
-                                  const int32_t* pc_ln, const int32_t* ck_cell, const int32_t* ck_lane, const int32_t* ck_rnd,
+                                  const int32_t* pc_ln, const int32_t* pc_lm, const int32_t* ck_cell, const int32_t* ck_lane, const int32_t* ck_rnd,
                                   const int32_t* ln_desc, const int32_t* ln_slot, const uint8_t* bc_flag,
                                   const double* f_ext, double* data, double* res, int config, void* stream) {
   if (int e = check_device()) return e;
   FEM_REQUIRE(points && sol && ref_tables && law_params_host && phdr && pn_node && pn_out && pn_acc && pn_info &&
-                  lnodes && pc_cell && pc_ln && ck_cell && ck_lane && ck_rnd && ln_desc && ln_slot && bc_flag && data && res,
+                  lnodes && pc_cell && pc_ln && pc_lm && ck_cell && ck_lane && ck_rnd && ln_desc && ln_slot && bc_flag && data && res,
               "null pointer");
   FEM_REQUIRE(n_patches >= 0 && n_patches < (1ll << 31), "n_patches out of range");
   if (!(ele_type == FEM_ELE_HEX8 && vec == 3 && (law_id == FEM_LAW_LINEAR_ELASTIC || law_id == FEM_LAW_SIMP))) {
@@ -333,7 +577,7 @@ extern "C" int fem_assemble_fused(int ele_type, int vec, int law_id, const doubl
   FusedArgs A{};
   A.points = points; A.sol = sol; A.iv = internal_var; A.ref = ref_tables;
   A.phdr = phdr; A.pn_node = pn_node; A.pn_out = pn_out; A.pn_acc = pn_acc; A.pn_info = pn_info; A.lnodes = lnodes;
-  A.pc_cell = pc_cell; A.pc_ln = pc_ln; A.ck_cell = ck_cell; A.ck_lane = ck_lane; A.ck_rnd = ck_rnd; A.ln_desc = ln_desc; A.ln_slot = ln_slot;
+  A.pc_cell = pc_cell; A.pc_ln = pc_ln; A.pc_lm = pc_lm; A.ck_cell = ck_cell; A.ck_lane = ck_lane; A.ck_rnd = ck_rnd; A.ln_desc = ln_desc; A.ln_slot = ln_slot;
   A.bc_flag = bc_flag; A.f_ext = f_ext; A.data = data; A.res = res; A.n_patches = (int)n_patches;
   for (int i = 0; i < 8; ++i) A.p[i] = law_params_host[i];
   // config == index into jax_fem_b200/patch_plan.py::CONFIGS (the tables must have been built for it)
@@ -342,6 +586,9 @@ extern "C" int fem_assemble_fused(int ele_type, int vec, int law_id, const doubl
     case 1: return launch_fused_law<FusedCfg<32, 16, 256, 4, 2>>(law_id, A, (cudaStream_t)stream);
     case 2: return launch_fused_law<FusedCfg<32, 16, 128, 2, 2>>(law_id, A, (cudaStream_t)stream);
     case 3: return launch_fused_law<FusedCfg<32, 16, 256, 2, 2>>(law_id, A, (cudaStream_t)stream);
+    case 4:
+      if (law_id == FEM_LAW_SIMP) return launch_fused_dmma<FEM_LAW_SIMP>(A, (cudaStream_t)stream);
+      return launch_fused_dmma<FEM_LAW_LINEAR_ELASTIC>(A, (cudaStream_t)stream);
   }
   set_error("unknown fused-assembly configuration %d", config);
   return FEM_EINVAL;

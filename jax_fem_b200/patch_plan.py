@@ -19,8 +19,8 @@ Tables (all int32, built once per Problem with torch sort/unique/searchsorted on
                       len(n) | (slot of the diagonal block << 8)
     lnodes            per patch the global ids of its local nodes: the owned ones first (same order as pn_node),
                       then the halo nodes of its cells, ascending
-    pc_cell, pc_ln    per (patch, cell) pair, ordered by (patch, chunk, cell id): global cell id and the N local
-                      node numbers of the cell's corners (uint8 packed in N/4 words)
+    pc_cell, pc_ln,   per (patch, cell) pair, ordered by (patch, chunk, cell id): global cell id, the N local node
+    pc_lm             numbers of the cell's corners (uint8 packed in N/4 words), (first lane, mask of owned corners)
     ck_cell, ck_lane, the cells of a patch are processed in chunks of <= `chunk` cells built greedily so that no owned
     ck_rnd            node occurs more than `rmax` times in a chunk (csrc/plan_host.cpp); per chunk the first
                       patch-cell, the first lane and the number of accumulation rounds (<= rmax)
@@ -54,8 +54,9 @@ CONFIGS = (
     FusedConfig(edge=(2, 4, 4), max_owned=32, chunk=16, rmax=2, max_local=159),    # 1: 2 CTAs/SM, 256 threads, 4 tasks/corner
     FusedConfig(edge=(2, 4, 4), max_owned=32, chunk=16, rmax=2, max_local=159),    # 2: 2 CTAs/SM, 128 threads
     FusedConfig(edge=(2, 4, 4), max_owned=32, chunk=16, rmax=2, max_local=159),    # 3: 2 CTAs/SM, 256 threads, 2 tasks/corner
+    FusedConfig(edge=(4, 4, 4), max_owned=64, chunk=8, rmax=1, max_local=255),     # 4: FP64 tensor-core (DMMA) phase 2, one warp per cell
 )
-DEFAULT_CONFIG = 1
+DEFAULT_CONFIG = 0
 
 
 @dataclass
@@ -74,6 +75,7 @@ class PatchPlan:
     lnodes: torch.Tensor
     pc_cell: torch.Tensor
     pc_ln: torch.Tensor
+    pc_lm: torch.Tensor
     ck_cell: torch.Tensor
     ck_lane: torch.Tensor
     ck_rnd: torch.Tensor
@@ -259,6 +261,10 @@ def _build(points, cells, nn, vec, brow_ptr, bcol, lens, max_owned, cfg, config)
     ln_chunk = pc_chunk[lp]
     ln_rank = rank[lp, la]
     ck_lane = _exclusive_ptr(torch.bincount(ln_chunk, minlength=n_chunks))
+    n_own = owned.long().sum(1)
+    pc_first = _exclusive_ptr(n_own)[:-1]
+    pc_mask = (owned.long() << torch.arange(N, device=dev)[None, :]).sum(1)
+    pc_lm = torch.stack([pc_first, pc_mask], dim=1)
     ck_rnd = torch.zeros(n_chunks, dtype=torch.int64, device=dev)
     if ln_chunk.numel():
         ck_rnd.scatter_reduce_(0, ln_chunk, ln_rank + 1, reduce='amax')
@@ -271,7 +277,7 @@ def _build(points, cells, nn, vec, brow_ptr, bcol, lens, max_owned, cfg, config)
     phdr[:-1, 4] = acc_total
     return PatchPlan(config=config, n_patches=P, n_chunks=n_chunks, n_lanes=int(ln_desc.numel()), nodes_per_cell=N, vec=vec,
                      phdr=i32(phdr), pn_node=i32(pn_node), pn_out=i32(pn_out), pn_acc=i32(pn_acc), pn_info=i32(pn_info),
-                     lnodes=i32(lnodes), pc_cell=i32(pc_cell), pc_ln=pc_ln, ck_cell=i32(ck_cell), ck_lane=i32(ck_lane),
+                     lnodes=i32(lnodes), pc_cell=i32(pc_cell), pc_ln=pc_ln, pc_lm=i32(pc_lm), ck_cell=i32(ck_cell), ck_lane=i32(ck_lane),
                      ck_rnd=i32(ck_rnd), ln_desc=i32(ln_desc), ln_slot=ln_slot, patch_of_node=pon)
 
 

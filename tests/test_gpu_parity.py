@@ -374,7 +374,7 @@ def _assemble_both_ways(prob, sol, monkeypatch):
 
 
 @pytest.mark.parametrize("case,config", [("perturbed_box", 0), ("perturbed_box", 1), ("perturbed_box", 2), ("perturbed_box", 3),
-                                         ("cylinder", 0), ("cylinder", 1), ("simp", 1)])
+                                         ("perturbed_box", 4), ("cylinder", 0), ("cylinder", 1), ("cylinder", 4), ("simp", 1), ("simp", 4)])
 def test_fused_assembly_matches_oracle_and_staged_path(case, config, monkeypatch):
     """One-kernel assembly (element evaluation + CSR rows + Dirichlet rows + nodal residual) against the oracle's
     get_A / compute_residual and against the two-kernel path, on non-affine and unstructured meshes."""
@@ -436,6 +436,6 @@ def test_fused_assembly_rejects_unregistered_combination():
     z = torch.zeros(64, dtype=torch.float64, device='cuda')
     zi = torch.zeros(64, dtype=torch.int32, device='cuda')
     P = _lib.ptr
-    code = lib.fem_assemble_fused(0, 3, 2, _lib.host_doubles([1., .3]), P(z), P(z), None, P(z), 1, *([P(zi)] * 13),
+    code = lib.fem_assemble_fused(0, 3, 2, _lib.host_doubles([1., .3]), P(z), P(z), None, P(z), 1, *([P(zi)] * 14),
                                   P(zi), None, P(z), P(z), 1, None)
     assert code == -1 and b"fused assembly is registered" in lib.fem_last_error()

@@ -191,6 +191,10 @@ def _patch_plan_case(points, cells, bc_info, law, config):
     data, res = emulate(pp, Ke, Re, flag, f_ext, plan.nnz)
     assert np.array_equal(A.indptr, plan.indptr.numpy()) and np.array_equal(A.indices, plan.indices.numpy())
     assert not np.isnan(data).any() and not np.isnan(res).any()
+    # (first lane, owned mask) of every patch-cell agree with the lane list
+    lm = pp.pc_lm.numpy()
+    assert np.array_equal(lm[:, 0], np.concatenate([[0], np.cumsum([bin(m).count('1') for m in lm[:, 1]])[:-1]]))
+    assert lm[:, 1].min() >= 1 and lm[:, 0][-1] + bin(lm[-1, 1]).count('1') == pp.n_lanes
     assert np.abs(data - A.data).max() <= 1e-13 * np.abs(A.data).max()
     ref = np.zeros((nn, 3))
     np.add.at(ref, cells.reshape(-1), Re.reshape(-1, 3))
@@ -198,19 +202,19 @@ def _patch_plan_case(points, cells, bc_info, law, config):
     return pp
 
 
-@pytest.mark.parametrize("config", [0, 1])
+@pytest.mark.parametrize("config", [0, 1, 4])
 def test_patch_plan_structured_box(config):
     """Fused owner-computes assembly tables: walking them in the kernel's order reproduces the oracle's CSR
     (Dirichlet rows included) and nodal residual on a box whose sides are not multiples of the patch edge."""
     m = fem.box_mesh(6, 9, 5, 1., 1.5, 1.)
     pp = _patch_plan_case(m.points, m.cells, cases.CUBE_BC, olaws.LinearElastic(70e3, 0.3), config)
-    assert pp.n_patches == (2, 4)[config] * 3 * 2          # 7 x 10 x 6 nodes in bricks of 4 (2) x 4 x 4 layers
+    assert pp.n_patches == {0: 2, 1: 4, 4: 2}[config] * 3 * 2          # 7 x 10 x 6 nodes in bricks of 4 (2) x 4 x 4 layers
     hdr = pp.phdr.numpy()
-    assert np.diff(hdr[:, 0]).max() == (64, 32)[config] and np.diff(hdr[:, 1]).max() <= (216, 144)[config]
+    assert np.diff(hdr[:, 0]).max() == {0: 64, 1: 32, 4: 64}[config] and np.diff(hdr[:, 1]).max() <= {0: 216, 1: 144, 4: 216}[config]
     assert np.array_equal(np.sort(pp.pn_node.numpy()), np.arange(len(m.points)))
 
 
-@pytest.mark.parametrize("config", [0, 1])
+@pytest.mark.parametrize("config", [0, 1, 4])
 def test_patch_plan_unstructured_golden_mesh(config):
     from jax_fem_b200.patch_plan import CONFIGS
     g = cases.load_golden("linear_elasticity_cylinder")
