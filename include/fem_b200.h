@@ -123,17 +123,16 @@ int fem_patch_chunks_host(int64_t n_patches, const int64_t* cell_ptr_host, const
  *              [W b, W (b+1)), W = 32 corners (8 for 27-node cells); gdesc[4b..4b+2] = first corner, first entry,
  *              first source of item b (the next item's triple closes the ranges).  No node may have more than
  *              16 corners (8 for 27-node cells).  Row blocks are padded to an even number of doubles.
- * eorder (nnzb): processing order of the entries inside each CTA (a permutation of the CTA's entry range, sorted by
- *              descending source count so that the lanes of a warp loop equally long); results do not depend on it.
- * edst (nnzb): offset in `data` of element (row vec*n, col vec*m) of the scalar CSR pattern
- *              (indptr[vec*n+i] = vec*vec*brow_ptr[n] + i*vec*len(n)).
- * einfo (nnzb): bits 0..15 = vec*len(n) (distance between the entry's consecutive scalar rows), bit 16 = m == n,
- *              bit 17+i = row vec*n+i is a Dirichlet row -> row zeroed, unit diagonal, pattern kept
- *              (Mat.zeroRows with KEEP_NONZERO_PATTERN, solver.py:477,527-528).
+ * emeta (nnzb, 4): per entry IN PROCESSING ORDER (inside each CTA's entry range the entries are sorted by descending
+ *              source count so that the lanes of a warp loop equally long; results do not depend on the order):
+ *              [0],[1] = its source range in `src`, [2] = offset in `data` of element (row vec*n, col vec*m) of the
+ *              scalar CSR pattern (indptr[vec*n+i] = vec*vec*brow_ptr[n] + i*vec*len(n)), [3] = bits 0..15 vec*len(n)
+ *              (distance between the entry's consecutive scalar rows), bit 16 = m == n, bit 17+i = row vec*n+i is a
+ *              Dirichlet row -> row zeroed, unit diagonal, pattern kept (Mat.zeroRows, solver.py:477,527-528).
+ *              16-byte aligned: the kernel fetches one int4 per entry.
  */
-int fem_gather_csr(int vec, int nn, int64_t n_blocks, const int32_t* gdesc, const int32_t* eorder,
-                   const int32_t* src_ptr, const int32_t* src, const int32_t* edst, const int32_t* einfo,
-                   const double* Ke, double* data, void* stream);
+int fem_gather_csr(int vec, int nn, int64_t n_blocks, const int32_t* gdesc, const int32_t* emeta,
+                   const int32_t* src, const double* Ke, double* data, void* stream);
 
 /* residual scatter-add of problem.py:426-437 as a per-node gather: nc_ptr (n_nodes+1) / nc codes
  * c*NN + a ascending; res = sum Re + f_ext (f_ext may be NULL).                                  */

@@ -24,7 +24,7 @@ _SIGNATURES = {
     "fem_hex27_residual_jacobian": (_i, [_i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "fem_assemble_fused": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64] + [_vp] * 18 + [_i, _vp]),
     "fem_patch_chunks_host": (_i, [_i64, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
-    "fem_gather_csr": (_i, [_i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fem_gather_csr": (_i, [_i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fem_gather_residual": (_i, [_i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fem_apply_bc_vec": (_i, [_i64, _vp, _vp, _d, _vp, _vp, _vp]),
     "fem_bc_initial_guess": (_i, [_i64, _i64, _vp, _vp, _vp, _vp, _vp]),

@@ -55,9 +55,8 @@ struct GatherMeta {
 
 template <int VEC, int NN>
 __global__ void __launch_bounds__(kGatherThreads) gather_csr_kernel(
-    int n_items, const int32_t* __restrict__ gdesc, const int32_t* __restrict__ eorder,
-    const int32_t* __restrict__ src_ptr, const int32_t* __restrict__ src, const int32_t* __restrict__ edst,
-    const int32_t* __restrict__ einfo, const double* __restrict__ Ke, double* __restrict__ data) {
+    int n_items, const int32_t* __restrict__ gdesc, const int4* __restrict__ emeta, const int32_t* __restrict__ src,
+    const double* __restrict__ Ke, double* __restrict__ data) {
   constexpr int VV = VEC * VEC;
   constexpr int ROW = (NN * VV + 1) / 2 * 2;                      // doubles per corner row block (16-byte multiple)
   constexpr int MAXC = GatherCfg<NN>::CORNERS + GatherCfg<NN>::TAIL;
@@ -84,11 +83,11 @@ __global__ void __launch_bounds__(kGatherThreads) gather_csr_kernel(
       m.dst[r] = -1;
       m.info[r] = 0;
       if (t < m.E1 - m.E0) {
-        const int e = eorder[m.E0 + t];
-        m.sb[r] = src_ptr[e] - m.S0;
-        m.se[r] = src_ptr[e + 1] - m.S0;
-        m.dst[r] = edst[e] - VV * m.E0;
-        m.info[r] = einfo[e];
+        const int4 em = emeta[m.E0 + t];     // entries in processing order: one independent 16-byte load each
+        m.sb[r] = em.x - m.S0;
+        m.se[r] = em.y - m.S0;
+        m.dst[r] = em.z - VV * m.E0;
+        m.info[r] = em.w;
       }
     }
   };
@@ -314,8 +313,8 @@ extern "C" int fem_device_count(void) {
 namespace femb200 {
 namespace {
 template <int VEC, int NN>
-int launch_gather(int n_items, const int32_t* gdesc, const int32_t* eorder, const int32_t* src_ptr, const int32_t* src,
-                  const int32_t* edst, const int32_t* einfo, const double* Ke, double* data, cudaStream_t st) {
+int launch_gather(int n_items, const int32_t* gdesc, const int32_t* emeta, const int32_t* src, const double* Ke,
+                  double* data, cudaStream_t st) {
   constexpr int MAXC = GatherCfg<NN>::CORNERS + GatherCfg<NN>::TAIL;
   constexpr int ROW = (NN * VEC * VEC + 1) / 2 * 2;
   const size_t smem = sizeof(double) * 2 * MAXC * ROW + sizeof(int) * MAXC * NN;
@@ -329,23 +328,23 @@ int launch_gather(int n_items, const int32_t* gdesc, const int32_t* eorder, cons
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kGatherThreads, smem);
     grid = (per_sm < 1 ? 1 : per_sm) * sms;
   }
-  k<<<grid < n_items ? grid : n_items, kGatherThreads, smem, st>>>(n_items, gdesc, eorder, src_ptr, src, edst, einfo, Ke, data);
+  k<<<grid < n_items ? grid : n_items, kGatherThreads, smem, st>>>(n_items, gdesc, reinterpret_cast<const int4*>(emeta), src, Ke, data);
   FEM_LAUNCH_CHECK();
   return FEM_OK;
 }
 }  // namespace
 }  // namespace femb200
 
-extern "C" int fem_gather_csr(int vec, int nn, int64_t n_blocks, const int32_t* gdesc, const int32_t* eorder,
-                              const int32_t* src_ptr, const int32_t* src, const int32_t* edst, const int32_t* einfo,
-                              const double* Ke, double* data, void* stream) {
+extern "C" int fem_gather_csr(int vec, int nn, int64_t n_blocks, const int32_t* gdesc, const int32_t* emeta,
+                              const int32_t* src, const double* Ke, double* data, void* stream) {
   if (int e = check_device()) return e;
-  FEM_REQUIRE(gdesc && eorder && src_ptr && src && edst && einfo && Ke && data, "null pointer");
+  FEM_REQUIRE(gdesc && emeta && src && Ke && data, "null pointer");
+  FEM_REQUIRE((reinterpret_cast<uintptr_t>(emeta) & 15) == 0, "emeta must be 16-byte aligned");
   if (n_blocks == 0) return FEM_OK;
   cudaStream_t st = (cudaStream_t)stream;
 #define FEM_G(V, N)                                                                                                  \
   if (vec == V && nn == N) {                                                                                         \
-    return launch_gather<V, N>((int)n_blocks, gdesc, eorder, src_ptr, src, edst, einfo, Ke, data, st);              \
+    return launch_gather<V, N>((int)n_blocks, gdesc, emeta, src, Ke, data, st);              \
   }
   FEM_G(3, 8) FEM_G(1, 8) FEM_G(1, 4) FEM_G(2, 4) FEM_G(3, 27)
 #undef FEM_G

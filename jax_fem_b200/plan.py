@@ -64,6 +64,13 @@ class AssemblyPlan:
     def n_gather_blocks(self):
         return int(self.gdesc.numel()) // 4 - 1
 
+    def entry_meta(self, bc_flag):
+        """emeta of fem_gather_csr: (source begin, source end, CSR destination, info) per entry in processing order."""
+        o = self.eorder.long()
+        sp = self.src_ptr.long()
+        info = self.entry_info(bc_flag).long()
+        return torch.stack([sp[o], sp[o + 1], self.edst.long()[o], info[o]], dim=1).to(torch.int32).contiguous()
+
     def entry_info(self, bc_flag):
         """einfo of fem_gather_csr: vec*len(n) | diag << 16 | Dirichlet flags of the entry's rows << 17."""
         v = self.vec

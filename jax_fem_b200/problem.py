@@ -182,11 +182,11 @@ class Problem:
             flag_dev = torch.from_numpy(flag).to(dev)
             self._bc_cache = (key, torch.from_numpy(rows).to(dev), torch.from_numpy(val[rows]).to(dev), flag_dev,
                               (fe.node_inds_list, fe.vec_inds_list, fe.vals_list),   # keep refs alive
-                              self.plan.entry_info(flag_dev))
+                              self.plan.entry_meta(flag_dev))
         return self._bc_cache[1], self._bc_cache[2], self._bc_cache[3]
 
-    def entry_info(self):
-        """Per-entry row stride / diagonal / Dirichlet bits consumed by the CSR gather kernel."""
+    def entry_meta(self):
+        """Per-entry (source range, CSR destination, row stride / diagonal / Dirichlet bits) of the CSR gather kernel."""
         self.bc_data()
         return self._bc_cache[5]
 

@@ -126,11 +126,10 @@ def get_A(problem):
     if data is not None:
         return CSRMatrix(p, data)
     Ke = problem.staged_tangents()
-    einfo = problem.entry_info()
+    emeta = problem.entry_meta()
     data = torch.empty(p.nnz, dtype=torch.float64, device=problem.device)
-    _lib.check(_lib.load().fem_gather_csr(fe.vec, fe.num_nodes, p.n_gather_blocks, _lib.ptr(p.gdesc), _lib.ptr(p.eorder),
-                                          _lib.ptr(p.src_ptr), _lib.ptr(p.src), _lib.ptr(p.edst), _lib.ptr(einfo),
-                                          _lib.ptr(Ke), _lib.ptr(data), _lib.stream_ptr()))
+    _lib.check(_lib.load().fem_gather_csr(fe.vec, fe.num_nodes, p.n_gather_blocks, _lib.ptr(p.gdesc), _lib.ptr(emeta),
+                                          _lib.ptr(p.src), _lib.ptr(Ke), _lib.ptr(data), _lib.stream_ptr()))
     return CSRMatrix(p, data)
 
 
