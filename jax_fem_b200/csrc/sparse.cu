@@ -80,13 +80,15 @@ __global__ void __launch_bounds__(kGatherThreads) gather_csr_kernel(
       const int t = threadIdx.x + r * kGatherThreads;
       m.soff[r] = (t < m.S1 - m.S0) ? src[m.S0 + t] : 0;
       m.sb[r] = m.se[r] = 0;
-      m.dst[r] = -1;
+      m.dst[r] = -1;   // raw (absolute) values; an entry slot beyond the item keeps dst < 0
       m.info[r] = 0;
       if (t < m.E1 - m.E0) {
-        const int4 em = emeta[m.E0 + t];     // entries in processing order: one independent 16-byte load each
-        m.sb[r] = em.x - m.S0;
-        m.se[r] = em.y - m.S0;
-        m.dst[r] = em.z - VV * m.E0;
+        // entries in processing order: one independent 16-byte load each; the raw values are kept (nothing is
+        // computed from them here) so that the load stays in flight until the item is processed
+        const int4 em = emeta[m.E0 + t];
+        m.sb[r] = em.x;
+        m.se[r] = em.y;
+        m.dst[r] = em.z;
         m.info[r] = em.w;
       }
     }
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_csr_kernel(
     for (int r = 0; r < EPT; ++r) {
 #pragma unroll
       for (int j = 0; j < VV; ++j) res[r][j] = 0.0;
-      for (int sidx = cur.sb[r]; sidx < cur.se[r]; ++sidx) {
+      for (int sidx = cur.sb[r] - cur.S0; sidx < cur.se[r] - cur.S0; ++sidx) {
         const int so = s_off[sidx];
         const double* blk = (ROW == NN * VV) ? sh + so * VV : sh + (so / NN) * ROW + (so % NN) * VV;
 #pragma unroll
@@ -156,12 +158,13 @@ __global__ void __launch_bounds__(kGatherThreads) gather_csr_kernel(
     for (int r = 0; r < EPT; ++r) {
       if (cur.dst[r] >= 0) {
         const int rowlen = cur.info[r] & 0xffff;
+        const int dst = cur.dst[r] - VV * cur.E0;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
           const bool bc = (cur.info[r] >> (17 + i)) & 1;
 #pragma unroll
           for (int kk = 0; kk < VEC; ++kk)
-            so[cur.dst[r] + i * rowlen + kk] =
+            so[dst + i * rowlen + kk] =
                 bc ? ((((cur.info[r] >> 16) & 1) && i == kk) ? 1.0 : 0.0) : res[r][i * VEC + kk];
         }
       }
