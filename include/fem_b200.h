@@ -120,11 +120,13 @@ int fem_patch_chunks_host(int64_t n_patches, const int64_t* cell_ptr_host, const
  * every (cell, local row node, local col node) contributing to it, in ascending (c,a,b) order (fixed
  * summation order => bit-reproducible).  Ke is the output of fem_element_residual_jacobian.
  * gdesc (4*(n_blocks+1)): work split.  CTA b owns the nodes whose first corner (in node-sorted order) lies in
- *              [W b, W (b+1)), W = 32 corners (8 for 27-node cells); gdesc[4b..4b+2] = first corner, first entry,
- *              first source of item b (the next item's triple closes the ranges).  No node may have more than
+ *              [W b, W (b+1)), W = 32 corners (8 for 27-node cells); gdesc[4b..4b+3] = first corner, first entry,
+ *              first source, first emeta row of item b (the next item's quadruple closes the ranges).  No node may have more than
  *              16 corners (8 for 27-node cells).  Row blocks are padded to an even number of doubles.
- * emeta (nnzb, 4): per entry IN PROCESSING ORDER (inside each CTA's entry range the entries are sorted by descending
- *              source count so that the lanes of a warp loop equally long; results do not depend on the order):
+ * emeta (n_rows, 4): one row per entry, two for an entry with more than 4 sources (the second, flagged by bit 20 of
+ *              [3], covers the second half of the sources and is added to the first half's sum), IN PROCESSING ORDER
+ *              (inside each CTA's range the rows are sorted by descending source count so that the lanes of a warp
+ *              loop equally long; results do not depend on the order):
  *              [0],[1] = its source range in `src`, [2] = offset in `data` of element (row vec*n, col vec*m) of the
  *              scalar CSR pattern (indptr[vec*n+i] = vec*vec*brow_ptr[n] + i*vec*len(n)), [3] = bits 0..15 vec*len(n)
  *              (distance between the entry's consecutive scalar rows), bit 16 = m == n, bit 17+i = row vec*n+i is a

@@ -48,7 +48,7 @@ template <int NN> struct GatherCfg { static constexpr int CORNERS = NN <= 8 ? 32
 // Per-item metadata a thread keeps in registers (prefetched one work item ahead).
 template <int EPT, int SPT>
 struct GatherMeta {
-  int C0, C1, E0, E1, S0, S1;      // corner / entry / source ranges of the item
+  int C0, C1, E0, E1, S0, S1, M0, M1;   // corner / entry / source / gather-row ranges of the item
   int soff[SPT];                   // raw block indices of the thread's sources
   int sb[EPT], se[EPT], dst[EPT], info[EPT];
 };
@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_csr_kernel(
     m.C0 = gdesc[it * 4 + 0]; m.C1 = gdesc[it * 4 + 4];
     m.E0 = gdesc[it * 4 + 1]; m.E1 = gdesc[it * 4 + 5];
     m.S0 = gdesc[it * 4 + 2]; m.S1 = gdesc[it * 4 + 6];
+    m.M0 = gdesc[it * 4 + 3]; m.M1 = gdesc[it * 4 + 7];
   };
   auto load_meta = [&](Meta& m) {          // global loads only; consumed one iteration later
 #pragma unroll
@@ -82,10 +83,10 @@ __global__ void __launch_bounds__(kGatherThreads) gather_csr_kernel(
       m.sb[r] = m.se[r] = 0;
       m.dst[r] = -1;   // raw (absolute) values; an entry slot beyond the item keeps dst < 0
       m.info[r] = 0;
-      if (t < m.E1 - m.E0) {
-        // entries in processing order: one independent 16-byte load each; the raw values are kept (nothing is
+      if (t < m.M1 - m.M0) {
+        // gather rows in processing order: one independent 16-byte load each; the raw values are kept (nothing is
         // computed from them here) so that the load stays in flight until the item is processed
-        const int4 em = emeta[m.E0 + t];
+        const int4 em = emeta[m.M0 + t];
         m.sb[r] = em.x;
         m.se[r] = em.y;
         m.dst[r] = em.z;
@@ -153,23 +154,29 @@ __global__ void __launch_bounds__(kGatherThreads) gather_csr_kernel(
 
     // phase C: results -> shared memory in CSR order (the item's rows are one contiguous range of `data`), then a
     // coalesced copy.  einfo: bits 0..15 = VEC*len(row node), bit 16 = diagonal block, bits 17.. = Dirichlet rows.
+    // A row with bit 20 is the second half of a split entry: it adds to what the first half stored (fixed order).
     double* so = stage_ptr(stage);
 #pragma unroll
-    for (int r = 0; r < EPT; ++r) {
-      if (cur.dst[r] >= 0) {
-        const int rowlen = cur.info[r] & 0xffff;
-        const int dst = cur.dst[r] - VV * cur.E0;
+    for (int half = 0; half < 2; ++half) {
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          const bool bc = (cur.info[r] >> (17 + i)) & 1;
+      for (int r = 0; r < EPT; ++r) {
+        if (cur.dst[r] >= 0 && ((cur.info[r] >> 20) & 1) == half) {
+          const int rowlen = cur.info[r] & 0xffff;
+          const int dst = cur.dst[r] - VV * cur.E0;
 #pragma unroll
-          for (int kk = 0; kk < VEC; ++kk)
-            so[dst + i * rowlen + kk] =
-                bc ? ((((cur.info[r] >> 16) & 1) && i == kk) ? 1.0 : 0.0) : res[r][i * VEC + kk];
+          for (int i = 0; i < VEC; ++i) {
+            const bool bc = (cur.info[r] >> (17 + i)) & 1;
+#pragma unroll
+            for (int kk = 0; kk < VEC; ++kk) {
+              double* o = so + dst + i * rowlen + kk;
+              if (half == 0) *o = bc ? ((((cur.info[r] >> 16) & 1) && i == kk) ? 1.0 : 0.0) : res[r][i * VEC + kk];
+              else if (!bc) *o += res[r][i * VEC + kk];
+            }
+          }
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
     double* __restrict__ out = data + (int64_t)VV * cur.E0;
     for (int t = threadIdx.x; t < nE * VV; t += kGatherThreads) out[t] = so[t];
     __syncthreads();                       // stage is free for the TMA issued in the next iteration

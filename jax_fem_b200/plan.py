@@ -23,6 +23,7 @@ from dataclasses import dataclass
 import torch
 
 INT32_MAX = 2 ** 31 - 1
+SPLIT_SOURCES = 4      # an entry with more sources is gathered as two half rows (csrc/sparse.cu phase C)
 
 
 @dataclass
@@ -40,7 +41,11 @@ class AssemblyPlan:
     indptr: torch.Tensor
     indices: torch.Tensor
     corner_pos: torch.Tensor = None    # (C*N,) position of corner (c,a) in the node-sorted order (inverse of nc)
-    gdesc: torch.Tensor = None         # gather work split: (first corner, first entry, first source, 0) per CTA
+    gdesc: torch.Tensor = None         # gather work split: (first corner, first entry, first source, first row) per CTA
+    m_sb: torch.Tensor = None          # gather rows (entries; entries with many sources are split in two halves) in
+    m_se: torch.Tensor = None          # processing order: source range, entry index, second-half flag
+    m_ent: torch.Tensor = None
+    m_add: torch.Tensor = None
     eorder: torch.Tensor = None        # entries of every gather CTA sorted by descending source count
     edst: torch.Tensor = None          # offset in CSR data of (row vec*n, col vec*m) per entry
     erow: torch.Tensor = None          # row node of every entry (int32)
@@ -65,11 +70,11 @@ class AssemblyPlan:
         return int(self.gdesc.numel()) // 4 - 1
 
     def entry_meta(self, bc_flag):
-        """emeta of fem_gather_csr: (source begin, source end, CSR destination, info) per entry in processing order."""
-        o = self.eorder.long()
-        sp = self.src_ptr.long()
-        info = self.entry_info(bc_flag).long()
-        return torch.stack([sp[o], sp[o + 1], self.edst.long()[o], info[o]], dim=1).to(torch.int32).contiguous()
+        """emeta of fem_gather_csr: (source begin, source end, CSR destination, info) per gather row in processing
+        order; info = entry_info | bit 20 for the second half of a split entry (added to the first half's result)."""
+        e = self.m_ent.long()
+        info = self.entry_info(bc_flag).long()[e] | (self.m_add.long() << 20)
+        return torch.stack([self.m_sb.long(), self.m_se.long(), self.edst.long()[e], info], dim=1).to(torch.int32).contiguous()
 
     def entry_info(self, bc_flag):
         """einfo of fem_gather_csr: vec*len(n) | diag << 16 | Dirichlet flags of the entry's rows << 17."""
@@ -187,13 +192,29 @@ def build_plan(cells, num_nodes, vec):
     starts = torch.arange(n_blocks + 1, device=dev, dtype=torch.int64) * width
     node0 = torch.searchsorted(nc_ptr[:-1].long().contiguous(), starts)            # first node of every CTA
     ent0 = brow_ptr.long()[node0]
-    gdesc = torch.stack([nc_ptr.long()[node0], ent0, src_ptr.long()[ent0], torch.zeros_like(ent0)], dim=1)
+    # gather rows: one per entry, two for an entry with more than SPLIT_SOURCES sources (first half stores, second half
+    # adds: halves the longest per-thread loop of the gather).  Inside a CTA the rows are sorted by descending source
+    # count (stable) so that the lanes of a warp loop equally long.
+    n_ent = bcol.numel()
+    cta_of_entry = torch.searchsorted(ent0[1:].contiguous(), torch.arange(n_ent, device=dev), right=True)
+    sp = src_ptr.long()
+    split = counts > SPLIT_SOURCES
+    half = torch.div(counts + 1, 2, rounding_mode='floor')
+    ent = torch.arange(n_ent, device=dev)
+    r_ent = torch.cat([ent, ent[split]])
+    r_sb = torch.cat([sp[:-1], (sp[:-1] + half)[split]])
+    r_se = torch.cat([torch.where(split, sp[:-1] + half, sp[1:]), sp[1:][split]])
+    r_add = torch.cat([torch.zeros(n_ent, dtype=torch.int64, device=dev), torch.ones(int(split.sum()), dtype=torch.int64, device=dev)])
+    key = cta_of_entry[r_ent] * 64 + (63 - (r_se - r_sb).clamp(max=63))
+    rorder = torch.sort(key, stable=True)[1]
+    m_ent, m_sb, m_se, m_add = [t[rorder].to(torch.int32) for t in (r_ent, r_sb, r_se, r_add)]
+    row0 = _exclusive_ptr(torch.bincount(cta_of_entry[r_ent], minlength=n_blocks))
+    gdesc = torch.stack([nc_ptr.long()[node0], ent0, src_ptr.long()[ent0], row0], dim=1)
     gdesc = gdesc.reshape(-1).to(torch.int32)
-    # balanced processing order: inside a CTA, entries sorted by descending source count (stable)
-    cta_of_entry = torch.searchsorted(ent0[1:].contiguous(), torch.arange(bcol.numel(), device=dev), right=True)
+    # (kept for reference / tests) balanced processing order of the unsplit entries
     key = cta_of_entry * 64 + (63 - counts.clamp(max=63))
     eorder = torch.sort(key, stable=True)[1].to(torch.int32)
-    del cta_of_entry, key
+    del cta_of_entry, key, rorder, r_ent, r_sb, r_se, r_add
     lens = (brow_ptr[1:] - brow_ptr[:-1]).long()
     erow = torch.repeat_interleave(torch.arange(num_nodes, device=dev), lens)
     slot = torch.arange(bcol.numel(), device=dev) - brow_ptr[:-1].long()[erow]
@@ -202,5 +223,5 @@ def build_plan(cells, num_nodes, vec):
     edst = edst.to(torch.int32)
     erow = erow.to(torch.int32)
     del counts
-    return AssemblyPlan(corner_pos=corner_pos, gdesc=gdesc, eorder=eorder, edst=edst, erow=erow, num_nodes=num_nodes, num_cells=C, nodes_per_cell=N, vec=vec, brow_ptr=brow_ptr, bcol=bcol,
+    return AssemblyPlan(m_sb=m_sb, m_se=m_se, m_ent=m_ent, m_add=m_add, corner_pos=corner_pos, gdesc=gdesc, eorder=eorder, edst=edst, erow=erow, num_nodes=num_nodes, num_cells=C, nodes_per_cell=N, vec=vec, brow_ptr=brow_ptr, bcol=bcol,
                         src_ptr=src_ptr, src=src, nc_ptr=nc_ptr, nc=nc, indptr=indptr, indices=indices)

@@ -80,6 +80,21 @@ def test_plan_pattern_bit_exact(N, vec):
     assert np.array_equal(info & 0xffff, vec * np.diff(plan.brow_ptr.numpy())[erow])
     assert np.array_equal((info >> 16) & 1, (plan.bcol.numpy() == erow).astype(np.int32))
     assert np.array_equal(info >> 17, np.where(erow == 5, 1 << (vec - 1), 0))
+    # gather rows: every entry's source range is covered once, in order, by one row or by a (store, add) pair of halves
+    em = plan.entry_meta(flag).numpy()
+    assert em.shape[0] == gd[-1, 3] and gd[0, 3] == 0 and np.all(np.diff(gd[:, 3]) >= np.diff(gd[:, 1]))
+    ment, madd = plan.m_ent.numpy(), plan.m_add.numpy()
+    spn = plan.src_ptr.numpy()
+    for e in (0, 5, len(spn) // 2, len(spn) - 2):
+        rows = np.flatnonzero(ment == e)
+        rows = rows[np.argsort(madd[rows])]
+        assert em[rows[0], 0] == spn[e] and em[rows[-1], 1] == spn[e + 1] and list(madd[rows]) == list(range(len(rows)))
+        assert len(rows) == (2 if spn[e + 1] - spn[e] > 4 else 1)
+        if len(rows) == 2:
+            assert em[rows[0], 1] == em[rows[1], 0] and (em[rows[1], 3] >> 20) & 1 and not (em[rows[0], 3] >> 20) & 1
+        assert np.all(em[rows, 2] == ed[e]) and np.all((em[rows, 3] & 0xfffff) == info[e])
+    cta_rows = np.searchsorted(gd[1:, 3], np.arange(len(em)), side='right')
+    assert np.array_equal(cta_rows, np.searchsorted(gd[1:, 1], ment, side='right'))       # rows stay inside their CTA
     # transpose permutation is an involution mapping (n,m) -> (m,n)
     t = plan.tperm.numpy()
     assert np.array_equal(t[t], np.arange(len(t)))
