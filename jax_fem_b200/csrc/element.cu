@@ -517,6 +517,188 @@ int launch_element_dmma(const ElemArgs& A, cudaStream_t st) {
   return FEM_OK;
 }
 
+// ---- HEX8 Neo-Hookean on the FP64 tensor cores ------------------------------------------------------------
+// K_ab[i][k] = sum_q  p_a[i] h_b[k] + q_a[i] f_b[k] + h_b[i] r_a[k] + delta_ik (c1 g_a . g_b)   (closed form of section 8a,
+// p = c2 f + c3 h, q = c2 h, r = c4 h, f = F g, h = F^-T g): every term is a sum over the quadrature points of an
+// outer product of per-node values, i.e. the same 8x8 (a, b) tiles contracted over q as in element_dmma_kernel --
+// 3 x 18 + 6 mma.sync.m8n8k4.f64 per cell for the tangent and 6 for the residual, operands in registers (26 loads per
+// lane and cell instead of ~1000 shared loads in the CUDA-core formulation).  Phase 1 (lane = (cell, q)) is the
+// CUDA-core code of element_kernel; it also stores f and h.  One warp owns 4 cells; 2 CTAs of 4 warps per SM.
+struct NhDmmaLayout {
+  static constexpr int NN = 8, NQ = 8, DIM = 3, VEC = 3;
+  static constexpr int TAB_STRIDE = 25, TAB_SIZE = NQ * TAB_STRIDE + NQ;
+  static constexpr int GS = 28;                        // per-q stride of the per-node vectors (conflict-free fragments)
+  static constexpr int OFF_X = 0, OFF_U = 24;          // X[8][3], U[8][3]
+  static constexpr int OFF_G = 48;                     // g[q][n][d]
+  static constexpr int OFF_F = OFF_G + NQ * GS;        // f[q][n][i]
+  static constexpr int OFF_H = OFF_F + NQ * GS;        // h[q][n][i]
+  static constexpr int OFF_S = OFF_H + NQ * GS;        // S[q][i][d] = P JxW
+  static constexpr int OFF_C = OFF_S + NQ * 9;         // c1..c4 per q
+  static constexpr int CELL = OFF_C + NQ * 4 + 2;      // 826 = 10 (mod 16)
+  static constexpr int WARP = 4 * CELL + 16;           // + 32 ints of corner positions
+  static constexpr int WARPS = 4;
+};
+
+__global__ void __launch_bounds__(NhDmmaLayout::WARPS * 32, 2) element_nh_dmma_kernel(const ElemArgs A) {
+  using L = NhDmmaLayout;
+  constexpr int NN = 8, NQ = 8, DIM = 3, VEC = 3, ND = 24;
+  extern __shared__ __align__(16) double sm[];
+  double* tab = sm;
+  const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
+  double* wb = sm + L::TAB_SIZE + warp * L::WARP;
+  int* pos = reinterpret_cast<int*>(wb + 4 * L::CELL);
+  for (int i = threadIdx.x; i < NQ * NN * DIM; i += L::WARPS * 32)
+    tab[(i / (NN * DIM)) * L::TAB_STRIDE + i % (NN * DIM)] = A.ref[i];
+  if (threadIdx.x < NQ) tab[NQ * L::TAB_STRIDE + threadIdx.x] = A.ref[NQ * NN * DIM + threadIdx.x];
+
+  // ---- phase 0/1: lane = (cell j, q) ----
+  const int j1 = l >> 3, q = l & 7;
+  const int64_t c1 = ((int64_t)blockIdx.x * L::WARPS + warp) * 4 + j1;
+  const bool act1 = c1 < A.C;
+  double* cb = wb + j1 * L::CELL;
+  if (act1) {
+    const int64_t node = A.cells[c1 * NN + q];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) cb[L::OFF_X + q * DIM + d] = A.points[node * DIM + d];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) cb[L::OFF_U + q * VEC + i] = A.sol[node * VEC + i];
+    pos[l] = A.corner_pos ? A.corner_pos[c1 * NN + q] : (int)(c1 * NN + q);
+  }
+  __syncthreads();
+  if (act1) {
+    double g[NN][DIM];
+    const double w = qp_geometry<NN, DIM>(cb + L::OFF_X, tab + q * L::TAB_STRIDE, tab[NQ * L::TAB_STRIDE + q], g);
+    double ug[VEC][DIM];
+    qp_grad_u<NN, DIM, VEC>(cb + L::OFF_U, g, ug);
+    const double* ivq = A.iv ? A.iv + c1 * NQ + q : nullptr;
+    const double E = A.p[0] * (ivq ? *ivq : 1.0), nu = A.p[1];
+    const double mu = E / (2.0 * (1.0 + nu)), kappa = E / (3.0 * (1.0 - 2.0 * nu));
+    NHPoint k;
+    nh_kinematics(ug, mu, A.p[2] != 0.0, k);
+    double P[3][3];
+    nh_stress(k, kappa, P);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) cb[L::OFF_S + q * 9 + i * 3 + d] = P[i][d] * w;
+#pragma unroll
+    for (int n = 0; n < NN; ++n)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        double sf = 0.0, sh = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          sf = fma(k.F[i][j], g[n][j], sf);
+          sh = fma(k.H[i][j], g[n][j], sh);
+        }
+        cb[L::OFF_G + q * L::GS + n * 3 + i] = g[n][i];
+        cb[L::OFF_F + q * L::GS + n * 3 + i] = sf;
+        cb[L::OFF_H + q * L::GS + n * 3 + i] = sh;
+      }
+    double* cc = cb + L::OFF_C + q * 4;
+    cc[0] = k.m * w;                                                             // delta_ik (g_a . g_b)
+    cc[1] = -(2.0 / 3.0) * k.m * w;                                              // f_a h_b + h_a f_b
+    cc[2] = ((2.0 / 9.0) * k.m * k.I1 + kappa * (2.0 * k.J - 1.0) * k.J) * w;    // h_a h_b
+    cc[3] = (k.m * k.I1 / 3.0 - kappa * (k.J - 1.0) * k.J) * w;                  // h_b h_a (swapped)
+  }
+  __syncwarp();
+
+  // ---- phase 2: the warp walks its 4 cells; lane = (node n, t) ----
+  const int n = l >> 2, t = l & 3;
+#pragma unroll 1
+  for (int j = 0; j < 4; ++j) {
+    const int64_t c = ((int64_t)blockIdx.x * L::WARPS + warp) * 4 + j;
+    if (c >= A.C) break;                                   // warp-uniform
+    const double* cj = wb + j * L::CELL;
+    double gq[2][3], fq[2][3], hq[2][3], ga[2][3], pa[2][3], qa[2][3], ra[2][3];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int qq = t + 4 * s;
+      const double* cc = cj + L::OFF_C + qq * 4;
+      const double k1 = cc[0], k2 = cc[1], k3 = cc[2], k4 = cc[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        gq[s][d] = cj[L::OFF_G + qq * L::GS + n * 3 + d];
+        fq[s][d] = cj[L::OFF_F + qq * L::GS + n * 3 + d];
+        hq[s][d] = cj[L::OFF_H + qq * L::GS + n * 3 + d];
+        ga[s][d] = k1 * gq[s][d];
+        pa[s][d] = k2 * fq[s][d] + k3 * hq[s][d];
+        qa[s][d] = k2 * hq[s][d];
+        ra[s][d] = k4 * hq[s][d];
+      }
+    }
+    double D[2] = {0.0, 0.0};
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) dmma884(D, ga[s][d], gq[s][d]);
+    double C[3][3][2];
+#pragma unroll
+    for (int I = 0; I < 3; ++I)
+#pragma unroll
+      for (int J = 0; J < 3; ++J) {
+        C[I][J][0] = (I == J) ? D[0] : 0.0;
+        C[I][J][1] = (I == J) ? D[1] : 0.0;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          dmma884(C[I][J], pa[s][I], hq[s][J]);
+          dmma884(C[I][J], qa[s][I], fq[s][J]);
+          dmma884(C[I][J], ra[s][J], hq[s][I]);
+        }
+      }
+    // residual: B[q][col] = S_q[i = col][d] for col < 3 (col = l/4), zero otherwise
+    double R[2] = {0.0, 0.0};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double b0 = (n < 3) ? cj[L::OFF_S + t * 9 + n * 3 + d] : 0.0;
+      const double b1 = (n < 3) ? cj[L::OFF_S + (t + 4) * 9 + n * 3 + d] : 0.0;
+      dmma884(R, gq[0][d], b0);
+      dmma884(R, gq[1][d], b1);
+    }
+    if (t == 0) {
+      A.Re[c * ND + n * 3 + 0] = R[0];
+      A.Re[c * ND + n * 3 + 1] = R[1];
+    } else if (t == 1) {
+      A.Re[c * ND + n * 3 + 2] = R[0];
+    }
+    // lane (n, t) holds K_{n,2t} and K_{n,2t+1}: 18 contiguous doubles of row block n; stage 4 row blocks at a time in
+    // the cell's own (dead) area and copy them to their node-sorted positions with coalesced 16-byte stores
+    double* out = wb + j * L::CELL;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      __syncwarp();
+      if ((n >> 2) == half) {
+        double* dst = out + (n & 3) * 72 + t * 18;
+#pragma unroll
+        for (int m = 0; m < 9; ++m) {
+          const int e0 = 2 * m, e1 = 2 * m + 1;          // element e of the 18: block e / 9, (i, k) = (e % 9) / 3, e % 3
+          reinterpret_cast<double2*>(dst)[m] = make_double2(C[(e0 % 9) / 3][e0 % 3][e0 / 9], C[(e1 % 9) / 3][e1 % 3][e1 / 9]);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 5; ++it) {
+        const int p2 = it * 32 + l;                     // 4 rows x 36 double2
+        if (p2 < 144) {
+          const int row = p2 / 36, w2 = p2 % 36;
+          reinterpret_cast<double2*>(A.Ke + (int64_t)pos[j * 8 + half * 4 + row] * 72)[w2] =
+              reinterpret_cast<const double2*>(out + row * 72)[w2];
+        }
+      }
+    }
+  }
+}
+
+int launch_element_nh_dmma(const ElemArgs& A, cudaStream_t st) {
+  using L = NhDmmaLayout;
+  const size_t smem = sizeof(double) * (L::TAB_SIZE + (size_t)L::WARPS * L::WARP);
+  const unsigned grid = (unsigned)((A.C + L::WARPS * 4 - 1) / (L::WARPS * 4));
+  FEM_CUDA_CHECK(cudaFuncSetAttribute(element_nh_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  element_nh_dmma_kernel<<<grid, L::WARPS * 32, smem, st>>>(A);
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
+}
+
 // ---- adjoint: -lambda^T dc/dtheta per quadrature point (thread per (cell, q)) -------------------
 template <int NN, int DIM, int VEC, int LAW, int CPB>
 __global__ void __launch_bounds__(CPB* NN) param_grad_kernel(const ElemArgs A) {
@@ -620,6 +802,7 @@ int dispatch(int ele, int vec, int law, const ElemArgs& A, cudaStream_t st) {
     if (use_dmma && A.Ke && ele == FEM_ELE_HEX8 && vec == 3) {
       if (law == FEM_LAW_LINEAR_ELASTIC) return launch_element_dmma<FEM_LAW_LINEAR_ELASTIC>(A, st);
       if (law == FEM_LAW_SIMP) return launch_element_dmma<FEM_LAW_SIMP>(A, st);
+      if (law == FEM_LAW_NEO_HOOKEAN) return launch_element_nh_dmma(A, st);
     }
   }
 #define FEM_CASE(ELE, NN, DIM, VEC, LAW, CPB)                                     \
