@@ -237,6 +237,79 @@ def distributed_cg(A, b, x0, part, halo, comm, vec, tol=1e-10, atol=1e-10, maxit
     return x, {'iterations': int(ws[6].item()), 'rr': float(ws[4].item())}
 
 
+def distributed_bicgstab(A, b, x0, part, halo, comm, vec, tol=1e-10, atol=1e-10, maxiter=10000, precond=True):
+    """Jacobi-BiCGSTAB on the rank's owned rows with the recurrences, early exit, breakdown codes and stopping rule of
+    jax.scipy.sparse.linalg.bicgstab (the reference's default and its adjoint solver, jax_fem/solver.py:78-84,1409):
+    stop when ||r||^2 <= max(tol^2 ||b||^2, atol^2).  The matrix may be non-symmetric (A^T of a matrix with Dirichlet
+    rows).  SpMV is the library's owned-row kernel behind one halo exchange; the dot products of a step travel in one
+    all-reduce each (4 per iteration) and the scalar recurrences stay on the device -- one host read per iteration
+    decides convergence, as the while_loop of the reference does.
+
+    A: local CSRMatrix (rows of owned nodes complete); b, x0: flat local vectors (owned first, then ghosts; x0 may be
+    None).  Returns (x with up-to-date ghosts, info)."""
+    lib = _lib.load()
+    P = _lib.ptr
+    n_owned, n_local = part.n_owned * vec, part.n_local * vec
+    indptr, indices, data = A.getValuesCSR()
+    dev = b.device
+    own = slice(0, n_owned)
+    ws = torch.zeros(lib.fem_krylov_workspace(n_local), dtype=torch.float64, device=dev)
+    minv = (1.0 / A.diagonal()[own]) if precond else None
+
+    def matvec(v_local, out):
+        halo.update(v_local)
+        _lib.check(lib.fem_dcg_spmv_dot(n_owned, n_local, P(indptr), P(indices), P(data), A.plan.vec, P(A.plan.brow_ptr),
+                                        P(A.plan.bcol), P(v_local), P(out), 0, P(ws), _lib.stream_ptr()))
+        return out
+
+    def dots(*pairs):
+        t = torch.stack([torch.dot(u[own], w[own]) for u, w in pairs])
+        comm.allreduce(t)
+        return t
+
+    def apply_m(v, out):
+        out[own] = v[own] * minv if precond else v[own]
+        return out
+
+    zeros = lambda: torch.zeros(n_local, dtype=torch.float64, device=dev)
+    x = zeros() if x0 is None else x0.reshape(-1).clone().contiguous()
+    q, t, phat, shat = zeros(), zeros(), zeros(), zeros()
+    b = b.reshape(-1)
+    r = zeros()
+    r[own] = b[own] - matvec(x, q)[own]
+    rhat = r.clone()
+    p = r.clone()
+    q = r.clone()
+    rho = alpha = omega = torch.ones((), dtype=torch.float64, device=dev)
+    atol2 = max(float(tol) ** 2 * float(dots((b, b))[0]), float(atol) ** 2)
+    k = 0
+    rr_rho = dots((r, r), (rhat, r))
+    while float(rr_rho[0]) > atol2 and 0 <= k < maxiter:
+        rho_ = rr_rho[1]
+        beta = rho_ / rho * alpha / omega
+        p[own] = r[own] + beta * (p[own] - omega * q[own])
+        matvec(apply_m(p, phat), q)
+        alpha = rho_ / dots((rhat, q))[0]
+        s = r                                                   # r is dead from here on: reuse its storage
+        s[own] = r[own] - alpha * q[own]
+        if float(dots((s, s))[0]) < atol2:                      # early exit of _bicgstab_solve
+            x[own] += alpha * phat[own]
+            rho, k = rho_, k + 1
+            rr_rho = dots((r, r), (rhat, r))
+            continue
+        matvec(apply_m(s, shat), t)
+        ts_tt = dots((t, s), (t, t))
+        omega = ts_tt[0] / ts_tt[1]
+        x[own] += alpha * phat[own] + omega * shat[own]
+        r[own] = s[own] - omega * t[own]
+        rho = rho_
+        rr_rho = dots((r, r), (rhat, r))
+        bad = torch.stack([omega == 0, alpha == 0, rho_ == 0]).tolist()
+        k = -11 if (bad[0] or bad[1]) else (-10 if bad[2] else k + 1)
+    halo.update(x)
+    return x, {'iterations': k, 'rr': float(rr_rho[0])}
+
+
 class ShardedProblem:
     """One rank's share of a global problem: a local ``Problem`` on (owned + ghost) nodes plus the halo plan."""
 
@@ -254,7 +327,12 @@ class ShardedProblem:
         self.comm.allreduce(s)
         return float(s.sqrt().item())
 
-    def solve(self, tol=1e-6, rel_tol=1e-8, max_newton=50, **cg_options):
+    def _krylov(self, method):
+        if method not in ('cg', 'bicgstab'):
+            raise ValueError(f"unknown sharded Krylov method {method!r} (registered: 'cg', 'bicgstab')")
+        return distributed_cg if method == 'cg' else distributed_bicgstab
+
+    def solve(self, tol=1e-6, rel_tol=1e-8, max_newton=50, method='cg', **cg_options):
         """Sharded Newton solve (jax_fem/solver.py:1285-1356 with the linear solve replaced by the distributed
         Jacobi-CG): every rank assembles its slab (no communication), the residual norm is all-reduced, the
         increment comes from ``distributed_cg`` and ghosts are refreshed by one halo exchange per iteration.
@@ -277,7 +355,7 @@ class ShardedProblem:
             x0 = torch.empty_like(dofs)
             _lib.check(_lib.load().fem_bc_initial_guess(n, rows.numel(), _lib.ptr(rows), _lib.ptr(vals), _lib.ptr(dofs),
                                                         _lib.ptr(x0), _lib.stream_ptr()))
-            inc, info = distributed_cg(A, -res, x0, self.part, self.halo, self.comm, self.vec, **cg_options)
+            inc, info = self._krylov(method)(A, -res, x0, self.part, self.halo, self.comm, self.vec, **cg_options)
             iters.append(info['iterations'])
             dofs = dofs + inc
             self.halo.update(dofs)
@@ -287,7 +365,34 @@ class ShardedProblem:
         self.last_info = {'newton_iterations': len(iters), 'cg_iterations': iters, 'residuals': history}
         return dofs.reshape(-1, self.vec)
 
-    def solve_linear(self, sol=None, **cg_options):
+    def adjoint_gradient(self, sol, v, **solver_options):
+        """Sharded implicit adjoint (jax_fem/solver.py:1362-1418) for the per-quadrature-point parameter
+        ``problem.internal_vars[0]``: assemble the slab, transpose it locally (every A(m, n) with n owned comes from
+        cells this rank holds, so the owned rows of A^T are complete), solve A^T lambda = v with the distributed
+        BiCGSTAB, zero lambda on the Dirichlet rows, refresh its ghosts and evaluate -lambda^T dc/dtheta per cell.
+        sol, v: local (owned + ghost) arrays.  Returns the gradient for the rank's local cells, shape
+        (n_local_cells, num_quads), in the order of ``self.part.local_cells`` (a cell held by two ranks gets the same
+        value on both; no reduction is needed)."""
+        from .solver import assign_zeros_bc, get_A
+        pb = self.problem
+        sol = pb._as_sol([sol]).reshape(-1, self.vec)
+        pb.newton_update([sol])
+        A_T = get_A(pb).transpose()
+        v = torch.as_tensor(v, dtype=torch.float64, device=pb.device).reshape(-1).contiguous()
+        lam, info = distributed_bicgstab(A_T, v, None, self.part, self.halo, self.comm, self.vec, **solver_options)
+        self.last_info = info
+        lam = assign_zeros_bc(lam, pb)
+        fe, law, iv = pb.fes[0], pb._law, pb._internal_var()
+        if iv is None:
+            raise ValueError("adjoint_gradient needs a per-quadrature-point parameter in problem.internal_vars")
+        grad = torch.empty_like(iv)
+        _lib.check(_lib.load().fem_adjoint_param_grad(
+            _lib.ELE[pb.ele_type], fe.vec, law.law_id, _lib.host_doubles(law.params()), _lib.ptr(pb._points),
+            _lib.ptr(pb._cells), pb.num_cells, _lib.ptr(sol.contiguous()), _lib.ptr(iv), _lib.ptr(lam), _lib.ptr(pb._ref),
+            _lib.ptr(grad), _lib.stream_ptr()))
+        return grad
+
+    def solve_linear(self, sol=None, method='cg', **cg_options):
         """One Newton step of a linear problem from ``sol`` (default 0): assemble locally, solve with distributed CG.
         Returns the local solution (owned + ghosts)."""
         from .solver import apply_bc_vec, get_A
@@ -300,6 +405,6 @@ class ShardedProblem:
         x0 = torch.empty_like(dofs)
         _lib.check(_lib.load().fem_bc_initial_guess(n, rows.numel(), _lib.ptr(rows), _lib.ptr(vals), _lib.ptr(dofs),
                                                     _lib.ptr(x0), _lib.stream_ptr()))
-        inc, info = distributed_cg(A, -res, x0, self.part, self.halo, self.comm, self.vec, **cg_options)
+        inc, info = self._krylov(method)(A, -res, x0, self.part, self.halo, self.comm, self.vec, **cg_options)
         self.last_info = info
         return (dofs + inc).reshape(-1, self.vec)
