@@ -11,7 +11,10 @@
 //   phase 2  for chunks of 32 quadrature points:
 //              all threads: g[q][n][:] = dN[q][n] J^-1(q)                     -> shared Gq[q][3n+d]
 //              DMMA: G(81x81) += sum_q (E_q w_q g(q)) g(q)^T as 8x8 tiles; only the 66 upper tiles of the 11x11
-//                    grid are computed (G is symmetric), 8-9 tiles per warp, accumulators in registers
+//                    grid are computed (G is symmetric).  The tile rows/columns form 4 groups (3, 3, 3, 2) and every
+//                    warp owns one block of the 4x4 upper block grid (<= 9 tiles): per k-step it loads the 2-3 row and
+//                    2-3 column fragments of its block ONCE and issues up to 9 DMMA with them (0.7 shared loads per
+//                    DMMA instead of 3: the kernel was bound by shared-memory bandwidth), accumulators in registers
 //              threads 0..80: r_(a,i) += sum_q S_q[i][:] . g_a(q)
 //   phase 3  tiles -> shared G (mirrored), in-place 3x3 conversion K_ab = lam' G_ab + mu' G_ab^T + mu' tr(G_ab) I,
 //            coalesced copy of the 27 row blocks to their node-sorted positions (row block = 27 blocks of 3x3,
@@ -26,9 +29,8 @@ constexpr int H27_QC = 32;                                 // quadrature points 
 constexpr int H27_GS = 100;                                // Gq row stride: 4 (mod 16) => conflict-free fragments
 constexpr int H27_GSS = 89;                                // G row stride (odd)
 constexpr int H27_QP = 19;                                 // per point: J^-1 (9), E w (1), S (9)
-constexpr int H27_THREADS = 256, H27_WARPS = 8;
-constexpr int H27_UPPER = H27_T * (H27_T + 1) / 2;         // 66
-constexpr int H27_TPW = (H27_UPPER + H27_WARPS - 1) / H27_WARPS;   // 9
+constexpr int H27_THREADS = 320, H27_WARPS = 10;              // one warp per block of the upper 4x4 block grid
+constexpr int H27_TPW = 9;                                 // tiles per warp (3 x 3 block)
 
 struct Hex27Args {
   const double* points;
@@ -69,7 +71,30 @@ __device__ __forceinline__ double det_inv3(const double (&J)[3][3], double (&inv
   return det;
 }
 
-__global__ void __launch_bounds__(H27_THREADS) hex27_kernel(const Hex27Args A) {
+// One 32-point chunk (8 k-steps) of a block of NR x NC tiles starting at tile (I0, J0); DIAG: only tiles c >= r, and the
+// row fragments are the column fragments scaled by E w.  Lane (row = l/4, k = l%4) holds A[row][k] = E w g[q][8I + l/4]
+// and B[k][col] = g[q][8J + l/4] with q = 4s + l%4.
+template <int NR, int NC, bool DIAG>
+__device__ __forceinline__ void h27_block_chunk(const double* __restrict__ Gq, const double* __restrict__ ew, int I0, int J0,
+                                                int l, double (&C)[H27_TPW][2]) {
+  const double* g = Gq + (l & 3) * H27_GS + (l >> 2);
+#pragma unroll
+  for (int s = 0; s < H27_QC / 4; ++s) {
+    const double e = ew[4 * s * H27_QP];
+    double a[NR], b[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) b[c] = g[4 * s * H27_GS + 8 * (J0 + c)];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) a[r] = e * (DIAG ? b[r] : g[4 * s * H27_GS + 8 * (I0 + r)]);
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        if (!DIAG || c >= r) dmma884(C[r * 3 + c], a[r], b[c]);
+  }
+}
+
+__global__ void __launch_bounds__(H27_THREADS, 2) hex27_kernel(const Hex27Args A) {
   extern __shared__ __align__(16) double sm[];
   const int nq = A.nq;
   const int nq_pad = (nq + H27_QC - 1) / H27_QC * H27_QC;
@@ -152,17 +177,13 @@ __global__ void __launch_bounds__(H27_THREADS) hex27_kernel(const Hex27Args A) {
   __syncthreads();
 
   // ---- phase 2: chunks of 32 points ----
-  // this warp's upper tiles u = warp, warp + 8, ...  ->  (I, J), I <= J
-  int tI[H27_TPW], tJ[H27_TPW];
-#pragma unroll
-  for (int k = 0; k < H27_TPW; ++k) {
-    int u = warp + k * H27_WARPS, I = 0;
-    if (u >= H27_UPPER) u = -1;
-    int rem = u;
-    while (u >= 0 && rem >= H27_T - I) { rem -= H27_T - I; ++I; }
-    tI[k] = u < 0 ? -1 : I;
-    tJ[k] = u < 0 ? -1 : I + rem;
-  }
+  // this warp's block of the upper 4 x 4 block grid: tile groups {0,1,2}, {3,4,5}, {6,7,8}, {9,10}
+  //   warps 0-2: (0,1) (0,2) (1,2)  3x3 tiles;  warps 3-5: (0,3) (1,3) (2,3)  3x2;  warps 6-8: diagonal 3x3 (6 tiles);  warp 9: diagonal 2x2 (3)
+  const int bgi = warp < 3 ? (warp == 2 ? 1 : 0) : (warp < 6 ? warp - 3 : warp - 6);
+  const int bgj = warp < 3 ? (warp == 0 ? 1 : 2) : (warp < 6 ? 3 : warp - 6);
+  const int I0 = 3 * bgi, J0 = 3 * bgj;
+  const int bnr = bgi == 3 ? 2 : 3, bnc = bgj == 3 ? 2 : 3;
+  const bool bdiag = bgi == bgj;
   double Cacc[H27_TPW][2];
 #pragma unroll
   for (int k = 0; k < H27_TPW; ++k) Cacc[k][0] = Cacc[k][1] = 0.0;
@@ -184,16 +205,15 @@ __global__ void __launch_bounds__(H27_THREADS) hex27_kernel(const Hex27Args A) {
       for (int d = 0; d < 3; ++d) Gq[ql * H27_GS + n * 3 + d] = g[d];
     }
     __syncthreads();
-    // DMMA: lane (row = l/4, col = l%4) holds A[row][k] = E w g[q = 4s + l%4][8I + l/4], B[k][col] = g[q][8J + l/4]
-#pragma unroll
-    for (int k = 0; k < H27_TPW; ++k) {
-      if (tI[k] < 0) continue;                            // warp-uniform
-      const double* ga = Gq + (l & 3) * H27_GS + 8 * tI[k] + (l >> 2);
-      const double* gb = Gq + (l & 3) * H27_GS + 8 * tJ[k] + (l >> 2);
+    {
       const double* ew = QP + (q0 + (l & 3)) * H27_QP + 9;
-#pragma unroll
-      for (int s = 0; s < H27_QC / 4; ++s)
-        dmma884(Cacc[k], ew[4 * s * H27_QP] * ga[4 * s * H27_GS], gb[4 * s * H27_GS]);
+      if (!bdiag) {                                        // warp-uniform
+        if (bnc == 3) h27_block_chunk<3, 3, false>(Gq, ew, I0, J0, l, Cacc);
+        else h27_block_chunk<3, 2, false>(Gq, ew, I0, J0, l, Cacc);
+      } else {
+        if (bnc == 3) h27_block_chunk<3, 3, true>(Gq, ew, I0, J0, l, Cacc);
+        else h27_block_chunk<2, 2, true>(Gq, ew, I0, J0, l, Cacc);
+      }
     }
     // residual r_(a,i) += sum_q S_q[i][:] . g_a(q)
     if (tid < H27_ND) {
@@ -211,16 +231,19 @@ __global__ void __launch_bounds__(H27_THREADS) hex27_kernel(const Hex27Args A) {
 
   // ---- phase 3: tiles -> G (mirrored); fragment: row = l/4, cols = 2(l%4), 2(l%4)+1 ----
 #pragma unroll
-  for (int k = 0; k < H27_TPW; ++k) {
-    if (tI[k] < 0) continue;
-    const int r = 8 * tI[k] + (l >> 2), c0 = 8 * tJ[k] + 2 * (l & 3);
-    G[r * H27_GSS + c0] = Cacc[k][0];
-    G[r * H27_GSS + c0 + 1] = Cacc[k][1];
-    if (tI[k] != tJ[k]) {
-      G[c0 * H27_GSS + r] = Cacc[k][0];
-      G[(c0 + 1) * H27_GSS + r] = Cacc[k][1];
+  for (int br = 0; br < 3; ++br)
+#pragma unroll
+    for (int bc = 0; bc < 3; ++bc) {
+      if (br >= bnr || bc >= bnc || (bdiag && bc < br)) continue;
+      const int tI = I0 + br, tJ = J0 + bc;
+      const int r = 8 * tI + (l >> 2), c0 = 8 * tJ + 2 * (l & 3);
+      G[r * H27_GSS + c0] = Cacc[br * 3 + bc][0];
+      G[r * H27_GSS + c0 + 1] = Cacc[br * 3 + bc][1];
+      if (tI != tJ) {
+        G[c0 * H27_GSS + r] = Cacc[br * 3 + bc][0];
+        G[(c0 + 1) * H27_GSS + r] = Cacc[br * 3 + bc][1];
+      }
     }
-  }
   __syncthreads();
   // in-place conversion of every 3x3 node-pair block
   for (int j = tid; j < H27_NN * H27_NN; j += H27_THREADS) {
