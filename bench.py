@@ -214,6 +214,19 @@ def build_problem(size, world=1, comm=None, workload="elasticity"):
     return sp.problem, sp
 
 
+def measured_traffic(args, world):
+    """DRAM bytes per assembly step from the committed ncu capture (profiles/r01_traffic.json): only valid for the
+    workload and size it was captured on; None otherwise."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
+    try:
+        t = json.load(open(path))
+    except (OSError, ValueError):
+        return None
+    if t.get("workload") == args.workload and t.get("size") == args.size and world == 1:
+        return t["assembly_bytes_per_step"]
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -422,7 +435,7 @@ def main():
                                   "assembly needs no communication; SpMV = halo send/recv with <= 2 neighbours; Krylov dots = all-reduce",
                        "l2": "inputs larger than L2 (element matrices + CSR >> 126 MB), no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": measured_traffic(args, world), "peak_source": peak_src,
                          "kernel": "assembly = element_kernel + gather_residual + apply_bc_vec + gather_csr",
                          "algorithmic_bytes": b_asm, "kernel_ms": asm_kernel_ms,
                          "kernels_ms": {"element_kernel+gather_residual": t_elem, "apply_bc_vec": t_bc, "gather_csr": t_gather}},
