@@ -373,8 +373,9 @@ struct DmmaLayout {
   static constexpr int OFF_S = OFF_G + NQ * GS;    // S[q][i][d] = sigma JxW        (272)
   static constexpr int OFF_E = OFF_S + NQ * 9;     // E_q JxW                       (344)
   static constexpr int CELL = 354;                 // 352 + 2: cell stride 2 (mod 16) spreads phase-1 stores
-  static constexpr int WARP = 4 * CELL + 16;       // + 32 ints of corner positions; the row blocks of a cell are
-                                                   // staged in the cell's own (by then dead) area, 4 rows at a time
+  static constexpr int OFF_SPARE = 4 * CELL + 16;  // after the 32 ints of corner positions
+  static constexpr int WARP = OFF_SPARE + 4 * 72;  // the row blocks of a cell leave through two staging areas of 4 rows:
+                                                   // rows 0-3 in the cell's own (by then dead) area, rows 4-7 in the spare
   static constexpr int WARPS = 4;
 };
 
@@ -480,29 +481,29 @@ __global__ void __launch_bounds__(DmmaLayout::WARPS * 32, 4) element_dmma_kernel
 #pragma unroll
         for (int k = 0; k < 3; ++k) K[e][i * 3 + k] = lam1 * C[i][k][e] + mu1 * C[k][i][e] + (i == k ? mu1 * tr : 0.0);
     }
-    // stage 4 row blocks at a time in the cell's own area (its g / S / E are in registers by now), then copy them
-    // to their node-sorted positions with coalesced 16-byte stores
-    double* out = wb + j * L::CELL;
+    // stage 4 row blocks at a time -- rows 0-3 in the cell's own area (its g / S / E are in registers by now), rows 4-7
+    // in the warp's spare area -- and hand every 576-byte row block to the TMA unit (cp.async.bulk shared -> global) for
+    // its node-sorted position: no LDS / STG for the copy-out.  The spare area was last used one cell earlier: all but
+    // the most recent bulk group of the issuing lanes must have been read before it is overwritten.
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
+      double* out = half == 0 ? wb + j * L::CELL : wb + L::OFF_SPARE;
+      if (half == 1 && l < 4) bulk_wait_read<1>();
       __syncwarp();
       if ((n >> 2) == half) {
         double* dst = out + (n & 3) * 72 + t * 18;
 #pragma unroll
         for (int m = 0; m < 9; ++m) reinterpret_cast<double2*>(dst)[m] = make_double2(K[(2 * m) / 9][(2 * m) % 9], K[(2 * m + 1) / 9][(2 * m + 1) % 9]);
+        fence_async_smem();
       }
       __syncwarp();
-#pragma unroll
-      for (int it = 0; it < 5; ++it) {
-        const int p2 = it * 32 + l;                     // 4 rows x 36 double2
-        if (p2 < 144) {
-          const int row = p2 / 36, w2 = p2 % 36;
-          reinterpret_cast<double2*>(A.Ke + (int64_t)pos[j * 8 + half * 4 + row] * 72)[w2] =
-              reinterpret_cast<const double2*>(out + row * 72)[w2];
-        }
+      if (l < 4) {
+        bulk_s2g(A.Ke + (int64_t)pos[j * 8 + half * 4 + l] * 72, out + l * 72, 72 * sizeof(double));
+        bulk_commit();
       }
     }
   }
+  if (l < 4) bulk_wait_read<0>();                    // shared memory must outlive the outstanding bulk reads
 }
 
 template <int LAW>
