@@ -237,6 +237,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--solve", action="store_true", help="also time a full Jacobi-CG solve")
+    ap.add_argument("--newton", action="store_true",
+                    help="also time the full Newton solve with per-iteration re-assembly (cfg 3 with --workload neohookean)")
     ap.add_argument("--workload", default="elasticity", choices=["elasticity", "neohookean", "hex27"],
                     help="elasticity = cfg 2 (the headline, default); neohookean = cfg 3's law on the same mesh; "
                          "hex27 = cfg 4 (use --size 60)")
@@ -409,6 +411,24 @@ def main():
                  "iterations": info['iterations'], "seconds": cs, "err": info.get('err'),
                  "ms_per_iteration": 1e3 * cs / max(info['iterations'], 1),
                  "effective_spmv_gbs": world * b_spmv / (cs / max(info['iterations'], 1)) / 1e9}
+    newton = None
+    if args.newton:
+        barrier()
+        c0 = time.perf_counter()
+        if sharded:
+            sharded.solve()
+            ninfo = sharded.last_info
+            ninfo = {"newton_iterations": ninfo["newton_iterations"], "krylov_iterations": ninfo["cg_iterations"],
+                     "residuals": ninfo["residuals"]}
+        else:
+            jf.solver(prob, {"jax_solver": {"method": "cg"}})
+            li = prob.last_newton_info
+            ninfo = {"newton_iterations": li["iterations"], "final_residual": li["res_val"]}
+        barrier()
+        ns = time.perf_counter() - c0
+        log(f"newton: {ninfo}, {ns:.2f}s")
+        newton = dict(ninfo, seconds=ns, method="Newton (tol 1e-6, rel 1e-8), tangent re-assembled every iteration, Jacobi-CG 1e-10"
+                      + (", cells sharded in x-slabs" if sharded else ""))
     clocks = sampler.stop() if rank == 0 else None
 
     # max over ranks (device times)
@@ -457,6 +477,8 @@ def main():
         }
         if solve:
             line["cg_solve"] = solve
+        if newton:
+            line["newton_solve"] = newton
         if not args.no_cpu_baseline and world == 1:
             log(f"timing the CPU oracle on {args.ref_size}^3")
             v, info = cpu_oracle_assembly(args.ref_size)
