@@ -206,6 +206,13 @@ def build_problem(size, world=1, comm=None, workload="elasticity"):
     left = lambda p: np.isclose(p[0], 0., atol=1e-5)
     right = lambda p: np.isclose(p[0], Lx, atol=1e-5)
     kw = dict(dirichlet_bc_info=[[left] * 3, [0, 1, 2], [lambda p: 0.] * 3], location_fns=[right], ele_type=ele)
+    if workload == "neohookean":
+        # cfg 3 (applications/scalability/hyperelastic3d_common.py:83-103): x=0 fixed, x=Lx pulled by 2 % in x with
+        # u_y = u_z = 0, traction on y=1
+        ymax = lambda p: np.isclose(p[1], 1., atol=1e-5)
+        kw = dict(dirichlet_bc_info=[[left] * 3 + [right] * 3, [0, 1, 2] * 2,
+                                     [lambda p: 0.] * 3 + [lambda p: 0.02 * Lx] + [lambda p: 0.] * 2],
+                  location_fns=[ymax], ele_type=ele)
     cls = problem_class(workload)
     if world == 1:
         return cls(jf.Mesh(m.points, cells), vec=3, dim=3, **kw), None
