@@ -439,3 +439,94 @@ def test_fused_assembly_rejects_unregistered_combination():
     code = lib.fem_assemble_fused(0, 3, 2, _lib.host_doubles([1., .3]), P(z), P(z), None, P(z), 1, *([P(zi)] * 14),
                                   P(zi), None, P(z), P(z), 1, None)
     assert code == -1 and b"fused assembly is registered" in lib.fem_last_error()
+
+
+# ---- full-size (BASELINE.json configs[1]) checks through size-independent properties -------------------------------
+def test_full_size_cfg2_properties(monkeypatch):
+    """HEX8 100^3 linear elasticity (3.09 M DOF, nnz 245 M) -- too large for the oracle, so the assembled operator is
+    checked through properties that hold at any size: pattern formula, rigid-body null space (translations and
+    infinitesimal rotations), symmetry (via the transpose kernel), linearity res(u) = A u + res(0), bit-reproducibility,
+    fused == two-kernel assembly, unit Dirichlet rows, and a Jacobi-CG solve whose true residual meets the tolerance."""
+    import jax_fem_b200 as jf
+    import gpu_problems as gp
+    from jax_fem_b200.solver import jax_solve
+    N = 100
+    m = jf.box_mesh(N, N, N, 1., 1., 1.)
+    pts, cells = m.points, m.cells_dict['hexahedron']
+    free = gp.PlainElasticity(jf.Mesh(pts, cells), vec=3, dim=3)                     # no Dirichlet rows
+    n = free.num_total_dofs_all_vars
+    assert free.plan.nnz == 9 * (3 * (N + 1) - 2) ** 3 and n == 3 * (N + 1) ** 3
+    rng = np.random.default_rng(7)
+    u = torch.from_numpy(1e-3 * rng.standard_normal((len(pts), 3))).cuda()
+    monkeypatch.setenv("FEM_ASSEMBLY", "staged")
+    res_u = free.newton_update([u])[0]
+    A = jf.get_A(free)
+    data0 = A.data.clone()
+    free.newton_update([u])
+    assert torch.equal(jf.get_A(free).data, data0)                                   # bit-reproducible at full size
+    scale = float(A.data.abs().max())
+    X = torch.from_numpy(pts).cuda()
+    rigid = [torch.tensor(t, dtype=torch.float64, device='cuda').expand(len(pts), 3).contiguous() for t in
+             ([1., 0, 0], [0, 1., 0], [0, 0, 1.])]
+    rigid += [torch.stack([-X[:, 1], X[:, 0], 0 * X[:, 0]], 1), torch.stack([0 * X[:, 0], -X[:, 2], X[:, 1]], 1),
+              torch.stack([X[:, 2], 0 * X[:, 0], -X[:, 0]], 1)]
+    for v in rigid:
+        y = A @ v.reshape(-1).contiguous()
+        assert float(y.abs().max()) <= 1e-12 * scale * 27 * float(v.abs().max())
+    assert float((A.transpose().data - A.data).abs().max()) <= 1e-12 * scale           # K_ba = K_ab^T
+    zero = torch.zeros_like(u)
+    res_0 = free.compute_residual([zero])[0]
+    lin = (res_u - res_0).reshape(-1) - A @ u.reshape(-1).contiguous()
+    assert float(lin.abs().max()) <= 1e-12 * scale * float(u.abs().max()) * 27
+    monkeypatch.setenv("FEM_ASSEMBLY", "fused")
+    res_f = free.newton_update([u])[0]
+    assert float((jf.get_A(free).data - data0).abs().max()) <= 1e-13 * scale
+    assert float((res_f - res_u).abs().max()) <= 1e-12 * float(res_u.abs().max())
+    del free, A, data0
+    torch.cuda.empty_cache()
+
+    # cfg 2 proper: u = 0 on x = 0, traction on x = 1, Jacobi-CG to 1e-10
+    monkeypatch.setenv("FEM_ASSEMBLY", "staged")
+    left = lambda p: np.isclose(p[0], 0., atol=1e-5)
+    right = lambda p: np.isclose(p[0], 1., atol=1e-5)
+    cls = type("Cfg2", (jf.Problem,), {"get_tensor_map": lambda self: jf.laws.LinearElasticity(70e3, 0.3),
+                                       "get_surface_maps": lambda self: [lambda u, x: np.array([0., 0., 100.])]})
+    pb = cls(jf.Mesh(pts, cells), vec=3, dim=3, dirichlet_bc_info=[[left] * 3, [0, 1, 2], [lambda p: 0.] * 3],
+             location_fns=[right])
+    dofs = torch.zeros(n, dtype=torch.float64, device='cuda')
+    b = -jf.apply_bc_vec(pb.newton_update([dofs.reshape(-1, 3)])[0].reshape(-1), dofs, pb)
+    A = jf.get_A(pb)
+    rows = pb.bc_data()[0].long()
+    indptr, indices, data = A.getValuesCSR()
+    r0 = int(rows[len(rows) // 2])
+    seg = slice(int(indptr[r0]), int(indptr[r0 + 1]))
+    assert torch.equal(data[seg], (indices[seg] == r0).double())                      # unit Dirichlet row, pattern kept
+    assert len(rows) == 3 * (N + 1) ** 2
+    x, info = jax_solve(A, b, torch.zeros_like(b), True, method='cg', return_info=True)
+    assert 0 < info['iterations'] < 3000
+    true_res = float((A @ x - b).norm())
+    assert true_res <= 1e-9 * max(float(b.norm()), 1.0) and info['err'] < 1e-6
+    assert float(x[rows].abs().max()) == 0.0
+
+
+def test_full_size_neohookean_tangent_is_the_derivative_of_the_residual():
+    """cfg 3's law at 100^3 cells (one GPU's share of the 8-GPU run): the assembled tangent (FP64 DMMA kernel) must be the
+    directional derivative of the assembled residual, A(u) v = d/de res(u + e v) (central difference, O(e^2)), and must be
+    symmetric (hyperelastic).  Size-independent, no oracle needed."""
+    import jax_fem_b200 as jf
+    import gpu_problems as gp
+    N = 100
+    m = jf.box_mesh(N, N, N, 1., 1., 1.)
+    pts, cells = m.points, m.cells_dict['hexahedron']
+    prob = gp.HyperElasticity(jf.Mesh(pts, cells), vec=3, dim=3)
+    rng = np.random.default_rng(3)
+    u = torch.from_numpy(2e-4 * rng.standard_normal((len(pts), 3))).cuda()            # |grad u| ~ 0.03: det F > 0 everywhere
+    v = torch.from_numpy(rng.standard_normal((len(pts), 3))).cuda()
+    prob.newton_update([u])
+    A = jf.get_A(prob)
+    Av = A @ v.reshape(-1).contiguous()
+    eps = 2e-7                                          # truncation ~ (eps |grad v|)^2 ~ 4e-9, round-off ~ 1e-16 |res| / eps
+    fd = (prob.compute_residual([u + eps * v])[0] - prob.compute_residual([u - eps * v])[0]).reshape(-1) / (2 * eps)
+    err, ref = float((Av - fd).abs().max()), float(Av.abs().max())
+    assert err <= 1e-7 * ref, (err, ref)
+    assert float((A.transpose().data - A.data).abs().max()) <= 1e-11 * float(A.data.abs().max())
