@@ -79,6 +79,15 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
+// FP64 tensor-core tile: C(8x8) += A(8x4, row-major) B(4x8, col-major).  Lane l supplies A[l/4][l%4] and B[l%4][l/4] and
+// holds C[l/4][2(l%4)], C[l/4][2(l%4)+1].  DMMA and DFMA share one FP64 pipe on B200 (tools/microbench.cu): this buys
+// operand bandwidth (operands come from registers), not flops.
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -358,11 +358,6 @@ __global__ void __launch_bounds__(CPB* NN, (LAW == FEM_LAW_NEO_HOOKEAN ? 256 / (
 // walks its cells one at a time: 18 + 6 DMMA, G -> K in registers (lane (n,t) holds K_{n,2t} and K_{n,2t+1}:
 // 18 contiguous doubles of row block n), staging in shared memory and a coalesced copy to the row block's
 // node-sorted position.
-__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c[0]), "+d"(c[1])
-               : "d"(a), "d"(b));
-}
 
 struct DmmaLayout {
   static constexpr int NN = 8, NQ = 8, DIM = 3, VEC = 3;

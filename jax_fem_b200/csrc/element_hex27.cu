@@ -47,11 +47,6 @@ struct Hex27Args {
   double p[8];
 };
 
-__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c[0]), "+d"(c[1])
-               : "d"(a), "d"(b));
-}
 
 __device__ __forceinline__ double det_inv3(const double (&J)[3][3], double (&inv)[3][3]) {
   const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];

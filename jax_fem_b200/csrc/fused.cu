@@ -308,11 +308,6 @@ int launch_fused(const FusedArgs& A, cudaStream_t st) {
 // Inside a cell no two lanes touch the same accumulator word; the plan's chunks hold <= 8 cells (one per warp) that
 // share no owned node (rmax = 1), so a barrier between chunks is the only ordering needed.  Cells on the patch
 // surface pay the full tile for the few rows that are kept (125 cells per 64 owned nodes).
-__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c[0]), "+d"(c[1])
-               : "d"(a), "d"(b));
-}
 
 struct FusedDmmaCfg {
   static constexpr int THREADS = 256, WARPS = 8, MAX_OWNED = 64, MAX_LOCAL = 256;
