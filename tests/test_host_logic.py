@@ -237,3 +237,28 @@ def test_patch_plan_unstructured_golden_mesh(config):
     hdr, cfg = pp.phdr.numpy(), CONFIGS[config]
     assert np.diff(hdr[:, 0]).max() <= cfg.max_owned and np.diff(hdr[:, 1]).max() <= cfg.max_local
     assert hdr[:-1, 4].max() <= cfg.acc_doubles
+
+
+def test_save_sol_round_trips_through_the_vtu_reader(tmp_path):
+    """save_sol (jax_fem/utils.py:13-57): float32 point field `sol`, optional cell / point fields; the file is read back
+    with the stdlib reader that parses the reference's own .vtu goldens."""
+    from oracle.vtu import read_vtu
+    m = jf.box_mesh(3, 2, 2, 1., 1., 1.)
+    fe = FiniteElement(jf.Mesh(m.points, m.cells_dict['hexahedron']), 3, 3, 'HEX8')
+    rng = np.random.default_rng(0)
+    sol = rng.standard_normal((fe.num_total_nodes, 3))
+    rho = rng.uniform(0, 1, fe.num_cells)
+    T = rng.standard_normal(fe.num_total_nodes)
+    path = str(tmp_path / "out" / "u.vtu")
+    jf.save_sol(fe, torch.from_numpy(sol), path, cell_infos=[('rho', rho)], point_infos=[('T', T)])
+    pts, cells, pd = read_vtu(path)
+    assert np.array_equal(pts, fe.points) and np.array_equal(cells, fe.cells)
+    assert np.array_equal(pd['sol'], sol.astype(np.float32)) and np.array_equal(pd['T'], T.astype(np.float32))
+    text = open(path).read()
+    assert 'Name="rho"' in text and text.count('<DataArray') == 7
+    with pytest.raises(AssertionError):
+        jf.save_sol(fe, sol, path, cell_infos=[('bad', rho[:-1])])
+    q = jf.rectangle_mesh(2, 2, 1., 1.)
+    fe2 = FiniteElement(jf.Mesh(q.points, q.cells_dict['quad']), 1, 2, 'QUAD4')
+    jf.save_sol(fe2, np.zeros((fe2.num_total_nodes, 1)), str(tmp_path / "q.vtu"))
+    assert read_vtu(str(tmp_path / "q.vtu"))[0].shape == (9, 3)
