@@ -523,19 +523,18 @@ int launch_element_dmma(const ElemArgs& A, cudaStream_t st) {
 struct NhDmmaLayout {
   static constexpr int NN = 8, NQ = 8, DIM = 3, VEC = 3;
   static constexpr int TAB_STRIDE = 25, TAB_SIZE = NQ * TAB_STRIDE + NQ;
-  static constexpr int GS = 28;                        // per-q stride of the per-node vectors (conflict-free fragments)
+  static constexpr int GS = 28;                        // per-q stride of g[n][d] (conflict-free fragments)
   static constexpr int OFF_X = 0, OFF_U = 24;          // X[8][3], U[8][3]
   static constexpr int OFF_G = 48;                     // g[q][n][d]
-  static constexpr int OFF_F = OFF_G + NQ * GS;        // f[q][n][i]
-  static constexpr int OFF_H = OFF_F + NQ * GS;        // h[q][n][i]
-  static constexpr int OFF_S = OFF_H + NQ * GS;        // S[q][i][d] = P JxW
+  static constexpr int OFF_FH = OFF_G + NQ * GS;       // F[q][3][3], H[q][3][3] = F^-T (f = F g and h = H g are formed in phase 2)
+  static constexpr int OFF_S = OFF_FH + NQ * 18;       // S[q][i][d] = P JxW
   static constexpr int OFF_C = OFF_S + NQ * 9;         // c1..c4 per q
-  static constexpr int CELL = OFF_C + NQ * 4 + 2;      // 826 = 10 (mod 16)
+  static constexpr int CELL = OFF_C + NQ * 4 + 2;      // 522 = 10 (mod 16); >= 4 * 72 doubles of output staging
   static constexpr int WARP = 4 * CELL + 16;           // + 32 ints of corner positions
   static constexpr int WARPS = 4;
 };
 
-__global__ void __launch_bounds__(NhDmmaLayout::WARPS * 32, 2) element_nh_dmma_kernel(const ElemArgs A) {
+__global__ void __launch_bounds__(NhDmmaLayout::WARPS * 32, 3) element_nh_dmma_kernel(const ElemArgs A) {
   using L = NhDmmaLayout;
   constexpr int NN = 8, NQ = 8, DIM = 3, VEC = 3, ND = 24;
   extern __shared__ __align__(16) double sm[];
@@ -580,16 +579,13 @@ __global__ void __launch_bounds__(NhDmmaLayout::WARPS * 32, 2) element_nh_dmma_k
 #pragma unroll
     for (int n = 0; n < NN; ++n)
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        double sf = 0.0, sh = 0.0;
+      for (int i = 0; i < 3; ++i) cb[L::OFF_G + q * L::GS + n * 3 + i] = g[n][i];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          sf = fma(k.F[i][j], g[n][j], sf);
-          sh = fma(k.H[i][j], g[n][j], sh);
-        }
-        cb[L::OFF_G + q * L::GS + n * 3 + i] = g[n][i];
-        cb[L::OFF_F + q * L::GS + n * 3 + i] = sf;
-        cb[L::OFF_H + q * L::GS + n * 3 + i] = sh;
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        cb[L::OFF_FH + q * 18 + i * 3 + j] = k.F[i][j];
+        cb[L::OFF_FH + q * 18 + 9 + i * 3 + j] = k.H[i][j];
       }
     double* cc = cb + L::OFF_C + q * 4;
     cc[0] = k.m * w;                                                             // delta_ik (g_a . g_b)
@@ -613,10 +609,15 @@ __global__ void __launch_bounds__(NhDmmaLayout::WARPS * 32, 2) element_nh_dmma_k
       const double* cc = cj + L::OFF_C + qq * 4;
       const double k1 = cc[0], k2 = cc[1], k3 = cc[2], k4 = cc[3];
 #pragma unroll
+      for (int d = 0; d < 3; ++d) gq[s][d] = cj[L::OFF_G + qq * L::GS + n * 3 + d];
+      const double* FH = cj + L::OFF_FH + qq * 18;        // broadcast: the 8 lanes of a q read the same 18 doubles
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        fq[s][i] = FH[i * 3] * gq[s][0] + FH[i * 3 + 1] * gq[s][1] + FH[i * 3 + 2] * gq[s][2];
+        hq[s][i] = FH[9 + i * 3] * gq[s][0] + FH[9 + i * 3 + 1] * gq[s][1] + FH[9 + i * 3 + 2] * gq[s][2];
+      }
+#pragma unroll
       for (int d = 0; d < 3; ++d) {
-        gq[s][d] = cj[L::OFF_G + qq * L::GS + n * 3 + d];
-        fq[s][d] = cj[L::OFF_F + qq * L::GS + n * 3 + d];
-        hq[s][d] = cj[L::OFF_H + qq * L::GS + n * 3 + d];
         ga[s][d] = k1 * gq[s][d];
         pa[s][d] = k2 * fq[s][d] + k3 * hq[s][d];
         qa[s][d] = k2 * hq[s][d];
