@@ -37,9 +37,9 @@ extern "C" {
 
 /* registered constitutive laws == the reference's get_tensor_map bodies          */
 #define FEM_LAW_POISSON 0         /* params: k                       ; optional per-quad scale   */
-#define FEM_LAW_LINEAR_ELASTIC 1  /* params: E, nu                                              */
+#define FEM_LAW_LINEAR_ELASTIC 1  /* params: E, nu, plane_stress(0/1, 2-D elements only)          */
 #define FEM_LAW_NEO_HOOKEAN 2     /* params: E, nu, clamp_J(0/1)     ; optional per-quad rho     */
-#define FEM_LAW_SIMP 3            /* params: Emax, Emin, nu, penal   ; REQUIRED per-quad theta   */
+#define FEM_LAW_SIMP 3            /* params: Emax, Emin, nu, penal, plane_stress(0/1, 2-D only); REQUIRED per-quad theta */
 
 const char* fem_last_error(void);
 int fem_version(void);

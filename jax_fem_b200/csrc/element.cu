@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(CPB* NN, (LAW == FEM_LAW_NEO_HOOKEAN ? 256 / (
     } else if constexpr (LAW == FEM_LAW_LINEAR_ELASTIC || LAW == FEM_LAW_SIMP) {
       static_assert(VEC == DIM, "elasticity needs vec == dim");
       const double E = iso_modulus<LAW>(A.p, ivq, false), nu = iso_nu<LAW>(A.p);
-      const double mu = E / (2.0 * (1.0 + nu)), lam = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
+      const double mu = E / (2.0 * (1.0 + nu)), lam = E * iso_lam1<LAW, DIM>(A.p, nu);
       double sig[DIM][DIM];
       iso_stress<DIM>(lam, mu, ug, sig);
 #pragma unroll
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(CPB* NN, (LAW == FEM_LAW_NEO_HOOKEAN ? 256 / (
             }
           }
           const double nu = iso_nu<LAW>(A.p);
-          const double mu1 = 1.0 / (2.0 * (1.0 + nu)), lam1 = nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
+          const double mu1 = 1.0 / (2.0 * (1.0 + nu)), lam1 = iso_lam1<LAW, DIM>(A.p, nu);
 #pragma unroll
           for (int j = 0; j < NB; ++j) {
             double G[DIM][DIM];
@@ -739,7 +739,7 @@ __global__ void __launch_bounds__(CPB* NN) param_grad_kernel(const ElemArgs A) {
       for (int d = 0; d < DIM; ++d) ds[i][d] = A.p[0] * ug[i][d];
   } else if constexpr (LAW == FEM_LAW_LINEAR_ELASTIC || LAW == FEM_LAW_SIMP) {
     const double dE = iso_modulus<LAW>(A.p, ivq, true), nu = iso_nu<LAW>(A.p);
-    iso_stress<DIM>(dE * nu / ((1.0 + nu) * (1.0 - 2.0 * nu)), dE / (2.0 * (1.0 + nu)), ug, ds);
+    iso_stress<DIM>(dE * iso_lam1<LAW, DIM>(A.p, nu), dE / (2.0 * (1.0 + nu)), ug, ds);
   } else {
     const double E = A.p[0], nu = A.p[1];      // P is linear in E: dP/drho = P(rho = 1)
     NHPoint k;

@@ -94,6 +94,14 @@ __device__ __forceinline__ double iso_modulus(const double* p, const double* ivq
     return p[0];
   }
 }
+// lambda / E of the isotropic laws.  Plane stress (2-D only; parameter slot 2 of LINEAR_ELASTIC, slot 4 of SIMP) is the law
+// of docs/source/learn/topology_optimization/example.ipynb cell 9: lambda* = E nu / ((1+nu)(1-nu)).
+template <int LAW, int DIM>
+__device__ __forceinline__ double iso_lam1(const double* p, double nu) {
+  const bool plane_stress = DIM == 2 && (LAW == FEM_LAW_SIMP ? p[4] : p[2]) != 0.0;
+  return plane_stress ? nu / ((1.0 + nu) * (1.0 - nu)) : nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
+}
+
 template <int LAW>
 __device__ __forceinline__ double iso_nu(const double* p) {
   return LAW == FEM_LAW_SIMP ? p[2] : p[1];

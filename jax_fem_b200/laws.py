@@ -48,11 +48,12 @@ class LinearElasticity(Law):
     tests/benchmarks/linear_elasticity_cube/test_linear_elasticity_cube.py:17-25."""
     law_id = 1
 
-    def __init__(self, E, nu):
-        self.E, self.nu = float(E), float(nu)
+    def __init__(self, E, nu, plane_stress=False):
+        """plane_stress (2-D elements only): lambda* = E nu / ((1+nu)(1-nu)) instead of the plane-strain / 3-D lambda."""
+        self.E, self.nu, self.plane_stress = float(E), float(nu), bool(plane_stress)
 
     def params(self):
-        return [self.E, self.nu]
+        return [self.E, self.nu, 1.0 if self.plane_stress else 0.0]
 
 
 class NeoHookean(Law):
@@ -78,11 +79,14 @@ class SIMP(Law):
     n_internal_vars = 1
     requires_internal_var = True
 
-    def __init__(self, Emax, Emin, nu, penal=3.0):
+    def __init__(self, Emax, Emin, nu, penal=3.0, plane_stress=None):
+        """plane_stress: None = the reference's own choice for the element (its only 2-D SIMP law, the topology
+        optimisation notebook, is plane stress; its 3-D one is the full isotropic law): True on QUAD4, False on 3-D."""
         self.Emax, self.Emin, self.nu, self.penal = float(Emax), float(Emin), float(nu), float(penal)
+        self.plane_stress = plane_stress
 
     def params(self):
-        return [self.Emax, self.Emin, self.nu, self.penal]
+        return [self.Emax, self.Emin, self.nu, self.penal, 1.0 if self.plane_stress else 0.0]
 
 
 REGISTERED = {
@@ -101,4 +105,10 @@ def resolve(tensor_map, ele_type, vec):
     if (ele_type, vec, type(tensor_map)) not in REGISTERED:
         raise UnregisteredLawError(
             f"no sm_100a kernel is registered for (ele_type={ele_type}, vec={vec}, law={type(tensor_map).__name__})")
+    if isinstance(tensor_map, (LinearElasticity, SIMP)):
+        two_d = ele_type == 'QUAD4'
+        if tensor_map.plane_stress is None:
+            tensor_map.plane_stress = two_d
+        if tensor_map.plane_stress and not two_d:
+            raise UnregisteredLawError("plane_stress is a 2-D assumption; it is not registered for 3-D elements")
     return tensor_map

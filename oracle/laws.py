@@ -58,12 +58,17 @@ def _iso_tangent(d):
 
 
 class LinearElastic:
-    def __init__(self, E, nu):
-        self.E, self.nu = float(E), float(nu)
+    """plane_stress=True (2-D only) is the law of docs/source/learn/topology_optimization/example.ipynb cell 9:
+    sig11 = E/((1+nu)(1-nu)) (eps11 + nu eps22), sig12 = E/(1+nu) eps12, i.e. the isotropic form with
+    lambda* = E nu / ((1+nu)(1-nu))."""
+
+    def __init__(self, E, nu, plane_stress=False):
+        self.E, self.nu, self.plane_stress = float(E), float(nu), bool(plane_stress)
 
     def lame(self, E):
         nu = self.nu
-        return E * nu / ((1 + nu) * (1 - 2 * nu)), E / (2. * (1. + nu))
+        lam = E * nu / ((1 + nu) * (1 - nu)) if self.plane_stress else E * nu / ((1 + nu) * (1 - 2 * nu))
+        return lam, E / (2. * (1. + nu))
 
     def stress(self, ug):
         lam, mu = self.lame(self.E)
@@ -79,8 +84,9 @@ class LinearElastic:
 class SIMP(LinearElastic):
     """E(theta) = Emin + (Emax - Emin) theta^p, then isotropic linear elasticity."""
 
-    def __init__(self, Emax, Emin, nu, p=3.0):
+    def __init__(self, Emax, Emin, nu, p=3.0, plane_stress=False):
         self.Emax, self.Emin, self.nu, self.p = float(Emax), float(Emin), float(nu), float(p)
+        self.plane_stress = bool(plane_stress)
 
     def E_of(self, theta):
         return self.Emin + (self.Emax - self.Emin) * theta ** self.p

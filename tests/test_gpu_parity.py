@@ -530,3 +530,42 @@ def test_full_size_neohookean_tangent_is_the_derivative_of_the_residual():
     err, ref = float((Av - fd).abs().max()), float(Av.abs().max())
     assert err <= 1e-7 * ref, (err, ref)
     assert float((A.transpose().data - A.data).abs().max()) <= 1e-11 * float(A.data.abs().max())
+
+
+@pytest.mark.parametrize("law_name", ["elastic_plane_strain", "elastic_plane_stress", "simp_default_plane_stress"])
+def test_quad4_elasticity_and_plane_stress_simp_match_oracle(law_name):
+    """2-D elasticity on QUAD4: plane strain, plane stress, and SIMP with the reference's own 2-D choice (plane stress,
+    docs/source/learn/topology_optimization/example.ipynb cell 9), element values and assembled operator vs the oracle."""
+    import jax_fem_b200 as jf
+    from jax_fem_b200 import laws
+    m = jf.rectangle_mesh(7, 5, 1.4, 1.0)
+    pts = m.points.copy()
+    rng = np.random.default_rng(2)
+    pts += 0.03 * rng.uniform(-0.5, 0.5, pts.shape)
+    cells = m.cells_dict['quad']
+    iv = None
+    if law_name == "simp_default_plane_stress":
+        law, olaw = laws.SIMP(70e3, 70.0, 0.3, 3.0), olaws.SIMP(70e3, 70.0, 0.3, 3.0, plane_stress=True)
+        iv = 0.2 + 0.7 * rng.uniform(0, 1, (len(cells), 4))
+    else:
+        ps = law_name.endswith("stress")
+        law, olaw = laws.LinearElasticity(70e3, 0.3, plane_stress=ps), olaws.LinearElastic(70e3, 0.3, plane_stress=ps)
+    left = lambda p: np.isclose(p[0], 0., atol=0.05)
+    bc = [[left, left], [0, 1], [lambda p: 0., lambda p: 0.01]]
+    cls = type("P2D", (jf.Problem,), {"get_tensor_map": lambda self: law})
+    prob = cls(jf.Mesh(pts, cells), vec=2, dim=2, ele_type='QUAD4', dirichlet_bc_info=bc)
+    assert law.plane_stress == (law_name != "elastic_plane_strain")
+    if iv is not None:
+        prob.internal_vars = [torch.from_numpy(iv).cuda()]
+    opb = fem.Problem(fem.Mesh(pts, cells), 2, 2, ele_type='QUAD4', dirichlet_bc_info=bc, law=olaw,
+                      internal_vars=() if iv is None else [iv])
+    sol = 0.01 * rng.standard_normal((len(pts), 2))
+    res = prob.newton_update([torch.from_numpy(sol).cuda()])[0]
+    A = jf.get_A(prob)
+    assert relmax(host(prob.element_tangents()), opb.cell_jacobians(sol)) <= VAL_TOL
+    ores = opb.newton_update(sol)
+    oA = fem.get_A(opb)
+    assert np.array_equal(host(A.getValuesCSR()[1]), oA.indices) and relmax(host(A.data), oA.data) <= VAL_TOL
+    assert relmax(host(res), ores) <= VAL_TOL
+    with pytest.raises(laws.UnregisteredLawError):
+        laws.resolve(laws.LinearElasticity(1., .3, plane_stress=True), 'HEX8', 3)

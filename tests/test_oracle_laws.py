@@ -104,3 +104,28 @@ def test_krylov_restatements_agree_with_direct_solve():
         x, k = fem.jax_solve(A, b, np.zeros_like(b), True, method, return_iters=True)
         assert 0 < k < 500
         assert np.abs(x - x_ref).max() <= 1e-8 * np.abs(x_ref).max()
+
+
+def test_plane_stress_simp_is_the_topology_optimisation_notebook_law():
+    """docs/source/learn/topology_optimization/example.ipynb cell 9 (restated): plane-stress Hooke's law with the SIMP
+    modulus.  The oracle expresses it as the isotropic form with lambda* = E nu / ((1+nu)(1-nu))."""
+    from oracle import laws
+    rng = np.random.default_rng(0)
+    ug = rng.standard_normal((5, 4, 2, 2)) * 0.01
+    theta = rng.uniform(0.1, 1.0, (5, 4))
+    Emax, nu, penal = 70e3, 0.3, 3.0
+    Emin = 1e-3 * Emax
+    law = laws.SIMP(Emax, Emin, nu, penal, plane_stress=True)
+    E = Emin + (Emax - Emin) * theta ** penal
+    eps = 0.5 * (ug + np.swapaxes(ug, -1, -2))
+    s11 = E / (1 + nu) / (1 - nu) * (eps[..., 0, 0] + nu * eps[..., 1, 1])
+    s22 = E / (1 + nu) / (1 - nu) * (nu * eps[..., 0, 0] + eps[..., 1, 1])
+    s12 = E / (1 + nu) * eps[..., 0, 1]
+    ref = np.stack([np.stack([s11, s12], -1), np.stack([s12, s22], -1)], -2)
+    assert np.abs(law.stress(ug, theta) - ref).max() <= 1e-13 * np.abs(ref).max()
+    # tangent and parameter derivative are consistent with the stress (finite differences)
+    assert np.abs(law.tangent(ug, theta) - laws.fd_tangent(law, ug, theta)).max() <= 1e-5 * np.abs(law.tangent(ug, theta)).max()
+    h = 1e-6
+    fd = (law.stress(ug, theta + h) - law.stress(ug, theta - h)) / (2 * h)
+    assert np.abs(law.dstress_dparam(ug, theta) - fd).max() <= 1e-6 * np.abs(fd).max()
+    assert np.abs(laws.SIMP(Emax, Emin, nu, penal).stress(ug, theta) - ref).max() > 1e-3 * np.abs(ref).max()   # plane strain differs
