@@ -68,6 +68,106 @@ struct FusedArgs {
   double p[8];
 };
 
+
+// ---- pieces shared by the two kernels ------------------------------------------------------------------------------
+struct PatchView {       // per-patch shared-memory state
+  double *acc, *racc, *fext, *xu;
+  int *s_node, *s_out, *s_acc, *s_info;      // s_info: len | diagonal slot << 8 | Dirichlet flags << 16
+};
+
+struct PatchRange {
+  int node0, lnode0, chunk0, n_owned, n_local, n_chunks;
+};
+
+__device__ __forceinline__ PatchRange patch_range(const FusedArgs& A, int patch) {
+  const int* h0 = A.phdr + (int64_t)patch * 8;
+  PatchRange r;
+  r.node0 = h0[0]; r.lnode0 = h0[1]; r.chunk0 = h0[3];
+  r.n_owned = h0[8] - r.node0; r.n_local = h0[9] - r.lnode0; r.n_chunks = h0[11] - r.chunk0;
+  return r;
+}
+
+// prologue: owned-node tables (with the Dirichlet flags and the constant loads) and the coordinates / solution of the
+// patch's local nodes -> shared memory
+template <int THREADS>
+__device__ __forceinline__ void patch_prologue(const FusedArgs& A, const PatchRange& r, const PatchView& v) {
+  const int tid = threadIdx.x;
+  __syncthreads();            // previous patch: epilogue done with s_*, xu, fext
+  if (tid < r.n_owned) {
+    const int nd = A.pn_node[r.node0 + tid];
+    const uint8_t* f = A.bc_flag + 3 * (int64_t)nd;
+    v.s_node[tid] = nd;
+    v.s_out[tid] = A.pn_out[r.node0 + tid];
+    v.s_acc[tid] = A.pn_acc[r.node0 + tid];
+    v.s_info[tid] = A.pn_info[r.node0 + tid] | ((f[0] ? 1 : 0) << 16) | ((f[1] ? 1 : 0) << 17) | ((f[2] ? 1 : 0) << 18);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) v.fext[tid * 3 + d] = A.f_ext ? A.f_ext[3 * (int64_t)nd + d] : 0.0;
+  }
+  for (int i = tid; i < r.n_local; i += THREADS) {
+    const int64_t node = A.lnodes[r.lnode0 + i];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) v.xu[i * 6 + d] = A.points[node * 3 + d];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) v.xu[i * 6 + 3 + d] = A.sol[node * 3 + d];
+  }
+  __syncthreads();
+}
+
+// phase 1 of one (cell, q): geometry, grad u, stress -> g[8][3], E w, S = sigma JxW (fe.py:112-141, problem.py:204-210)
+template <int LAW>
+__device__ __forceinline__ void cell_point(const FusedArgs& A, const double* xu, const double* tabq, double wq, int pc, int q,
+                                           double nu, double (&g)[8][3], double& Ew, double (&S)[3][3]) {
+  const int2 lw = reinterpret_cast<const int2*>(A.pc_ln)[pc];
+  const double* ivq = A.iv ? A.iv + (int64_t)A.pc_cell[pc] * 8 + q : nullptr;
+  const double E = iso_modulus<LAW>(A.p, ivq, false);
+  double X[24], U[24];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const int ln = ((m < 4 ? lw.x : lw.y) >> (8 * (m & 3))) & 255;
+    const double2* src = reinterpret_cast<const double2*>(xu + ln * 6);
+    const double2 v0 = src[0], v1 = src[1], v2 = src[2];
+    X[m * 3 + 0] = v0.x; X[m * 3 + 1] = v0.y; X[m * 3 + 2] = v1.x;
+    U[m * 3 + 0] = v1.y; U[m * 3 + 1] = v2.x; U[m * 3 + 2] = v2.y;
+  }
+  const double w = qp_geometry<8, 3>(X, tabq, wq, g);
+  double ug[3][3];
+  qp_grad_u<8, 3, 3>(U, g, ug);
+  const double mu = E / (2.0 * (1.0 + nu)), lam = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
+  iso_stress<3>(lam, mu, ug, S);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) S[i][d] *= w;
+  Ew = E * w;
+}
+
+// epilogue: Dirichlet rows -> unit rows (pattern kept), coalesced copy of the finished CSR rows, residual + constant
+// loads; the accumulators are zeroed for the next patch on the way out
+template <int THREADS>
+__device__ __forceinline__ void patch_epilogue(const FusedArgs& A, const PatchRange& r, const PatchView& v) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = warp; i < r.n_owned; i += THREADS / 32) {
+    const int nd = v.s_node[i], info = v.s_info[i];
+    const int len = info & 255, dg = (info >> 8) & 255, fl = info >> 16;
+    const int tot = 9 * len, len3 = 3 * len;
+    double* src = v.acc + v.s_acc[i];
+    double* dst = A.data + v.s_out[i];
+    for (int e = lane; e < tot; e += 32) {
+      double val = src[e];
+      src[e] = 0.0;
+      if (fl) {
+        const int row = e / len3, col = e - row * len3;
+        if ((fl >> row) & 1) val = (col == 3 * dg + row) ? 1.0 : 0.0;
+      }
+      dst[e] = val;
+    }
+    if (lane < 3) {
+      A.res[3 * (int64_t)nd + lane] = v.racc[i * 3 + lane] + v.fext[i * 3 + lane];
+      v.racc[i * 3 + lane] = 0.0;
+    }
+  }
+}
+
 template <int LAW, class L>
 __global__ void __launch_bounds__(L::THREADS, L::CTAS) fused_assembly_kernel(const FusedArgs A) {
   constexpr int NN = L::NN, NQ = L::NQ, DIM = L::DIM, VEC = L::VEC, SPLIT = L::SPLIT, CPT = L::CPT;
@@ -82,7 +182,8 @@ __global__ void __launch_bounds__(L::THREADS, L::CTAS) fused_assembly_kernel(con
   int* s_out = s_node + L::MAX_OWNED;
   int* s_acc = s_out + L::MAX_OWNED;
   int* s_info = s_acc + L::MAX_OWNED;      // len | diagonal slot << 8 | Dirichlet flags << 16
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const PatchView pv{acc, racc, fext, xu, s_node, s_out, s_acc, s_info};
+  const int tid = threadIdx.x;
 
   for (int i = tid; i < NQ * NN * DIM; i += L::THREADS) tab[(i / (NN * DIM)) * L::TAB_STRIDE + i % (NN * DIM)] = A.ref[i];
   if (tid < NQ) tab[NQ * L::TAB_STRIDE + tid] = A.ref[NQ * NN * DIM + tid];
@@ -93,28 +194,9 @@ __global__ void __launch_bounds__(L::THREADS, L::CTAS) fused_assembly_kernel(con
 
 #pragma unroll 1
   for (int patch = blockIdx.x; patch < A.n_patches; patch += gridDim.x) {
-    const int* h0 = A.phdr + (int64_t)patch * 8;
-    const int node0 = h0[0], lnode0 = h0[1], chunk0 = h0[3];
-    const int n_owned = h0[8] - node0, n_local = h0[9] - lnode0, n_chunks = h0[11] - chunk0;
-    __syncthreads();            // previous patch: epilogue done with s_*, xu, fext
-    if (tid < n_owned) {
-      const int n = A.pn_node[node0 + tid];
-      const uint8_t* f = A.bc_flag + 3 * (int64_t)n;
-      s_node[tid] = n;
-      s_out[tid] = A.pn_out[node0 + tid];
-      s_acc[tid] = A.pn_acc[node0 + tid];
-      s_info[tid] = A.pn_info[node0 + tid] | ((f[0] ? 1 : 0) << 16) | ((f[1] ? 1 : 0) << 17) | ((f[2] ? 1 : 0) << 18);
-#pragma unroll
-      for (int d = 0; d < VEC; ++d) fext[tid * 3 + d] = A.f_ext ? A.f_ext[3 * (int64_t)n + d] : 0.0;
-    }
-    for (int i = tid; i < n_local; i += L::THREADS) {
-      const int64_t node = A.lnodes[lnode0 + i];
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) xu[i * 6 + d] = A.points[node * DIM + d];
-#pragma unroll
-      for (int d = 0; d < VEC; ++d) xu[i * 6 + 3 + d] = A.sol[node * VEC + d];
-    }
-    __syncthreads();
+    const PatchRange pr = patch_range(A, patch);
+    const int chunk0 = pr.chunk0, n_chunks = pr.n_chunks;
+    patch_prologue<L::THREADS>(A, pr, pv);
 
 #pragma unroll 1
     for (int k = 0; k < n_chunks; ++k) {
@@ -131,35 +213,17 @@ __global__ void __launch_bounds__(L::THREADS, L::CTAS) fused_assembly_kernel(con
       // ---------------- phase 1: thread = (cell, q) ----------------
       if (tid < ncell * NQ) {
         const int cl = tid >> 3, q = tid & 7;
-        const int pc = c0 + cl;
-        const int2 lw = reinterpret_cast<const int2*>(A.pc_ln)[pc];
-        const double* ivq = A.iv ? A.iv + (int64_t)A.pc_cell[pc] * NQ + q : nullptr;
-        const double E = iso_modulus<LAW>(A.p, ivq, false);
-        double X[NN * DIM], U[NN * VEC];
-#pragma unroll
-        for (int n = 0; n < NN; ++n) {
-          const int ln = ((n < 4 ? lw.x : lw.y) >> (8 * (n & 3))) & 255;
-          const double2* src = reinterpret_cast<const double2*>(xu + ln * 6);
-          const double2 v0 = src[0], v1 = src[1], v2 = src[2];
-          X[n * 3 + 0] = v0.x; X[n * 3 + 1] = v0.y; X[n * 3 + 2] = v1.x;
-          U[n * 3 + 0] = v1.y; U[n * 3 + 1] = v2.x; U[n * 3 + 2] = v2.y;
-        }
-        double g[NN][DIM];
-        const double w = qp_geometry<NN, DIM>(X, tab + q * L::TAB_STRIDE, tab[NQ * L::TAB_STRIDE + q], g);
-        double ug[VEC][DIM];
-        qp_grad_u<NN, DIM, VEC>(U, g, ug);
-        const double mu = E / (2.0 * (1.0 + nu)), lam = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
-        double sig[DIM][DIM];
-        iso_stress<DIM>(lam, mu, ug, sig);
+        double g[NN][DIM], sig[DIM][DIM], Ew;
+        cell_point<LAW>(A, xu, tab + q * L::TAB_STRIDE, tab[NQ * L::TAB_STRIDE + q], c0 + cl, q, nu, g, Ew, sig);
         double* rq = recs + cl * L::CELLREC + q * L::QREC;
 #pragma unroll
         for (int t = 0; t < 12; ++t)
           reinterpret_cast<double2*>(rq + L::OFF_G)[t] = make_double2(g[(2 * t) / 3][(2 * t) % 3], g[(2 * t + 1) / 3][(2 * t + 1) % 3]);
-        rq[L::OFF_E] = E * w;
+        rq[L::OFF_E] = Ew;
 #pragma unroll
         for (int i = 0; i < VEC; ++i)
 #pragma unroll
-          for (int d = 0; d < DIM; ++d) rq[L::OFF_S + i * DIM + d] = sig[i][d] * w;
+          for (int d = 0; d < DIM; ++d) rq[L::OFF_S + i * DIM + d] = sig[i][d];
       }
       __syncthreads();
 
@@ -263,27 +327,7 @@ __global__ void __launch_bounds__(L::THREADS, L::CTAS) fused_assembly_kernel(con
       if (ntask == 0) __syncthreads();     // records may not be overwritten before every thread left phase 2
     }
 
-    // ---------------- epilogue: Dirichlet rows, coalesced copy-out, re-zero ----------------
-    for (int i = warp; i < n_owned; i += L::THREADS / 32) {
-      const int n = s_node[i], info = s_info[i];
-      const int len = info & 255, dg = (info >> 8) & 255, fl = info >> 16;
-      const int tot = 9 * len, len3 = 3 * len;
-      double* src = acc + s_acc[i];
-      double* dst = A.data + s_out[i];
-      for (int e = lane; e < tot; e += 32) {
-        double v = src[e];
-        src[e] = 0.0;
-        if (fl) {
-          const int row = e / len3, col = e - row * len3;
-          if ((fl >> row) & 1) v = (col == 3 * dg + row) ? 1.0 : 0.0;
-        }
-        dst[e] = v;
-      }
-      if (lane < 3) {
-        A.res[3 * (int64_t)n + lane] = racc[i * 3 + lane] + fext[i * 3 + lane];
-        racc[i * 3 + lane] = 0.0;
-      }
-    }
+    patch_epilogue<L::THREADS>(A, pr, pv);
   }
 }
 
@@ -310,7 +354,7 @@ int launch_fused(const FusedArgs& A, cudaStream_t st) {
 // surface pay the full tile for the few rows that are kept (125 cells per 64 owned nodes).
 
 struct FusedDmmaCfg {
-  static constexpr int THREADS = 256, WARPS = 8, MAX_OWNED = 64, MAX_LOCAL = 256;
+  static constexpr int THREADS = 256, MAX_OWNED = 64, MAX_LOCAL = 256;
   static constexpr int SUB = 8;                    // cells per chunk (patch_plan CONFIGS[4].chunk) = warps
   static constexpr int NSUB = 4;                   // chunks per phase-1 batch
   static constexpr int BATCH = SUB * NSUB;
@@ -345,6 +389,7 @@ __global__ void __launch_bounds__(FusedDmmaCfg::THREADS, 1) fused_dmma_kernel(co
   int* s_out = s_node + L::MAX_OWNED;
   int* s_acc = s_out + L::MAX_OWNED;
   int* s_info = s_acc + L::MAX_OWNED;      // len | diagonal slot << 8 | Dirichlet flags << 16
+  const PatchView pv{acc, racc, fext, xu, s_node, s_out, s_acc, s_info};
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   for (int i = tid; i < NQ * NN * DIM; i += L::THREADS) tab[(i / (NN * DIM)) * L::TAB_STRIDE + i % (NN * DIM)] = A.ref[i];
@@ -357,28 +402,9 @@ __global__ void __launch_bounds__(FusedDmmaCfg::THREADS, 1) fused_dmma_kernel(co
 
 #pragma unroll 1
   for (int patch = blockIdx.x; patch < A.n_patches; patch += gridDim.x) {
-    const int* h0 = A.phdr + (int64_t)patch * 8;
-    const int node0 = h0[0], lnode0 = h0[1], chunk0 = h0[3];
-    const int n_owned = h0[8] - node0, n_local = h0[9] - lnode0, n_chunks = h0[11] - chunk0;
-    __syncthreads();            // previous patch: epilogue done with s_*, xu, fext
-    if (tid < n_owned) {
-      const int nd = A.pn_node[node0 + tid];
-      const uint8_t* f = A.bc_flag + 3 * (int64_t)nd;
-      s_node[tid] = nd;
-      s_out[tid] = A.pn_out[node0 + tid];
-      s_acc[tid] = A.pn_acc[node0 + tid];
-      s_info[tid] = A.pn_info[node0 + tid] | ((f[0] ? 1 : 0) << 16) | ((f[1] ? 1 : 0) << 17) | ((f[2] ? 1 : 0) << 18);
-#pragma unroll
-      for (int d = 0; d < VEC; ++d) fext[tid * 3 + d] = A.f_ext ? A.f_ext[3 * (int64_t)nd + d] : 0.0;
-    }
-    for (int i = tid; i < n_local; i += L::THREADS) {
-      const int64_t node = A.lnodes[lnode0 + i];
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) xu[i * 6 + d] = A.points[node * DIM + d];
-#pragma unroll
-      for (int d = 0; d < VEC; ++d) xu[i * 6 + 3 + d] = A.sol[node * VEC + d];
-    }
-    __syncthreads();
+    const PatchRange pr = patch_range(A, patch);
+    const int chunk0 = pr.chunk0, n_chunks = pr.n_chunks;
+    patch_prologue<L::THREADS>(A, pr, pv);
 
 #pragma unroll 1
     for (int k0 = 0; k0 < n_chunks; k0 += L::NSUB) {
@@ -409,26 +435,8 @@ __global__ void __launch_bounds__(FusedDmmaCfg::THREADS, 1) fused_dmma_kernel(co
       // ---------------- phase 1: thread = (cell, q) ----------------
       if (tid < ncell * NQ) {
         const int cl = tid >> 3, q = tid & 7;
-        const int pc = cbase + cl;
-        const int2 lw = reinterpret_cast<const int2*>(A.pc_ln)[pc];
-        const double* ivq = A.iv ? A.iv + (int64_t)A.pc_cell[pc] * NQ + q : nullptr;
-        const double E = iso_modulus<LAW>(A.p, ivq, false);
-        double X[NN * DIM], U[NN * VEC];
-#pragma unroll
-        for (int m = 0; m < NN; ++m) {
-          const int ln = ((m < 4 ? lw.x : lw.y) >> (8 * (m & 3))) & 255;
-          const double2* src = reinterpret_cast<const double2*>(xu + ln * 6);
-          const double2 v0 = src[0], v1 = src[1], v2 = src[2];
-          X[m * 3 + 0] = v0.x; X[m * 3 + 1] = v0.y; X[m * 3 + 2] = v1.x;
-          U[m * 3 + 0] = v1.y; U[m * 3 + 1] = v2.x; U[m * 3 + 2] = v2.y;
-        }
-        double g[NN][DIM];
-        const double w = qp_geometry<NN, DIM>(X, tab + q * L::TAB_STRIDE, tab[NQ * L::TAB_STRIDE + q], g);
-        double ug[VEC][DIM];
-        qp_grad_u<NN, DIM, VEC>(U, g, ug);
-        const double mu = E / (2.0 * (1.0 + nu)), lam = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
-        double sig[DIM][DIM];
-        iso_stress<DIM>(lam, mu, ug, sig);
+        double g[NN][DIM], sig[DIM][DIM], Ew;
+        cell_point<LAW>(A, xu, tab + q * L::TAB_STRIDE, tab[NQ * L::TAB_STRIDE + q], cbase + cl, q, nu, g, Ew, sig);
         double* cb = cellsm + cl * L::CELL;
 #pragma unroll
         for (int u = 0; u < 12; ++u)
@@ -436,8 +444,8 @@ __global__ void __launch_bounds__(FusedDmmaCfg::THREADS, 1) fused_dmma_kernel(co
 #pragma unroll
         for (int i = 0; i < VEC; ++i)
 #pragma unroll
-          for (int d = 0; d < DIM; ++d) cb[L::OFF_S + q * 9 + i * DIM + d] = sig[i][d] * w;
-        cb[L::OFF_E + q] = E * w;
+          for (int d = 0; d < DIM; ++d) cb[L::OFF_S + q * 9 + i * DIM + d] = sig[i][d];
+        cb[L::OFF_E + q] = Ew;
       }
       __syncthreads();
 
@@ -502,27 +510,7 @@ __global__ void __launch_bounds__(FusedDmmaCfg::THREADS, 1) fused_dmma_kernel(co
       }
     }
 
-    // ---------------- epilogue: Dirichlet rows, coalesced copy-out, re-zero ----------------
-    for (int i = warp; i < n_owned; i += L::THREADS / 32) {
-      const int nd = s_node[i], info = s_info[i];
-      const int len = info & 255, dg = (info >> 8) & 255, fl = info >> 16;
-      const int tot = 9 * len, len3 = 3 * len;
-      double* src = acc + s_acc[i];
-      double* dst = A.data + s_out[i];
-      for (int e = lane; e < tot; e += 32) {
-        double v = src[e];
-        src[e] = 0.0;
-        if (fl) {
-          const int row = e / len3, col = e - row * len3;
-          if ((fl >> row) & 1) v = (col == 3 * dg + row) ? 1.0 : 0.0;
-        }
-        dst[e] = v;
-      }
-      if (lane < 3) {
-        A.res[3 * (int64_t)nd + lane] = racc[i * 3 + lane] + fext[i * 3 + lane];
-        racc[i * 3 + lane] = 0.0;
-      }
-    }
+    patch_epilogue<L::THREADS>(A, pr, pv);
   }
 }
 

@@ -187,7 +187,8 @@ def test_product_never_imports_the_oracle():
 
 
 def _patch_plan_case(points, cells, bc_info, law, config):
-    from jax_fem_b200.patch_plan import CONFIGS, build_patch_plan, emulate
+    from jax_fem_b200.patch_plan import CONFIGS, build_patch_plan
+    from patch_emulator import emulate
     pb = fem.Problem(fem.Mesh(points, cells), 3, 3, dirichlet_bc_info=bc_info, law=law)
     nn = len(points)
     sol = np.random.default_rng(1).standard_normal((nn, 3)) * 1e-3
