@@ -569,3 +569,31 @@ def test_quad4_elasticity_and_plane_stress_simp_match_oracle(law_name):
     assert relmax(host(res), ores) <= VAL_TOL
     with pytest.raises(laws.UnregisteredLawError):
         laws.resolve(laws.LinearElasticity(1., .3, plane_stress=True), 'HEX8', 3)
+
+
+@pytest.mark.parametrize("mode", ["staged", "fused"])
+def test_assembly_on_randomly_renumbered_mesh(mode, monkeypatch):
+    """Generality of the plans: a non-affine box whose nodes and cells are randomly renumbered (no tensor-grid structure in
+    the numbering, scattered CSR rows, bin-based patches) must assemble to the oracle's operator in both assembly modes."""
+    import jax_fem_b200 as jf
+    import gpu_problems as gp
+    pts, cells = perturbed_box(12, seed=9)
+    rng = np.random.default_rng(21)
+    perm = rng.permutation(len(pts))                 # new id of old node i
+    pts2 = np.empty_like(pts)
+    pts2[perm] = pts
+    cells2 = perm[cells][rng.permutation(len(cells))]
+    bc = [[lambda p: p[0] < 0.05] * 3, [0, 1, 2], [lambda p: 0., lambda p: 0.01, lambda p: -0.01]]
+    monkeypatch.setenv("FEM_ASSEMBLY", mode)
+    prob = gp.PlainElasticity(jf.Mesh(pts2, cells2), vec=3, dim=3, dirichlet_bc_info=bc)
+    opb = fem.Problem(fem.Mesh(pts2, cells2), 3, 3, dirichlet_bc_info=bc, law=olaws.LinearElastic(70e3, 0.3))
+    sol = 0.01 * rng.standard_normal((len(pts2), 3))
+    res = prob.newton_update([torch.from_numpy(sol).cuda()])[0]
+    A = jf.get_A(prob)
+    ores = opb.newton_update(sol)
+    oA = fem.get_A(opb)
+    indptr, indices, data = [host(t) for t in A.getValuesCSR()]
+    assert np.array_equal(indptr, oA.indptr) and np.array_equal(indices, oA.indices)
+    assert relmax(data, oA.data) <= VAL_TOL and relmax(host(res), ores) <= VAL_TOL
+    x = jf.solver(prob, {'jax_solver': {'method': 'cg'}})[0]
+    assert relmax(host(x), fem.solver(opb, method='cg')) <= SOL_TOL
