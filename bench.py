@@ -191,7 +191,14 @@ def problem_class(workload="elasticity"):
         def get_surface_maps(self):
             return [lambda u, x: np.array([0., 1e-3, 0.])]
 
-    return NeoHookean if workload == "neohookean" else Elasticity
+    class SIMPCantilever(jf.Problem):         # cfg 5: topology_optimization example.ipynb cell 9 law, 3-D isotropic form
+        def get_tensor_map(self):
+            return laws.SIMP(70e3, 70.0, 0.3, 3.0)
+
+        def get_surface_maps(self):
+            return [lambda u, x: np.array([0., 0., 100.])]
+
+    return {"neohookean": NeoHookean, "simp": SIMPCantilever}.get(workload, Elasticity)
 
 
 def build_problem(size, world=1, comm=None, workload="elasticity"):
@@ -246,7 +253,9 @@ def main():
     ap.add_argument("--solve", action="store_true", help="also time a full Jacobi-CG solve")
     ap.add_argument("--newton", action="store_true",
                     help="also time the full Newton solve with per-iteration re-assembly (cfg 3 with --workload neohookean)")
-    ap.add_argument("--workload", default="elasticity", choices=["elasticity", "neohookean", "hex27"],
+    ap.add_argument("--adjoint", action="store_true",
+                    help="also time cfg 5's chain: forward solve + implicit adjoint + per-element density gradient (--workload simp)")
+    ap.add_argument("--workload", default="elasticity", choices=["elasticity", "neohookean", "hex27", "simp"],
                     help="elasticity = cfg 2 (the headline, default); neohookean = cfg 3's law on the same mesh; "
                          "hex27 = cfg 4 (use --size 60)")
     args = ap.parse_args()
@@ -291,6 +300,12 @@ def main():
     own_frac = n / n_local
     b_asm, b_spmv = algorithmic_bytes(n, int(nnz * own_frac), int(prob.num_cells * own_frac), int(fe.num_total_nodes * own_frac),
                                       nodes_per_cell=fe.num_nodes)
+    if args.workload == "simp":
+        # theta = 0.5 + 0.1 U(-1, 1) per cell (default_rng(0) on the GLOBAL cell numbering), constant over a cell's points
+        n_cells_global = args.size ** 3 * world
+        theta_g = 0.5 + 0.1 * np.random.default_rng(0).uniform(-1, 1, n_cells_global)
+        local_cells = sharded.part.local_cells if sharded else np.arange(n_cells_global)
+        prob.internal_vars = [torch.from_numpy(np.repeat(theta_g[local_cells][:, None], fe.num_quads, axis=1)).to(dev)]
     rng = np.random.default_rng(rank)
     sol_host = torch.from_numpy(1e-3 * rng.standard_normal((fe.num_total_nodes, 3))).pin_memory()
     sol = sol_host.to(dev)
@@ -436,6 +451,38 @@ def main():
         log(f"newton: {ninfo}, {ns:.2f}s")
         newton = dict(ninfo, seconds=ns, method="Newton (tol 1e-6, rel 1e-8), tangent re-assembled every iteration, Jacobi-CG 1e-10"
                       + (", cells sharded in x-slabs" if sharded else ""))
+    adjoint = None
+    if args.adjoint:
+        from jax_fem_b200.solver import implicit_vjp
+        barrier()
+        c0 = time.perf_counter()
+        if sharded:
+            u = sharded.solve_linear()
+            it_fwd = sharded.last_info["iterations"]
+            f_ext = prob._f_ext if prob._f_ext is not None else torch.zeros_like(u)
+            Jloc = -(f_ext[:sharded.part.n_owned] * u[:sharded.part.n_owned]).sum().reshape(1)
+            comm.allreduce(Jloc)
+            barrier()
+            c1 = time.perf_counter()
+            grad = sharded.adjoint_gradient(u, -f_ext)
+            it_adj = sharded.last_info["iterations"]
+        else:
+            u = jf.solver(prob, {"jax_solver": {"method": "cg"}})[0]
+            it_fwd = None
+            Jloc = -(prob._f_ext * u).sum().reshape(1)
+            torch.cuda.synchronize()
+            c1 = time.perf_counter()
+            grad = implicit_vjp(prob, [u], None, [-prob._f_ext], {"jax_solver": {}})
+            it_adj = None
+        barrier()
+        c2 = time.perf_counter()
+        gsum = grad.sum(1)
+        log(f"adjoint: J={float(Jloc):.6e}, forward {c1 - c0:.2f}s ({it_fwd} its), adjoint+gradient {c2 - c1:.2f}s ({it_adj} its), "
+            f"|dJ/dtheta|_max={float(gsum.abs().max()):.4e}")
+        adjoint = {"objective": "compliance int t.u ds", "J": float(Jloc), "forward_seconds": c1 - c0, "forward_iterations": it_fwd,
+                   "adjoint_seconds": c2 - c1, "adjoint_iterations": it_adj, "grad_abs_max": float(gsum.abs().max()),
+                   "method": "forward Jacobi-CG 1e-10; adjoint A^T lambda = dJ/du by Jacobi-BiCGSTAB 1e-10; gradient -lambda^T dc/dtheta per cell"
+                             + (", cells sharded in x-slabs" if sharded else "")}
     clocks = sampler.stop() if rank == 0 else None
 
     # max over ranks (device times)
@@ -459,6 +506,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": {"neohookean": "[NON-HEADLINE: Neo-Hookean E=10 nu=0.3] ", "hex27": "[NON-HEADLINE: HEX27, 216-point quadrature] ",
+                                    "simp": "[NON-HEADLINE: SIMP Emax=70e3 Emin=70 p=3, theta = 0.5 + 0.1 U(-1,1)] ",
                                     "elasticity": ""}[args.workload] +
                                    f"HEX8 box {args.size * world}x{args.size}x{args.size} linear elasticity E=70e3 nu=0.3, u=0 on x=0, "
                                    f"traction on x=Lx (cfg 2{'' if world == 1 else ' extended in x: weak scaling'})",
@@ -486,6 +534,8 @@ def main():
             line["cg_solve"] = solve
         if newton:
             line["newton_solve"] = newton
+        if adjoint:
+            line["adjoint"] = adjoint
         if not args.no_cpu_baseline and world == 1:
             log(f"timing the CPU oracle on {args.ref_size}^3")
             v, info = cpu_oracle_assembly(args.ref_size)
