@@ -207,7 +207,14 @@ def build_problem(size, world=1, comm=None, workload="elasticity"):
     import jax_fem_b200 as jf
     Lx = float(world)
     hex27 = workload == "hex27"
-    m = (jf.box_mesh_hex27 if hex27 else jf.box_mesh)(size * world, size, size, Lx, 1., 1.)
+    if workload == "simp":
+        # cfg 5: cantilever Lx:Ly:Lz = 2:0.5:1 (applications/outdated/top_opt/box.py:29-30) with size^3 cells per GPU:
+        # 4s x s x 2s cells, s = size (world / 8)^(1/3)
+        s = max(2, int(round(size * (world / 8.0) ** (1.0 / 3.0))))
+        Lx = 2.0
+        m = jf.box_mesh(4 * s, s, 2 * s, 2.0, 0.5, 1.0)
+    else:
+        m = (jf.box_mesh_hex27 if hex27 else jf.box_mesh)(size * world, size, size, Lx, 1., 1.)
     cells = m.cells_dict['hexahedron27' if hex27 else 'hexahedron']
     ele = 'HEX27' if hex27 else 'HEX8'
     left = lambda p: np.isclose(p[0], 0., atol=1e-5)
@@ -302,7 +309,11 @@ def main():
                                       nodes_per_cell=fe.num_nodes)
     if args.workload == "simp":
         # theta = 0.5 + 0.1 U(-1, 1) per cell (default_rng(0) on the GLOBAL cell numbering), constant over a cell's points
-        n_cells_global = args.size ** 3 * world
+        n_cells_global = prob.num_cells if not sharded else int(sharded.part.local_cells.max()) + 1
+        if sharded:
+            t = torch.tensor([n_cells_global], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            n_cells_global = int(t.item())
         theta_g = 0.5 + 0.1 * np.random.default_rng(0).uniform(-1, 1, n_cells_global)
         local_cells = sharded.part.local_cells if sharded else np.arange(n_cells_global)
         prob.internal_vars = [torch.from_numpy(np.repeat(theta_g[local_cells][:, None], fe.num_quads, axis=1)).to(dev)]
@@ -466,6 +477,7 @@ def main():
             c1 = time.perf_counter()
             grad = sharded.adjoint_gradient(u, -f_ext)
             it_adj = sharded.last_info["iterations"]
+            rr_adj = sharded.last_info["rr"]
         else:
             u = jf.solver(prob, {"jax_solver": {"method": "cg"}})[0]
             it_fwd = None
@@ -473,14 +485,14 @@ def main():
             torch.cuda.synchronize()
             c1 = time.perf_counter()
             grad = implicit_vjp(prob, [u], None, [-prob._f_ext], {"jax_solver": {}})
-            it_adj = None
+            it_adj = rr_adj = None
         barrier()
         c2 = time.perf_counter()
         gsum = grad.sum(1)
         log(f"adjoint: J={float(Jloc):.6e}, forward {c1 - c0:.2f}s ({it_fwd} its), adjoint+gradient {c2 - c1:.2f}s ({it_adj} its), "
             f"|dJ/dtheta|_max={float(gsum.abs().max()):.4e}")
         adjoint = {"objective": "compliance int t.u ds", "J": float(Jloc), "forward_seconds": c1 - c0, "forward_iterations": it_fwd,
-                   "adjoint_seconds": c2 - c1, "adjoint_iterations": it_adj, "grad_abs_max": float(gsum.abs().max()),
+                   "adjoint_seconds": c2 - c1, "adjoint_iterations": it_adj, "adjoint_final_rr": rr_adj, "grad_abs_max": float(gsum.abs().max()),
                    "method": "forward Jacobi-CG 1e-10; adjoint A^T lambda = dJ/du by Jacobi-BiCGSTAB 1e-10; gradient -lambda^T dc/dtheta per cell"
                              + (", cells sharded in x-slabs" if sharded else "")}
     clocks = sampler.stop() if rank == 0 else None
@@ -508,8 +520,10 @@ def main():
             "config": {"workload": {"neohookean": "[NON-HEADLINE: Neo-Hookean E=10 nu=0.3] ", "hex27": "[NON-HEADLINE: HEX27, 216-point quadrature] ",
                                     "simp": "[NON-HEADLINE: SIMP Emax=70e3 Emin=70 p=3, theta = 0.5 + 0.1 U(-1,1)] ",
                                     "elasticity": ""}[args.workload] +
-                                   f"HEX8 box {args.size * world}x{args.size}x{args.size} linear elasticity E=70e3 nu=0.3, u=0 on x=0, "
-                                   f"traction on x=Lx (cfg 2{'' if world == 1 else ' extended in x: weak scaling'})",
+                                   (f"HEX8 cantilever 2 x 0.5 x 1 with {prob.num_cells if not sharded else 'size^3 * n_gpus'} cells "
+                                    f"(4s x s x 2s), u=0 on x=0, traction on x=2 (cfg 5)" if args.workload == "simp" else
+                                    f"HEX8 box {args.size * world}x{args.size}x{args.size} linear elasticity E=70e3 nu=0.3, u=0 on x=0, "
+                                    f"traction on x=Lx (cfg 2{'' if world == 1 else ' extended in x: weak scaling'})"),
                        "n_dofs_total": n_total, "n_dofs_per_gpu": n, "nnz_per_gpu": int(nnz * own_frac), "cells_per_gpu": int(prob.num_cells * own_frac),
                        "per_gpu": "whole mesh" if world == 1 else f"x-slab of {args.size}^3 cells + 1 ghost cell layer per interface; "
                                   "assembly needs no communication; SpMV = halo send/recv with <= 2 neighbours; Krylov dots = all-reduce",
