@@ -430,7 +430,7 @@ def main():
         c0 = time.perf_counter()
         if sharded:
             sharded.solve_linear()
-            info = dict(sharded.last_info, err=None)
+            info = dict(sharded.last_info)
         else:
             r0 = jf.apply_bc_vec(prob.newton_update([dofs.reshape(-1, 3)])[0].reshape(-1), dofs, prob)
             A0 = jf.get_A(prob)
@@ -478,6 +478,7 @@ def main():
             grad = sharded.adjoint_gradient(u, -f_ext)
             it_adj = sharded.last_info["iterations"]
             rr_adj = sharded.last_info["rr"]
+            err_adj = sharded.last_info.get("err")
         else:
             u = jf.solver(prob, {"jax_solver": {"method": "cg"}})[0]
             it_fwd = None
@@ -485,14 +486,14 @@ def main():
             torch.cuda.synchronize()
             c1 = time.perf_counter()
             grad = implicit_vjp(prob, [u], None, [-prob._f_ext], {"jax_solver": {}})
-            it_adj = rr_adj = None
+            it_adj = rr_adj = err_adj = None
         barrier()
         c2 = time.perf_counter()
         gsum = grad.sum(1)
         log(f"adjoint: J={float(Jloc):.6e}, forward {c1 - c0:.2f}s ({it_fwd} its), adjoint+gradient {c2 - c1:.2f}s ({it_adj} its), "
             f"|dJ/dtheta|_max={float(gsum.abs().max()):.4e}")
         adjoint = {"objective": "compliance int t.u ds", "J": float(Jloc), "forward_seconds": c1 - c0, "forward_iterations": it_fwd,
-                   "adjoint_seconds": c2 - c1, "adjoint_iterations": it_adj, "adjoint_final_rr": rr_adj, "grad_abs_max": float(gsum.abs().max()),
+                   "adjoint_seconds": c2 - c1, "adjoint_iterations": it_adj, "adjoint_final_rr": rr_adj, "adjoint_true_residual": err_adj, "grad_abs_max": float(gsum.abs().max()),
                    "method": "forward Jacobi-CG 1e-10; adjoint A^T lambda = dJ/du by Jacobi-BiCGSTAB 1e-10; gradient -lambda^T dc/dtheta per cell"
                              + (", cells sharded in x-slabs" if sharded else "")}
     clocks = sampler.stop() if rank == 0 else None

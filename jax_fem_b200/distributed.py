@@ -192,6 +192,24 @@ class Halo:
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def _post_check(A, x, b, part, halo, comm, vec, info):
+    """The reference's check after every linear solve (jax_fem/solver.py:87-89): err = ||A x - b|| over all ranks must
+    be below 0.1 -- reaching maxiter is not an error by itself there, a wrong solution is."""
+    lib = _lib.load()
+    P = _lib.ptr
+    n_owned, n_local = part.n_owned * vec, part.n_local * vec
+    indptr, indices, data = A.getValuesCSR()
+    ax = torch.zeros(n_local, dtype=torch.float64, device=x.device)
+    ws = torch.zeros(lib.fem_krylov_workspace(n_local), dtype=torch.float64, device=x.device)
+    _lib.check(lib.fem_dcg_spmv_dot(n_owned, n_local, P(indptr), P(indices), P(data), A.plan.vec, P(A.plan.brow_ptr),
+                                    P(A.plan.bcol), P(x), P(ax), 0, P(ws), _lib.stream_ptr()))
+    e2 = ((ax[:n_owned] - b.reshape(-1)[:n_owned]) ** 2).sum().reshape(1)
+    comm.allreduce(e2)
+    info['err'] = float(e2.sqrt())
+    assert info['err'] < 0.1, f"distributed linear solver failed to converge with err = {info['err']}"
+    return info
+
+
 def distributed_cg(A, b, x0, part, halo, comm, vec, tol=1e-10, atol=1e-10, maxiter=10000, check_every=25,
                    precond=True):
     """Jacobi-CG on the rank's owned rows; same recurrences / stopping rule as fem_pcg (jax's cg).
@@ -234,7 +252,7 @@ def distributed_cg(A, b, x0, part, halo, comm, vec, tol=1e-10, atol=1e-10, maxit
         it += check_every
         done = bool(ws[7].item() != 0.0)
     halo.update(x)
-    return x, {'iterations': int(ws[6].item()), 'rr': float(ws[4].item())}
+    return x, _post_check(A, x, b, part, halo, comm, vec, {'iterations': int(ws[6].item()), 'rr': float(ws[4].item())})
 
 
 def distributed_bicgstab(A, b, x0, part, halo, comm, vec, tol=1e-10, atol=1e-10, maxiter=10000, precond=True):
@@ -307,7 +325,7 @@ def distributed_bicgstab(A, b, x0, part, halo, comm, vec, tol=1e-10, atol=1e-10,
         bad = torch.stack([omega == 0, alpha == 0, rho_ == 0]).tolist()
         k = -11 if (bad[0] or bad[1]) else (-10 if bad[2] else k + 1)
     halo.update(x)
-    return x, {'iterations': k, 'rr': float(rr_rho[0])}
+    return x, _post_check(A, x, b, part, halo, comm, vec, {'iterations': k, 'rr': float(rr_rho[0])})
 
 
 class ShardedProblem:
