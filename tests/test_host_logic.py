@@ -263,3 +263,23 @@ def test_save_sol_round_trips_through_the_vtu_reader(tmp_path):
     fe2 = FiniteElement(jf.Mesh(q.points, q.cells_dict['quad']), 1, 2, 'QUAD4')
     jf.save_sol(fe2, np.zeros((fe2.num_total_nodes, 1)), str(tmp_path / "q.vtu"))
     assert read_vtu(str(tmp_path / "q.vtu"))[0].shape == (9, 3)
+
+
+def test_header_is_plain_c_and_every_entry_point_cites_the_reference(tmp_path):
+    """The drop-in boundary is a C ABI: include/fem_b200.h must compile as C (no CUDA / C++ / torch types in any
+    signature) and document which reference seam each group of entry points replaces (file:line)."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "fem_b200.h")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "fem_b200.h"\nint main(void) { int (*f)(void) = fem_version; return f == 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.dirname(hdr), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = open(hdr).read()
+    assert not re.search(r"\b(cudaStream_t|torch|at::|std::)\b", re.sub(r"/\*.*?\*/", "", text, flags=re.S))
+    for seam in ("jax_fem/problem.py:439-460", "jax_fem/solver.py:469-553", "jax_fem/solver.py:290-363",
+                 "jax_fem/solver.py:63-92", "jax_fem/solver.py:1386-1394", "jax_fem/fe.py:112-141"):
+        assert seam in text, seam
