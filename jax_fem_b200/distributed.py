@@ -192,17 +192,34 @@ class Halo:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def _post_check(A, x, b, part, halo, comm, vec, info):
+class _LibraryOps:
+    """The rank-local pieces of a Krylov step that touch the matrix: y[owned] = (A x)[owned] by the library's owned-row
+    SpMV (x must have up-to-date ghosts) and the owned diagonal.  The CPU tests substitute a SciPy version to run the
+    distributed recurrences over gloo."""
+
+    def __init__(self, A, part, vec):
+        self.A, self.n_owned, self.n_local = A, part.n_owned * vec, part.n_local * vec
+        self.ws = None
+
+    def matvec(self, x, out):
+        lib, P, A = _lib.load(), _lib.ptr, self.A
+        indptr, indices, data = A.getValuesCSR()
+        if self.ws is None:
+            self.ws = torch.zeros(lib.fem_krylov_workspace(self.n_local), dtype=torch.float64, device=x.device)
+        _lib.check(lib.fem_dcg_spmv_dot(self.n_owned, self.n_local, P(indptr), P(indices), P(data), A.plan.vec,
+                                        P(A.plan.brow_ptr), P(A.plan.bcol), P(x), P(out), 0, P(self.ws), _lib.stream_ptr()))
+        return out
+
+    def diagonal(self):
+        return self.A.diagonal()[:self.n_owned]
+
+
+def _post_check(A, x, b, part, halo, comm, vec, info, ops=None):
     """The reference's check after every linear solve (jax_fem/solver.py:87-89): err = ||A x - b|| over all ranks must
     be below 0.1 -- reaching maxiter is not an error by itself there, a wrong solution is."""
-    lib = _lib.load()
-    P = _lib.ptr
+    ops = ops or _LibraryOps(A, part, vec)
     n_owned, n_local = part.n_owned * vec, part.n_local * vec
-    indptr, indices, data = A.getValuesCSR()
-    ax = torch.zeros(n_local, dtype=torch.float64, device=x.device)
-    ws = torch.zeros(lib.fem_krylov_workspace(n_local), dtype=torch.float64, device=x.device)
-    _lib.check(lib.fem_dcg_spmv_dot(n_owned, n_local, P(indptr), P(indices), P(data), A.plan.vec, P(A.plan.brow_ptr),
-                                    P(A.plan.bcol), P(x), P(ax), 0, P(ws), _lib.stream_ptr()))
+    ax = ops.matvec(x, torch.zeros(n_local, dtype=torch.float64, device=x.device))
     e2 = ((ax[:n_owned] - b.reshape(-1)[:n_owned]) ** 2).sum().reshape(1)
     comm.allreduce(e2)
     info['err'] = float(e2.sqrt())
@@ -255,7 +272,7 @@ def distributed_cg(A, b, x0, part, halo, comm, vec, tol=1e-10, atol=1e-10, maxit
     return x, _post_check(A, x, b, part, halo, comm, vec, {'iterations': int(ws[6].item()), 'rr': float(ws[4].item())})
 
 
-def distributed_bicgstab(A, b, x0, part, halo, comm, vec, tol=1e-10, atol=1e-10, maxiter=10000, precond=True):
+def distributed_bicgstab(A, b, x0, part, halo, comm, vec, tol=1e-10, atol=1e-10, maxiter=10000, precond=True, ops=None):
     """Jacobi-BiCGSTAB on the rank's owned rows with the recurrences, early exit, breakdown codes and stopping rule of
     jax.scipy.sparse.linalg.bicgstab (the reference's default and its adjoint solver, jax_fem/solver.py:78-84,1409):
     stop when ||r||^2 <= max(tol^2 ||b||^2, atol^2).  The matrix may be non-symmetric (A^T of a matrix with Dirichlet
@@ -265,20 +282,15 @@ def distributed_bicgstab(A, b, x0, part, halo, comm, vec, tol=1e-10, atol=1e-10,
 
     A: local CSRMatrix (rows of owned nodes complete); b, x0: flat local vectors (owned first, then ghosts; x0 may be
     None).  Returns (x with up-to-date ghosts, info)."""
-    lib = _lib.load()
-    P = _lib.ptr
+    ops = ops or _LibraryOps(A, part, vec)
     n_owned, n_local = part.n_owned * vec, part.n_local * vec
-    indptr, indices, data = A.getValuesCSR()
     dev = b.device
     own = slice(0, n_owned)
-    ws = torch.zeros(lib.fem_krylov_workspace(n_local), dtype=torch.float64, device=dev)
-    minv = (1.0 / A.diagonal()[own]) if precond else None
+    minv = (1.0 / ops.diagonal()) if precond else None
 
     def matvec(v_local, out):
         halo.update(v_local)
-        _lib.check(lib.fem_dcg_spmv_dot(n_owned, n_local, P(indptr), P(indices), P(data), A.plan.vec, P(A.plan.brow_ptr),
-                                        P(A.plan.bcol), P(v_local), P(out), 0, P(ws), _lib.stream_ptr()))
-        return out
+        return ops.matvec(v_local, out)
 
     def dots(*pairs):
         t = torch.stack([torch.dot(u[own], w[own]) for u, w in pairs])
@@ -325,7 +337,7 @@ def distributed_bicgstab(A, b, x0, part, halo, comm, vec, tol=1e-10, atol=1e-10,
         bad = torch.stack([omega == 0, alpha == 0, rho_ == 0]).tolist()
         k = -11 if (bad[0] or bad[1]) else (-10 if bad[2] else k + 1)
     halo.update(x)
-    return x, _post_check(A, x, b, part, halo, comm, vec, {'iterations': k, 'rr': float(rr_rho[0])})
+    return x, _post_check(A, x, b, part, halo, comm, vec, {'iterations': k, 'rr': float(rr_rho[0])}, ops)
 
 
 class ShardedProblem:
