@@ -283,3 +283,65 @@ def test_header_is_plain_c_and_every_entry_point_cites_the_reference(tmp_path):
     for seam in ("jax_fem/problem.py:439-460", "jax_fem/solver.py:469-553", "jax_fem/solver.py:290-363",
                  "jax_fem/solver.py:63-92", "jax_fem/solver.py:1386-1394", "jax_fem/fe.py:112-141"):
         assert seam in text, seam
+
+
+def test_mma_optimiser_and_filters_match_the_oracle():
+    """jax_fem_b200/mma.py (torch, device-agnostic; here on the CPU) against the oracle's NumPy restatement of
+    jax_fem/mma.py: filter matrix and filters, one sub-problem solve incl. dual variables, and the design after a few
+    iterations of optimize() with the reference's calling convention."""
+    from oracle import mma as omma
+    from jax_fem_b200 import mma
+    m = jf.box_mesh(5, 4, 3, 1.0, 0.8, 0.6)
+    fe = FiniteElement(jf.Mesh(m.points, m.cells_dict['hexahedron']), 3, 3, 'HEX8')
+    H, Hs = mma.compute_filter_kd_tree(fe)
+    oH, oHs = omma.kd_filter(fe.points, fe.cells, fe.get_JxW(), 3)
+    assert np.abs(H.to_dense().numpy() - oH.toarray()).max() < 1e-14 and np.abs(Hs.numpy() - oHs).max() < 1e-14
+    n = fe.num_cells
+    rng = np.random.default_rng(4)
+    rho, dJ, dvc = rng.uniform(0.0005, 1.0, (n, 1)), rng.standard_normal((n, 1)), rng.standard_normal((2, n, 1))
+    ft = {'H': H, 'Hs': Hs}
+    a, b = mma.applySensitivityFilter(ft, rho, dJ, dvc)
+    oa, ob = omma.sensitivity_filter(oH, oHs, rho, dJ, dvc)
+    assert np.abs(a.numpy() - oa).max() < 1e-13 and np.abs(b.numpy() - ob).max() < 1e-13
+    assert np.abs(mma.applyDensityFilter(ft, rho).numpy() - omma.density_filter(oH, oHs, rho)).max() < 1e-14
+
+    # one sub-problem, both Schur branches (m < n and m >= n), third iteration so that the asymptote update is exercised
+    for mm, nn, seed in [(2, 30, 0), (5, 4, 1)]:
+        r = np.random.default_rng(seed)
+        xval, xo1, xo2 = r.uniform(0.3, 0.7, nn), r.uniform(0.3, 0.7, nn), r.uniform(0.3, 0.7, nn)
+        df0, f, df = r.standard_normal(nn), 0.1 * r.standard_normal(mm), r.standard_normal((mm, nn))
+        st = omma.MMAState(xval, np.zeros(nn), np.ones(nn), mm, move=0.2)
+        st.xold1, st.xold2, st.epoch = xo1, xo2, 3
+        st.low, st.upp = xval - 0.4, xval + 0.45
+        ref = omma.mma_step(st, 1.0, df0, f, df)
+        opt = mma.MMA()
+        opt.setNumConstraints(mm); opt.setNumDesignVariables(nn)
+        opt.setMinandMaxBoundsForDesignVariables(np.zeros((nn, 1)), np.ones((nn, 1)))
+        opt.registerMMAIter(xval[:, None], xo1[:, None], xo2[:, None])
+        opt.epoch = 3
+        opt.setLowerAndUpperAsymptotes((xval - 0.4)[:, None], (xval + 0.45)[:, None])
+        opt.setScalingParams(1.0, np.zeros((mm, 1)), 10000 * np.ones((mm, 1)), np.zeros((mm, 1)))
+        opt.setMoveLimit(0.2)
+        opt.setObjectiveWithGradient(1.0, df0[:, None])
+        opt.setConstraintWithGradient(f[:, None], df)
+        opt.mmasub(xval[:, None])
+        x, y, z = opt.getOptimalValues()
+        lam = opt.getLagrangeMultipliers()[0]
+        # both solvers stop when the KKT residual drops below 0.9e-7 (epsimin): the iterates agree to that accuracy
+        assert np.abs(x.numpy()[:, 0] - ref[0]).max() < 1e-7 and np.abs(y.numpy()[:, 0] - ref[1]).max() < 1e-7
+        assert abs(float(z) - ref[2]) < 1e-7 and np.abs(lam.numpy()[:, 0] - ref[3]).max() < 1e-6 * max(1.0, np.abs(ref[3]).max())
+        low, upp = opt.getAsymptoteValues()
+        assert np.array_equal(low.numpy()[:, 0], st.low) and np.array_equal(upp.numpy()[:, 0], st.upp)
+
+    # the loop: compliance-like separable objective with a volume constraint, reference calling convention
+    t = rng.uniform(0.1, 0.95, n)
+    v = 0.4
+    obj_np = lambda r_: (float(((r_[:, 0] - t) ** 2).sum()), 2 * (r_ - t[:, None]))
+    con_np = lambda r_, it: (np.array([r_.mean() / v - 1.0]), np.ones((1, n, 1)) / (n * v))
+    tt = torch.from_numpy(t)
+    obj_t = lambda r_: (((r_[:, 0] - tt) ** 2).sum(), 2 * (r_ - tt[:, None]))
+    con_t = lambda r_, it: (torch.stack([r_.mean() / v - 1.0]), torch.ones((1, n, 1), dtype=torch.float64) / (n * v))
+    params = {'movelimit': 0.2, 'maxIters': 6}
+    out = mma.optimize(fe, np.full((n, 1), v), params, obj_t, con_t, 1)
+    oout = omma.optimize((oH, oHs), np.full((n, 1), v), params, obj_np, con_np, 1)
+    assert out.shape == (n, 1) and np.abs(out.numpy() - oout).max() < 1e-6
