@@ -254,7 +254,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", type=int, default=100)
-    ap.add_argument("--ref-size", type=int, default=50)
+    ap.add_argument("--ref-size", type=int, default=64,
+                    help="edge length of the CPU sample (cells per direction): 64^3 is about 10-20 s of host work")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--solve", action="store_true", help="also time a full Jacobi-CG solve")
