@@ -225,8 +225,30 @@ def newton_step(problem, res_vec, A, dofs, newton_cfg, timing):
     linear_s = _sync_time() - t0
     _timing_record(timing, 'linear', linear_s)
     if newton_cfg.get('line_search_flag', False):
-        raise NotImplementedError("line search is outside the B200 hot path")
+        return line_search(problem, dofs, inc), linear_s
     return dofs + inc, linear_s
+
+
+def line_search(problem, dofs, inc):
+    """Step halving of the reference (solver.py:424-462): alpha = 1, then up to three halvings, each kept only while the
+    norm of the residual with Dirichlet rows keeps decreasing.  Residual-only evaluations (no tangent)."""
+    def res_norm_fn(alpha):
+        d = dofs + alpha * inc
+        res = problem.compute_residual(problem.unflatten_fn_sol_list(d))[0].reshape(-1)
+        return _norm(apply_bc_vec(res, d, problem))
+
+    alpha = 1.
+    res_norm = res_norm_fn(alpha)
+    for i in range(3):
+        alpha *= 0.5
+        res_norm_half = res_norm_fn(alpha)
+        logger.debug("Line search (step halving): i = %d, alpha = %g, res_norm = %g, res_norm_half = %g",
+                     i, alpha, res_norm, res_norm_half)
+        if res_norm_half > res_norm:
+            alpha *= 2.
+            break
+        res_norm = res_norm_half
+    return dofs + alpha * inc
 
 
 def solver(problem, solver_options={}):
@@ -238,8 +260,6 @@ def solver(problem, solver_options={}):
     if unsupported:
         raise NotImplementedError(f"linear back-end(s) {sorted(unsupported)} are outside the B200 hot path: only "
                                   "'jax_solver' (device Jacobi-BiCGSTAB/CG) and 'custom_solver' exist; no fallback")
-    if cfg.get('line_search_flag', False):
-        raise NotImplementedError("line search is outside the B200 hot path")
     logger.info("Solving the nonlinear problem...")
     timing = {'local_assembly': 0., 'global_matrix': 0., 'linear': 0.}
     wall_start = time.perf_counter()

@@ -429,7 +429,25 @@ def jax_solve(A, b, x0, precond=True, method='bicgstab', return_iters=False):
 
 
 # ----------------------------------------------------------------------------
-def solver(problem, tol=1e-6, rel_tol=1e-8, method='bicgstab', initial_guess=None, log=None):
+def line_search(problem, dofs, inc):
+    """Step halving of solver.py:424-462: alpha = 1, then up to three halvings, each kept only while the norm of the
+    residual (with Dirichlet rows) keeps decreasing."""
+    def res_norm(alpha):
+        d = dofs + alpha * inc
+        return np.linalg.norm(apply_bc_vec(problem.compute_residual(d.reshape(-1, problem.vec)).reshape(-1), d, problem))
+    alpha = 1.0
+    norm = res_norm(alpha)
+    for _ in range(3):
+        alpha *= 0.5
+        half = res_norm(alpha)
+        if half > norm:
+            alpha *= 2.0
+            break
+        norm = half
+    return dofs + alpha * inc
+
+
+def solver(problem, tol=1e-6, rel_tol=1e-8, method='bicgstab', initial_guess=None, log=None, line_search_flag=False):
     """Newton loop, solver.py:1285-1356 + newton_step :390-421.  Returns (nodes, vec) solution."""
     n = problem.num_total_dofs_all_vars
     dofs = np.zeros(n) if initial_guess is None else np.asarray(initial_guess, dtype=np.float64).reshape(-1).copy()
@@ -443,7 +461,8 @@ def solver(problem, tol=1e-6, rel_tol=1e-8, method='bicgstab', initial_guess=Non
     hist = [res_val]
     while res_val / res0 > rel_tol and res_val > tol:
         x0 = assign_bc(np.zeros(n), problem) - copy_bc(dofs, problem)     # solver.py:402-409
-        dofs = dofs + jax_solve(A, -res_vec, x0, True, method)
+        inc = jax_solve(A, -res_vec, x0, True, method)
+        dofs = line_search(problem, dofs, inc) if line_search_flag else dofs + inc            # solver.py:416-419
         res_vec, A = helper(dofs)
         res_val = np.linalg.norm(res_vec)
         hist.append(res_val)

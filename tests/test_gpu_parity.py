@@ -652,3 +652,22 @@ def test_topology_optimisation_loop_matches_oracle():
     assert len(history) == 3 and relmax(history, ohist) <= SOL_TOL
     assert history[2] < history[0]                                   # compliance goes down
     assert np.abs(host(rho) - orho).max() <= 1e-6                    # the sub-problem is solved to 1e-7 on both sides
+
+
+def test_newton_line_search_matches_oracle():
+    """solver_options['line_search_flag'] (step halving, jax_fem/solver.py:416-462): same Newton path as the oracle --
+    iteration count and converged state -- on a Neo-Hookean block stretched by 60 % in one load step."""
+    import jax_fem_b200 as jf
+    import gpu_problems as gp
+    m = jf.box_mesh(4, 4, 4, 1., 1., 1.)
+    pts, cells = m.points, m.cells_dict['hexahedron']
+    left = lambda p: np.isclose(p[0], 0., atol=1e-5)
+    right = lambda p: np.isclose(p[0], 1., atol=1e-5)
+    bc = [[left] * 3 + [right] * 3, [0, 1, 2] * 2, [lambda p: 0.] * 3 + [lambda p: 0.6] + [lambda p: 0.3] * 2]
+    prob = gp.HyperElasticity(jf.Mesh(pts, cells), vec=3, dim=3, dirichlet_bc_info=bc)
+    sol = jf.solver(prob, {'line_search_flag': True, 'jax_solver': {}})[0]
+    opb = fem.Problem(fem.Mesh(pts, cells), 3, 3, dirichlet_bc_info=bc, law=olaws.NeoHookean(1e3, 0.3))
+    log = []
+    osol = fem.solver(opb, log=log, line_search_flag=True)
+    assert prob.last_newton_info['iterations'] == len(log) - 1 > 5
+    assert relmax(host(sol), osol) <= SOL_TOL

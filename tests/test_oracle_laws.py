@@ -129,3 +129,20 @@ def test_plane_stress_simp_is_the_topology_optimisation_notebook_law():
     fd = (law.stress(ug, theta + h) - law.stress(ug, theta - h)) / (2 * h)
     assert np.abs(law.dstress_dparam(ug, theta) - fd).max() <= 1e-6 * np.abs(fd).max()
     assert np.abs(laws.SIMP(Emax, Emin, nu, penal).stress(ug, theta) - ref).max() > 1e-3 * np.abs(ref).max()   # plane strain differs
+
+
+def test_newton_with_step_halving_line_search_reaches_the_same_equilibrium():
+    """solver.py:424-462 restated in the oracle: with a 60 % stretch imposed in one step the halving rule is active (more,
+    shorter Newton steps), and the converged state is the one plain Newton finds."""
+    from oracle import fem, laws
+    m = fem.box_mesh(4, 4, 4, 1., 1., 1.)
+    left = lambda p: np.isclose(p[0], 0., atol=1e-5)
+    right = lambda p: np.isclose(p[0], 1., atol=1e-5)
+    bc = [[left] * 3 + [right] * 3, [0, 1, 2] * 2, [lambda p: 0.] * 3 + [lambda p: 0.6] + [lambda p: 0.3] * 2]
+    sols, its = [], []
+    for flag in (False, True):
+        pb = fem.Problem(m, 3, 3, dirichlet_bc_info=bc, law=laws.NeoHookean(1e3, 0.3))
+        log = []
+        sols.append(fem.solver(pb, log=log, line_search_flag=flag))
+        its.append(len(log) - 1)
+    assert its[1] > its[0] and np.abs(sols[0] - sols[1]).max() <= 1e-8 * np.abs(sols[0]).max()
