@@ -268,6 +268,9 @@ def _build(points, cells, nn, vec, brow_ptr, bcol, lens, max_owned, cfg, config)
     ck_rnd = torch.zeros(n_chunks, dtype=torch.int64, device=dev)
     if ln_chunk.numel():
         ck_rnd.scatter_reduce_(0, ln_chunk, ln_rank + 1, reduce='amax')
+    if n_chunks and int(ck_rnd.max()) > cfg.rmax:
+        raise ValueError("a cell lists the same node twice (degenerate connectivity): the fused assembly orders its "
+                         f"accumulation by rounds and allows {cfg.rmax} per chunk")
     ln_desc = cic[lp] | (la << 5) | (own_idx[ln_node] << 8) | (ln_rank << 16)
     slots = torch.searchsorted(gkeys, (ln_node[:, None] * nn + pcn[lp]).reshape(-1)).reshape(-1, N) - brow_ptr[ln_node][:, None]
     ln_slot = _pack_u8(slots)

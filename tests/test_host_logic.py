@@ -345,3 +345,49 @@ def test_mma_optimiser_and_filters_match_the_oracle():
     out = mma.optimize(fe, np.full((n, 1), v), params, obj_t, con_t, 1)
     oout = omma.optimize((oH, oHs), np.full((n, 1), v), params, obj_np, con_np, 1)
     assert out.shape == (n, 1) and np.abs(out.numpy() - oout).max() < 1e-6
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_plans_on_random_connectivity(seed):
+    """Plans only see connectivity: on RANDOM cell -> node tables (no geometric structure at all, valence up to the
+    limits) the CSR pattern must equal the oracle's and the fused-assembly tables, walked in the kernel's order with
+    random element blocks, must reproduce the COO -> CSR sum of those blocks."""
+    import scipy.sparse as sp
+    from jax_fem_b200.patch_plan import CONFIGS, build_patch_plan
+    from patch_emulator import emulate
+    rng = np.random.default_rng(seed)
+    nn, C, v = 60, 45, 3
+    cells = np.stack([np.concatenate([[c % nn], rng.choice(np.delete(np.arange(nn), c % nn), 7, replace=False)])
+                      for c in range(C)])                         # 8 DISTINCT nodes per cell; every low node id is used
+    points = rng.uniform(0, 1, (nn, 3))
+    plan = build_plan(torch.from_numpy(cells), nn, v)
+    indptr, indices = fem.csr_pattern_from_cells(cells, v, v * nn)
+    assert np.array_equal(plan.indptr.numpy(), indptr) and np.array_equal(plan.indices.numpy(), indices)
+    Ke = rng.standard_normal((C, 8, v, 8, v))
+    Re = rng.standard_normal((C, 8, v))
+    dof = (v * cells[:, :, None] + np.arange(v)).reshape(C, -1)
+    I = np.repeat(dof[:, :, None], 8 * v, axis=2).reshape(-1)
+    J = np.repeat(dof[:, None, :], 8 * v, axis=1).reshape(-1)
+    A = sp.coo_matrix((Ke.reshape(-1), (I, J)), shape=(v * nn, v * nn)).tocsr()
+    A.sort_indices()
+    assert np.array_equal(A.indices, indices)
+    flag = np.zeros(v * nn, dtype=np.uint8)
+    flag[rng.choice(v * nn, 11, replace=False)] = 1
+    ref = A.data.copy()
+    for r in np.flatnonzero(flag):
+        seg = slice(indptr[r], indptr[r + 1])
+        ref[seg] = (indices[seg] == r).astype(float)
+    res_ref = np.zeros((nn, v))
+    np.add.at(res_ref, cells.reshape(-1), Re.reshape(-1, v))
+    for config in (0, 1, 4):
+        pp = build_patch_plan(torch.from_numpy(points), torch.from_numpy(cells), nn, v, plan.brow_ptr, plan.bcol, config=config)
+        cfg = CONFIGS[config]
+        assert pp.ck_rnd.max() <= cfg.rmax and np.diff(pp.ck_cell.numpy()).max() <= cfg.chunk
+        data, res = emulate(pp, Ke, Re, flag, None, plan.nnz)
+        assert np.abs(data - ref).max() <= 1e-12 * np.abs(ref).max() and np.abs(res - res_ref).max() <= 1e-12
+    if seed == 0:                                                  # a cell that repeats a node is rejected, not mis-assembled
+        bad = cells.copy()
+        bad[3, 5] = bad[3, 2]
+        bplan = build_plan(torch.from_numpy(bad), nn, v)
+        with pytest.raises(ValueError, match="same node twice"):
+            build_patch_plan(torch.from_numpy(points), torch.from_numpy(bad), nn, v, bplan.brow_ptr, bplan.bcol, config=4)
