@@ -104,6 +104,30 @@ int fem_assemble_fused(int ele_type, int vec, int law_id, const double* law_para
                        const int32_t* ln_desc, const int32_t* ln_slot, const uint8_t* bc_flag,
                        const double* f_ext, double* data, double* res, int config, void* stream);
 
+/* ---- (1)+(2) staged in one kernel: compute_newton_vars (jax_fem/problem.py:447-460) + _PetscTangentCache.update / get_A
+ *      (jax_fem/solver.py:469-553) for HEX8 / vec 3 / isotropic elasticity (linear, SIMP) as work items of ONE persistent
+ *      kernel.  E item i evaluates cells_p[16 i .. 16 i + 16) (the plan's processing order; corder = their cell ids for
+ *      internal_var / Re) and writes the row block of corner (slot, a) to staging row dest_row[8 slot + a] once the G
+ *      item prev_g[8 slot + a] (-1: none) that read the row's previous occupant is done; G item g sums the CSR rows of its
+ *      nodes (the fem_gather_csr work item) once the E items holding the cells around its nodes are done.
+ *      tdesc (n_e + n_gather, 32): one descriptor per ticket, in ticket order: [0] E: 0x80000000 | item, G: item; G only:
+ *      [1] first staging row, [2..5] first corner / entry / source / emeta row, [6..9] their ends, [10] number of E items
+ *      it waits for, [11] -1 or the offset of their list in gdep when they do not fit, [12..31] those E items.
+ *      The staging buffer `stage` (rows of 72 doubles, 128-byte aligned) is a ring that stays in L2 plus a spill area;
+ *      jax_fem_b200/stage_plan.py builds the tables and checks that every wait is on an EARLIER ticket (no deadlock).
+ *      Staging rows hold G = sum_q E_q w_q g_a (x) g_b as 9 tiles [I][J][b]; K = lam' G + mu' G^T + mu' tr(G) I is
+ *      applied after the sum.  ctrl: fem_staged_ctrl_ints(n_e, n_gather) int32 of scratch (zeroed by the call).
+ *      Outputs: data (nnz) CSR values with Dirichlet rows treated (emeta, see fem_gather_csr), Re (n_cells, 24).
+ *      fem_staged_status: *status_host != 0 after a call whose waits exceeded their limit (plan bug; values invalid).  */
+int64_t fem_staged_ctrl_ints(int64_t n_e, int64_t n_gather);
+int fem_assemble_staged(int law_id, const double* law_params_host, const double* points, const double* sol,
+                        const double* internal_var, const double* ref_tables, int64_t n_cells,
+                        const int32_t* cells_p, const int32_t* corder, const int32_t* dest_row,
+                        const int32_t* prev_g, int64_t n_gather, const int32_t* tdesc, const int32_t* gdep,
+                        const int32_t* emeta, const int32_t* src, double* stage,
+                        int32_t* ctrl, double* Re, double* data, void* stream);
+int fem_staged_status(const int32_t* ctrl, int32_t* status_host, void* stream);
+
 /* Plan construction helper (HOST pointers, no CUDA): greedy split of every patch's cells into chunks of <= chunk
  * cells in which no owned node occurs more than rmax times.  cell_ptr (n_patches+1); owned_idx (M, nodes_per_cell):
  * owned-node index of the corner or 255; outputs: chunk of every patch-cell (inside its patch), round of every

@@ -28,6 +28,7 @@ from .fe import FiniteElement, evaluate_point_fn
 from .generate_mesh import Mesh
 from .patch_plan import DEFAULT_CONFIG, build_patch_plan
 from .plan import build_plan
+from .stage_plan import StageConfig, build_stage_plan
 
 
 def _device():
@@ -97,6 +98,8 @@ class Problem:
         self._Ke = None
         self._Re = None
         self._patch_plan = None
+        self._stage_plan = None
+        self._ring = None              # (staging buffer, ctrl, pinned status, event) of the one-kernel staged assembly
         self._A_data = None            # CSR values left by the fused assembly of the last newton_update
         self._A_bc_key = None
         self._last_sol = None
@@ -214,15 +217,79 @@ class Problem:
             sol = torch.as_tensor(np.asarray(sol), dtype=torch.float64)
         return sol.detach().to(device=self.device, dtype=torch.float64).contiguous()
 
-    # ---- fused owner-computes assembly (csrc/fused.cu) ------------------------------------------------------
-    def fused_assembly_enabled(self):
-        """FEM_ASSEMBLY=fused in the environment selects, for HEX8 / vec 3 / isotropic elasticity, the one-kernel
-        owner-computes assembly (element evaluation + CSR rows + Dirichlet rows + residual, no staging buffer).
-        Measured on B200 it is slower than the two-kernel path (3.9 vs 2.9 ms at 100^3), so the
-        two-kernel path stays the default; both are parity-tested."""
+    # ---- assembly modes -------------------------------------------------------------------------------------
+    def assembly_mode(self):
+        """'staged' : element kernel -> HBM staging buffer -> gather kernel (every registered combination; the default);
+           'ring'   : element evaluation + CSR gather as work items of ONE persistent kernel, the element tangents staged
+                      in an L2-resident ring (csrc/staged.cu; HEX8 / vec 3 / isotropic elasticity).  HBM traffic drops from
+                      12.1 to 3.4 GB per assembly at 100^3 (ncu), but the kernel is latency-bound and measures 3.4 ms
+                      against 2.45 ms for 'staged' (profiles/r02_ring_assembly.md), so it is opt-in;
+           'fused'  : owner-computes patches (csrc/fused.cu; measured slower).
+        FEM_ASSEMBLY in the environment selects the mode; every mode is parity-tested."""
         import os
-        return (os.environ.get('FEM_ASSEMBLY', 'staged') == 'fused' and self.ele_type == 'HEX8' and self.fes[0].vec == 3
-                and self._law.law_id in (laws.LinearElasticity.law_id, laws.SIMP.law_id))
+        eligible = (self.ele_type == 'HEX8' and self.fes[0].vec == 3
+                    and self._law.law_id in (laws.LinearElasticity.law_id, laws.SIMP.law_id))
+        mode = os.environ.get('FEM_ASSEMBLY', 'staged')
+        if mode not in ('ring', 'staged', 'fused'):
+            raise ValueError(f"FEM_ASSEMBLY={mode!r}: registered modes are 'ring', 'staged', 'fused'")
+        return mode if eligible else 'staged'
+
+    def fused_assembly_enabled(self):
+        return self.assembly_mode() == 'fused'
+
+    @property
+    def stage_plan(self):
+        if self._stage_plan is None:
+            import os
+            cfg = StageConfig()
+            for name in ('ring_bytes', 'tile_cells', 'slack', 'margin', 'in_flight'):
+                v = os.environ.get('FEM_RING_' + name.upper())
+                if v is not None:
+                    setattr(cfg, name, int(v))
+            self._stage_plan = build_stage_plan(self.plan, self._cells, self._points, cfg)
+        return self._stage_plan
+
+    def _run_ring(self, sol):
+        fe, p, sp = self.fes[0], self.plan, self.stage_plan
+        lib, P = _lib.load(), _lib.ptr
+        dev = self.device
+        if self._ring is None:
+            stage = torch.empty(sp.n_rows * 72, dtype=torch.float64, device=dev)
+            ctrl = torch.zeros(lib.fem_staged_ctrl_ints(sp.n_e, sp.n_g), dtype=torch.int32, device=dev)
+            self._ring = (stage, ctrl, torch.zeros(1, dtype=torch.int32).pin_memory(), torch.cuda.Event())
+        stage, ctrl, status, event = self._ring
+        self.check_assembly_status(block=False)
+        if self._Re is None:
+            self._Re = torch.empty((self.num_cells, fe.num_nodes * fe.vec), dtype=torch.float64, device=dev)
+        iv = self._internal_var()
+        emeta = self.entry_meta()
+        data = torch.empty(p.nnz, dtype=torch.float64, device=dev)
+        _lib.check(lib.fem_assemble_staged(
+            self._law.law_id, _lib.host_doubles(self._law.params()), P(self._points), P(sol), P(iv), P(self._ref),
+            self.num_cells, P(sp.cells_p), P(sp.corder), P(sp.dest_row), P(sp.prev_g), sp.n_g, P(sp.tdesc), P(sp.gdep),
+            P(emeta), P(p.src), P(stage), P(ctrl), P(self._Re), P(data), _lib.stream_ptr()))
+        status.copy_(ctrl[3:4], non_blocking=True)
+        event.record()
+        self._ring_pending = True
+        res = torch.empty((fe.num_total_nodes, fe.vec), dtype=torch.float64, device=dev)
+        _lib.check(lib.fem_gather_residual(fe.vec, fe.num_nodes, fe.num_total_nodes, P(p.nc_ptr), P(p.nc),
+                                           P(self._Re), P(self._f_ext), P(res), _lib.stream_ptr()))
+        self._A_data, self._A_bc_key = data, self._bc_cache[0]
+        return res
+
+    def check_assembly_status(self, block=True):
+        """Raise if a wait of the last one-kernel assembly exceeded its limit (a schedule bug: the values are invalid).
+        Non-blocking calls only look at a status copy that has already arrived."""
+        if self._ring is None or not getattr(self, '_ring_pending', False):
+            return
+        _, _, status, event = self._ring
+        if block:
+            event.synchronize()
+        elif not event.query():
+            return
+        self._ring_pending = False
+        if int(status[0]) != 0:
+            raise RuntimeError("staged assembly: a dependency wait timed out (schedule bug); results are invalid")
 
     @property
     def patch_plan(self):
@@ -299,9 +366,10 @@ class Problem:
         sol = self._as_sol(sol_list)
         self._last_sol = sol
         self._A_data = None
-        if self.fused_assembly_enabled():
+        mode = self.assembly_mode()
+        if mode != 'staged':
             self._Ke_valid = False
-            return [self._run_fused(sol)]
+            return [self._run_fused(sol) if mode == 'fused' else self._run_ring(sol)]
         self._Ke_valid = True
         return [self._run_element_kernel(sol, jac=True)]
 

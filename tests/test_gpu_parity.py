@@ -364,11 +364,12 @@ print('RELMAX', np.abs(K - Ko).max() / np.abs(Ko).max())
 def _assemble_both_ways(prob, sol, monkeypatch):
     import jax_fem_b200 as jf
     out = {}
-    for mode in ("fused", "staged"):
+    for mode in ("fused", "staged", "ring"):
         monkeypatch.setenv("FEM_ASSEMBLY", mode)
-        assert prob.fused_assembly_enabled() == (mode == "fused")
+        assert prob.assembly_mode() == mode and prob.fused_assembly_enabled() == (mode == "fused")
         res = prob.newton_update([torch.from_numpy(sol).cuda()])[0]
         A = jf.get_A(prob)
+        prob.check_assembly_status()
         out[mode] = (host(res), host(A.data))
     return out
 
@@ -412,11 +413,12 @@ def test_fused_assembly_matches_oracle_and_staged_path(case, config, monkeypatch
     f_ext = host(prob._f_ext) if prob._f_ext is not None else 0.0
     opb.newton_update(sol)
     oA = fem.get_A(opb)
-    for mode in ("fused", "staged"):
+    for mode in ("fused", "staged", "ring"):
         res, data = out[mode]
         assert relmax(data, oA.data) <= VAL_TOL, mode
         assert relmax(res, ores + f_ext) <= VAL_TOL, mode
     assert relmax(out["fused"][1], out["staged"][1]) <= 1e-13      # same blocks, different (fixed) summation order
+    assert relmax(out["ring"][1], out["staged"][1]) <= 1e-13       # isotropic map applied after the sum instead of before
     # Dirichlet rows are exact unit rows in both
     rows = host(prob.bc_data()[0])
     indptr, indices = host(prob.plan.indptr), host(prob.plan.indices)
@@ -439,6 +441,40 @@ def test_fused_assembly_rejects_unregistered_combination():
     code = lib.fem_assemble_fused(0, 3, 2, _lib.host_doubles([1., .3]), P(z), P(z), None, P(z), 1, *([P(zi)] * 14),
                                   P(zi), None, P(z), P(z), 1, None)
     assert code == -1 and b"fused assembly is registered" in lib.fem_last_error()
+
+
+@pytest.mark.parametrize("ring_kb,tile,slack,margin", [(400, 64, 2, 8), (150, 10 ** 9, 0, 0), (4000, 200, 16, 64)])
+def test_ring_assembly_recycles_rows_correctly(ring_kb, tile, slack, margin, monkeypatch):
+    """The one-kernel staged assembly with a ring far smaller than the element tangents (rows recycled many times, strip
+    edges spilled) on a 24 x 12 x 10 non-affine box: CSR values and residual equal the two-kernel path bit for bit in the
+    pattern and to 1e-13 in the values, every run gives the same bits, and no wait times out."""
+    import jax_fem_b200 as jf
+    import gpu_problems as gp
+    m = jf.box_mesh(24, 12, 10, 2.4, 1.2, 1.0)
+    rng = np.random.default_rng(3)
+    pts = m.points + 0.015 * rng.uniform(-1, 1, m.points.shape)
+    cells = m.cells_dict['hexahedron']
+    bc = [[lambda p: p[0] < 0.03] * 3, [0, 1, 2], [lambda p: 0., lambda p: 0.01, lambda p: -0.01]]
+    sol = torch.from_numpy(0.01 * rng.standard_normal((len(pts), 3))).cuda()
+    for k, v in (("RING_BYTES", ring_kb * 1024), ("TILE_CELLS", tile), ("SLACK", slack), ("MARGIN", margin), ("IN_FLIGHT", 0)):
+        monkeypatch.setenv("FEM_RING_" + k, str(v))
+    monkeypatch.setenv("FEM_ASSEMBLY", "staged")
+    ref = gp.PlainElasticity(jf.Mesh(pts, cells), vec=3, dim=3, dirichlet_bc_info=bc)
+    res0 = ref.newton_update([sol])[0]
+    data0 = jf.get_A(ref).data
+    monkeypatch.setenv("FEM_ASSEMBLY", "ring")
+    prob = gp.PlainElasticity(jf.Mesh(pts, cells), vec=3, dim=3, dirichlet_bc_info=bc)
+    sp = prob.stage_plan
+    if ring_kb == 400:
+        assert sp.ring_rows > 0 and int(sp.prev_g.max()) >= 0 and 0 < sp.spill_fraction < 1
+    res = prob.newton_update([sol])[0]
+    data = jf.get_A(prob).data.clone()
+    prob.check_assembly_status()
+    assert relmax(host(data), host(data0)) <= 1e-13 and relmax(host(res), host(res0)) <= 1e-13
+    for _ in range(5):
+        prob.newton_update([sol])
+        assert torch.equal(jf.get_A(prob).data, data)
+    prob.check_assembly_status()
 
 
 # ---- full-size (BASELINE.json configs[1]) checks through size-independent properties -------------------------------
@@ -482,11 +518,24 @@ def test_full_size_cfg2_properties(monkeypatch):
     res_f = free.newton_update([u])[0]
     assert float((jf.get_A(free).data - data0).abs().max()) <= 1e-13 * scale
     assert float((res_f - res_u).abs().max()) <= 1e-12 * float(res_u.abs().max())
-    del free, A, data0
+    # the default: one persistent kernel, element tangents staged in the L2-resident ring (csrc/staged.cu)
+    monkeypatch.setenv("FEM_ASSEMBLY", "ring")
+    res_r = free.newton_update([u])[0]
+    data_r = jf.get_A(free).data.clone()
+    free.check_assembly_status()
+    assert free.stage_plan.ring_rows > 0 and free.stage_plan.spill_fraction < 0.2
+    assert free.stage_plan.staging_bytes < 0.2 * 8 * 72 * 8 * len(cells)            # no full-size element-tangent buffer
+    assert float((data_r - data0).abs().max()) <= 1e-13 * scale
+    assert float((res_r - res_u).abs().max()) <= 1e-12 * float(res_u.abs().max())
+    for _ in range(3):                                                              # bit-reproducible under any schedule
+        free.newton_update([u])
+        assert torch.equal(jf.get_A(free).data, data_r)
+    free.check_assembly_status()
+    del free, A, data0, data_r
     torch.cuda.empty_cache()
 
-    # cfg 2 proper: u = 0 on x = 0, traction on x = 1, Jacobi-CG to 1e-10
-    monkeypatch.setenv("FEM_ASSEMBLY", "staged")
+    # cfg 2 proper: u = 0 on x = 0, traction on x = 1, Jacobi-CG to 1e-10 (default assembly mode)
+    monkeypatch.delenv("FEM_ASSEMBLY")
     left = lambda p: np.isclose(p[0], 0., atol=1e-5)
     right = lambda p: np.isclose(p[0], 1., atol=1e-5)
     cls = type("Cfg2", (jf.Problem,), {"get_tensor_map": lambda self: jf.laws.LinearElasticity(70e3, 0.3),
@@ -571,7 +620,7 @@ def test_quad4_elasticity_and_plane_stress_simp_match_oracle(law_name):
         laws.resolve(laws.LinearElasticity(1., .3, plane_stress=True), 'HEX8', 3)
 
 
-@pytest.mark.parametrize("mode", ["staged", "fused"])
+@pytest.mark.parametrize("mode", ["staged", "fused", "ring"])
 def test_assembly_on_randomly_renumbered_mesh(mode, monkeypatch):
     """Generality of the plans: a non-affine box whose nodes and cells are randomly renumbered (no tensor-grid structure in
     the numbering, scattered CSR rows, bin-based patches) must assemble to the oracle's operator in both assembly modes."""
