@@ -3,11 +3,14 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--size S] [--impl reference]
 
-Workload (BASELINE.json configs[1]): box_mesh(S,S,S) HEX8, linear elasticity E=70e3 nu=0.3,
-u=0 on x=0, traction on x=1; default S=100 (3,090,903 DOF, nnz 245,438,109).  A "step" is one full
-residual+Jacobian assembly: element kernels -> deterministic gather into CSR with Dirichlet rows treated
--> residual with apply_bc_vec.  `value` = DOFs/s with inputs resident in HBM; `e2e` = the same step through
-the public API from pinned host memory (solution H2D, residual D2H inside the timed region).
+Workload (BASELINE.json north_star target): box_mesh(S,S,S) HEX8, linear elasticity E=70e3 nu=0.3,
+u=0 on x=0, traction on x=1; default S=200 (24,361,803 DOF, nnz 1,953,736,209: the >= 24M-DOF mesh of the north star,
+cfg 2's problem at cfg 3's size).  The mesh is FIXED: with --gpus N its cells are sharded in x-slabs over the N ranks
+("scaling": "strong").  A "step" is one full residual+Jacobian assembly: element kernels -> deterministic gather into CSR
+with Dirichlet rows treated -> residual with apply_bc_vec.  `value` = DOFs/s with inputs resident in HBM; `e2e` = the
+same step through the public API from pinned host memory (solution H2D, residual D2H inside the timed region).  Every
+run also times the SpMV and a full Jacobi-CG solve (`cg_solve`: iterations, ms per iteration, true residual) and, on one
+GPU, cfg 2 itself (100^3, `cfg2_100cube`).
 
 One JSON line on stdout (rank 0).  --impl reference times the CPU oracle (NumPy/SciPy port of the reference's
 algorithm; the reference itself needs jax/basix/petsc4py which are not installable here) on the host cores.
@@ -202,19 +205,18 @@ def problem_class(workload="elasticity"):
 
 
 def build_problem(size, world=1, comm=None, workload="elasticity"):
-    """cfg 2 on one GPU; for N GPUs the box is N times longer in x (weak scaling: size^3 cells per rank) and its
-    cells are sharded in x-slabs with one ghost layer (jax_fem_b200/distributed.py).  Returns (problem, sharded)."""
+    """The fixed size^3 box (cfg 5: the 4s x s x 2s cantilever) on one GPU, or its cells sharded in x-slabs with one ghost
+    layer over `world` ranks (jax_fem_b200/distributed.py) -- strong scaling.  Returns (problem, sharded)."""
     import jax_fem_b200 as jf
-    Lx = float(world)
+    Lx = 1.0
     hex27 = workload == "hex27"
     if workload == "simp":
-        # cfg 5: cantilever Lx:Ly:Lz = 2:0.5:1 (applications/outdated/top_opt/box.py:29-30) with size^3 cells per GPU:
-        # 4s x s x 2s cells, s = size (world / 8)^(1/3)
-        s = max(2, int(round(size * (world / 8.0) ** (1.0 / 3.0))))
+        # cfg 5: cantilever Lx:Ly:Lz = 2:0.5:1 (applications/outdated/top_opt/box.py:29-30): 4s x s x 2s cells, s = size / 2
+        s = max(2, size // 2)
         Lx = 2.0
         m = jf.box_mesh(4 * s, s, 2 * s, 2.0, 0.5, 1.0)
     else:
-        m = (jf.box_mesh_hex27 if hex27 else jf.box_mesh)(size * world, size, size, Lx, 1., 1.)
+        m = (jf.box_mesh_hex27 if hex27 else jf.box_mesh)(size, size, size, Lx, 1., 1.)
     cells = m.cells_dict['hexahedron27' if hex27 else 'hexahedron']
     ele = 'HEX27' if hex27 else 'HEX8'
     left = lambda p: np.isclose(p[0], 0., atol=1e-5)
@@ -235,16 +237,36 @@ def build_problem(size, world=1, comm=None, workload="elasticity"):
     return sp.problem, sp
 
 
+def time_assembly(prob, sol, steps, jf, torch, barrier):
+    """(ms per step, element ms, bc ms, gather ms) of `steps` assemblies, CUDA events on the current stream."""
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    barrier()
+    for k in range(steps):
+        ev[k][0].record()
+        res = prob.newton_update([sol])[0]
+        ev[k][1].record()
+        jf.apply_bc_vec(res.reshape(-1), sol.reshape(-1), prob)
+        ev[k][2].record()
+        jf.get_A(prob)
+        ev[k][3].record()
+    barrier()
+    t = [sum(e[i].elapsed_time(e[i + 1]) for e in ev) / steps for i in range(3)]
+    return ev[0][0].elapsed_time(ev[-1][3]) / steps, t[0], t[1], t[2]
+
+
 def measured_traffic(args, world):
-    """DRAM bytes per assembly step from the committed ncu capture (profiles/r01_traffic.json): only valid for the
-    workload and size it was captured on; None otherwise."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
+    """DRAM bytes per assembly step from the committed ncu capture of this code (profiles/r02_traffic.json, written by
+    tools/ncu_traffic.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`): only valid for the workload, size
+    and assembly mode it was captured on; None otherwise (a bench run cannot host ncu itself)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_traffic.json")
     try:
         t = json.load(open(path))
     except (OSError, ValueError):
         return None
-    if t.get("workload") == args.workload and t.get("size") == args.size and world == 1:
-        return t["assembly_bytes_per_step"]
+    for entry in t.get("captures", []):
+        if (entry.get("workload") == args.workload and entry.get("size") == args.size and world == 1
+                and entry.get("mode") == os.environ.get("FEM_ASSEMBLY", "staged")):
+            return entry["assembly_bytes_per_step"]
     return None
 
 
@@ -253,12 +275,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--size", type=int, default=100)
+    ap.add_argument("--size", type=int, default=200, help="cells per direction of the FIXED mesh (200: the north star's 24M-DOF mesh)")
+    ap.add_argument("--cfg2-size", type=int, default=100, help="edge of the cfg 2 sub-run on one GPU (0 = skip)")
+    ap.add_argument("--no-solve", action="store_true", help="skip the Jacobi-CG solve (it is part of every default run)")
     ap.add_argument("--ref-size", type=int, default=64,
                     help="edge length of the CPU sample (cells per direction): 64^3 is about 10-20 s of host work")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--solve", action="store_true", help="also time a full Jacobi-CG solve")
     ap.add_argument("--newton", action="store_true",
                     help="also time the full Newton solve with per-iteration re-assembly (cfg 3 with --workload neohookean)")
     ap.add_argument("--adjoint", action="store_true",
@@ -294,11 +317,11 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     t0 = time.perf_counter()
-    log(f"building problem {args.size}^3 per GPU, {world} GPU(s)")
+    log(f"building problem {args.size}^3 (fixed mesh), {world} GPU(s)")
     comm = None
     if world > 1:
-        from jax_fem_b200.distributed import TorchDistComm
-        comm = TorchDistComm()
+        from jax_fem_b200.distributed import NcclComm
+        comm = NcclComm()                        # the library's own NCCL communicator (csrc/dist.cu)
     prob, sharded = build_problem(args.size, world, comm, args.workload)
     setup_s = time.perf_counter() - t0
     fe = prob.fes[0]
@@ -306,6 +329,7 @@ def main():
     n = sharded.n_owned if sharded else n_local               # dofs this rank owns (what it is credited for)
     log(f"problem built in {setup_s:.1f}s: {n} owned dofs (+{n_local - n} ghost), local nnz {prob.plan.nnz}")
     own_frac = n / n_local
+    cells_per_gpu = int(prob.num_cells * own_frac)
     b_asm, b_spmv = algorithmic_bytes(n, int(nnz * own_frac), int(prob.num_cells * own_frac), int(fe.num_total_nodes * own_frac),
                                       nodes_per_cell=fe.num_nodes)
     if args.workload == "simp":
@@ -318,8 +342,11 @@ def main():
         theta_g = 0.5 + 0.1 * np.random.default_rng(0).uniform(-1, 1, n_cells_global)
         local_cells = sharded.part.local_cells if sharded else np.arange(n_cells_global)
         prob.internal_vars = [torch.from_numpy(np.repeat(theta_g[local_cells][:, None], fe.num_quads, axis=1)).to(dev)]
-    rng = np.random.default_rng(rank)
-    sol_host = torch.from_numpy(1e-3 * rng.standard_normal((fe.num_total_nodes, 3))).pin_memory()
+    # the same global field on every partition (seeded on the global node numbering)
+    n_nodes_global = fe.num_total_nodes if not sharded else int(sharded.part.node_ranges[-1])
+    sol_global = 1e-3 * np.random.default_rng(0).standard_normal((n_nodes_global, 3))
+    sol_host = torch.from_numpy(sol_global[sharded.part.l2g] if sharded else sol_global).pin_memory()
+    del sol_global
     sol = sol_host.to(dev)
     res_host = torch.empty(n_local, dtype=torch.float64).pin_memory()
 
@@ -343,22 +370,8 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
-    barrier()
-    for k in range(args.steps):
-        ev[k][0].record()
-        res = prob.newton_update([sol])[0]
-        ev[k][1].record()
-        res_vec = jf.apply_bc_vec(res.reshape(-1), sol.reshape(-1), prob)
-        ev[k][2].record()
-        A = jf.get_A(prob)
-        ev[k][3].record()
-    barrier()
-    t_elem = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
-    t_bc = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
-    t_gather = sum(e[2].elapsed_time(e[3]) for e in ev) / args.steps
-    t_total_ms = ev[0][0].elapsed_time(ev[-1][3])
-    ms_step = t_total_ms / args.steps
+    ms_step, t_elem, t_bc, t_gather = time_assembly(prob, sol, args.steps, jf, torch, barrier)
+    res_vec, A = step(sol)
 
     # ---- e2e: public API from pinned host buffers -------------------------------------------------------
     # Every step copies its input from pinned host memory and its result (the residual with Dirichlet rows) back.
@@ -393,6 +406,7 @@ def main():
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1) / args.steps
+    del sol_bufs
     log(f"assembly {ms_step:.3f} ms/step (element {t_elem:.3f}, bc {t_bc:.3f}, gather {t_gather:.3f}); e2e {e2e_ms:.3f} ms")
 
     # ---- SpMV (the CG kernel) on the assembled matrix; with N > 1 it includes the halo exchange of x ---------
@@ -405,7 +419,6 @@ def main():
     def spmv():
         if sharded:
             sharded.halo.update(x)
-        if sharded:
             _lib.check(lib.fem_dcg_spmv_dot(n, n_local, _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(data), 3,
                                             _lib.ptr(prob.plan.brow_ptr), _lib.ptr(prob.plan.bcol), _lib.ptr(x), _lib.ptr(y),
                                             0, _lib.ptr(ws), _lib.stream_ptr()))
@@ -422,29 +435,48 @@ def main():
     s1.record()
     barrier()
     spmv_ms = s0.elapsed_time(s1) / reps
+    del x, y, ws
     log(f"spmv {spmv_ms:.3f} ms = {b_spmv / spmv_ms / 1e6:.0f} GB/s per GPU")
 
+    # ---- the Jacobi-CG solve of the linear problem (tol = atol = 1e-10), every run ------------------------------------
     solve = None
-    if args.solve:
+    if not args.no_solve and args.workload in ("elasticity", "simp"):
         dofs = torch.zeros(n_local, dtype=torch.float64, device=dev)
-        barrier()
-        c0 = time.perf_counter()
+        r0 = jf.apply_bc_vec(prob.newton_update([dofs.reshape(-1, 3)])[0].reshape(-1), dofs, prob)
+        A0 = jf.get_A(prob)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if sharded:
-            sharded.solve_linear()
-            info = dict(sharded.last_info)
+            from jax_fem_b200.distributed import distributed_cg
+            run_cg = lambda **kw: distributed_cg(A0, -r0, torch.zeros_like(dofs), sharded.part, sharded.halo, comm, 3, **kw)
         else:
-            r0 = jf.apply_bc_vec(prob.newton_update([dofs.reshape(-1, 3)])[0].reshape(-1), dofs, prob)
-            A0 = jf.get_A(prob)
-            torch.cuda.synchronize()
-            c0 = time.perf_counter()
-            _, info = jax_solve(A0, -r0, torch.zeros_like(dofs), True, method='cg', return_info=True)
+            run_cg = lambda **kw: jax_solve(A0, -r0, torch.zeros_like(dofs), True, method='cg', return_info=True, **kw)
+        try:
+            run_cg(maxiter=5)                         # warm-up: workspace, occupancy queries, NCCL channels of the all-reduce
+        except AssertionError:
+            pass                                      # 5 iterations do not meet the reference's err < 0.1 post-check
         barrier()
-        cs = time.perf_counter() - c0
-        log(f"cg: {info}, {cs:.2f}s")
-        solve = {"method": "jacobi-cg" + (" (sharded: halo + 2 all-reduces per iteration; time includes one assembly)" if sharded else ""),
-                 "iterations": info['iterations'], "seconds": cs, "err": info.get('err'),
-                 "ms_per_iteration": 1e3 * cs / max(info['iterations'], 1),
-                 "effective_spmv_gbs": world * b_spmv / (cs / max(info['iterations'], 1)) / 1e9}
+        w0 = time.perf_counter()
+        c0.record()
+        xs, info = run_cg()
+        c1.record()
+        barrier()
+        cs_wall = time.perf_counter() - w0
+        t_cg = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
+        chk = torch.stack([xs[:n].abs().sum(), (xs[:n] ** 2).sum()])
+        if world > 1:
+            dist.all_reduce(t_cg, op=dist.ReduceOp.MAX)
+            dist.all_reduce(chk, op=dist.ReduceOp.SUM)
+        cg_ms = float(t_cg.item())
+        its = max(int(info['iterations']), 1)
+        log(f"cg: {info}, {cg_ms / 1e3:.2f}s device time ({cs_wall:.2f}s wall)")
+        solve = {"method": "Jacobi-CG, tol = atol = 1e-10" + (", whole loop in the library: 1 halo exchange (ncclSend/ncclRecv) + 2 "
+                 "all-reduces per iteration" if sharded else ", device-resident scalars"),
+                 "iterations": int(info['iterations']), "seconds": cg_ms / 1e3, "ms_per_iteration": cg_ms / its,
+                 "err": info.get('err'), "final_rr": info.get('rr'),
+                 "solution_l1": float(chk[0]), "solution_l2": float(chk[1].sqrt()),
+                 "halo_bytes_per_rank_per_exchange": sharded.halo.bytes_per_exchange if sharded else 0,
+                 "effective_spmv_gbs": world * b_spmv / (cg_ms * 1e-3 / its) / 1e9}
+        del A0, r0, xs, dofs
     newton = None
     if args.newton:
         barrier()
@@ -480,6 +512,13 @@ def main():
             it_adj = sharded.last_info["iterations"]
             rr_adj = sharded.last_info["rr"]
             err_adj = sharded.last_info.get("err")
+            # compliance is self-adjoint: lambda = u on the free rows -- a check that needs no second solve
+            lam, rows = sharded.last_lambda, prob.bc_data()[0].long()
+            d = (lam - u.reshape(-1))
+            d[rows] = 0.
+            sa = torch.stack([(d[:n] ** 2).sum(), (u.reshape(-1)[:n] ** 2).sum()])
+            comm.allreduce(sa)
+            self_adj = float((sa[0] / sa[1]).sqrt())
         else:
             u = jf.solver(prob, {"jax_solver": {"method": "cg"}})[0]
             it_fwd = None
@@ -487,18 +526,40 @@ def main():
             torch.cuda.synchronize()
             c1 = time.perf_counter()
             grad = implicit_vjp(prob, [u], None, [-prob._f_ext], {"jax_solver": {}})
-            it_adj = rr_adj = err_adj = None
+            it_adj = rr_adj = err_adj = self_adj = None
         barrier()
         c2 = time.perf_counter()
         gsum = grad.sum(1)
+        gl = torch.stack([gsum.abs().sum(), (gsum ** 2).sum()])
         log(f"adjoint: J={float(Jloc):.6e}, forward {c1 - c0:.2f}s ({it_fwd} its), adjoint+gradient {c2 - c1:.2f}s ({it_adj} its), "
-            f"|dJ/dtheta|_max={float(gsum.abs().max()):.4e}")
+            f"|dJ/dtheta|_max={float(gsum.abs().max()):.4e}, ||lambda - u|| / ||u|| = {self_adj}")
         adjoint = {"objective": "compliance int t.u ds", "J": float(Jloc), "forward_seconds": c1 - c0, "forward_iterations": it_fwd,
-                   "adjoint_seconds": c2 - c1, "adjoint_iterations": it_adj, "adjoint_final_rr": rr_adj, "adjoint_true_residual": err_adj, "grad_abs_max": float(gsum.abs().max()),
+                   "adjoint_seconds": c2 - c1, "adjoint_iterations": it_adj, "adjoint_final_rr": rr_adj, "adjoint_true_residual": err_adj,
+                   "self_adjoint_check_rel": self_adj, "grad_abs_max": float(gsum.abs().max()),
+                   "grad_l1_local_rank0": float(gl[0]), "grad_l2_local_rank0": float(gl[1].sqrt()),
                    "method": "forward Jacobi-CG 1e-10; adjoint A^T lambda = dJ/du by Jacobi-BiCGSTAB 1e-10; gradient -lambda^T dc/dtheta per cell"
-                             + (", cells sharded in x-slabs" if sharded else "")}
+                             + (", cells sharded in x-slabs, whole Krylov loops in the library" if sharded else "")}
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- cfg 2 itself (BASELINE.json configs[1], 100^3) on one GPU, for continuity with round 1 --------------------------
+    cfg2 = None
+    if world == 1 and args.cfg2_size and args.cfg2_size != args.size and args.workload == "elasticity":
+        del A, res_vec, res, sol, prob
+        torch.cuda.empty_cache()
+        p2, _ = build_problem(args.cfg2_size)
+        f2 = p2.fes[0]
+        s2 = torch.from_numpy(1e-3 * np.random.default_rng(0).standard_normal((f2.num_total_nodes, 3))).to(dev)
+        for _ in range(args.warmup):
+            p2.newton_update([s2])
+            jf.get_A(p2)
+        ms2, te2, tb2, tg2 = time_assembly(p2, s2, args.steps, jf, torch, barrier)
+        ba2, _ = algorithmic_bytes(p2.num_total_dofs_all_vars, p2.plan.nnz, p2.num_cells, f2.num_total_nodes)
+        peaks2, _ = measured_peaks()
+        cfg2 = {"workload": f"HEX8 box {args.cfg2_size}^3 linear elasticity (cfg 2)", "n_dofs": p2.num_total_dofs_all_vars,
+                "ms_per_step": ms2, "value": p2.num_total_dofs_all_vars / (ms2 * 1e-3), "unit": "DOF/s",
+                "kernels_ms": {"element_kernel+gather_residual": te2, "apply_bc_vec": tb2, "gather_csr": tg2},
+                "roofline_frac": ba2 / ((te2 + tb2 + tg2) * 1e-3) / 1e9 / float(peaks2["hbm_gbs"])}
+        log(f"cfg 2 ({args.cfg2_size}^3): {ms2:.3f} ms/step")
     # max over ranks (device times)
     t = torch.tensor([ms_step, e2e_ms, spmv_ms, t_elem, t_gather, t_bc], dtype=torch.float64, device=dev)
     n_total = torch.tensor([float(n)], dtype=torch.float64, device=dev)
@@ -515,33 +576,38 @@ def main():
         asm_kernel_ms = t_elem + t_gather + t_bc
         achieved = b_asm / (asm_kernel_ms * 1e-3) / 1e9
         spmv_gbs = b_spmv / (spmv_ms * 1e-3) / 1e9
+        mode = os.environ.get("FEM_ASSEMBLY", "staged")
+        nx = "4s x s x 2s" if args.workload == "simp" else f"{args.size}x{args.size}x{args.size}"
         line = {
             "metric": "assembled DOFs/s (residual+Jacobian), HEX8 linear elasticity", "value": value, "unit": "DOF/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": {"neohookean": "[NON-HEADLINE: Neo-Hookean E=10 nu=0.3] ", "hex27": "[NON-HEADLINE: HEX27, 216-point quadrature] ",
                                     "simp": "[NON-HEADLINE: SIMP Emax=70e3 Emin=70 p=3, theta = 0.5 + 0.1 U(-1,1)] ",
                                     "elasticity": ""}[args.workload] +
-                                   (f"HEX8 cantilever 2 x 0.5 x 1 with {prob.num_cells if not sharded else 'size^3 * n_gpus'} cells "
-                                    f"(4s x s x 2s), u=0 on x=0, traction on x=2 (cfg 5)" if args.workload == "simp" else
-                                    f"HEX8 box {args.size * world}x{args.size}x{args.size} linear elasticity E=70e3 nu=0.3, u=0 on x=0, "
-                                    f"traction on x=Lx (cfg 2{'' if world == 1 else ' extended in x: weak scaling'})"),
-                       "n_dofs_total": n_total, "n_dofs_per_gpu": n, "nnz_per_gpu": int(nnz * own_frac), "cells_per_gpu": int(prob.num_cells * own_frac),
-                       "per_gpu": "whole mesh" if world == 1 else f"x-slab of {args.size}^3 cells + 1 ghost cell layer per interface; "
-                                  "assembly needs no communication; SpMV = halo send/recv with <= 2 neighbours; Krylov dots = all-reduce",
+                                   (f"HEX8 cantilever 2 x 0.5 x 1, {nx} cells with s = {max(2, args.size // 2)}, u=0 on x=0, traction on x=2 (cfg 5)"
+                                    if args.workload == "simp" else
+                                    f"HEX8 box {nx} linear elasticity E=70e3 nu=0.3, u=0 on x=0, traction on x=1: the north star's "
+                                    f">= 24M-DOF mesh (cfg 2's problem on cfg 3's 200^3 mesh), FIXED for every GPU count"),
+                       "n_dofs_total": n_total, "n_dofs_per_gpu": n, "nnz_per_gpu": int(nnz * own_frac), "cells_per_gpu": cells_per_gpu,
+                       "per_gpu": "whole mesh" if world == 1 else f"x-slab of the fixed mesh (1/{world} of the nodes) + 1 ghost cell layer per interface; "
+                                  "assembly needs no communication; SpMV = halo ncclSend/ncclRecv with <= 2 neighbours; Krylov dots = ncclAllReduce",
+                       "assembly_mode": mode,
                        "l2": "inputs larger than L2 (element matrices + CSR >> 126 MB), no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": measured_traffic(args, world), "peak_source": peak_src,
+                         "traffic": measured_traffic(args, world), "traffic_source": "profiles/r02_traffic.json (ncu dram__bytes of this code, same workload/size/mode) or null",
+                         "peak_source": peak_src,
                          "kernel": "assembly = element_kernel + gather_residual + apply_bc_vec + gather_csr",
                          "algorithmic_bytes": b_asm, "kernel_ms": asm_kernel_ms,
                          "kernels_ms": {"element_kernel+gather_residual": t_elem, "apply_bc_vec": t_bc, "gather_csr": t_gather}},
             "roofline_spmv": {"bound": "hbm", "achieved": spmv_gbs, "peak": hbm, "unit": "GB/s", "frac": spmv_gbs / hbm,
                               "kernel_bytes": int(8 * nnz * own_frac + 4 * nnz * own_frac / 9 + 24 * n),
                               "kernel_gbs": (8 * nnz * own_frac + 4 * nnz * own_frac / 9 + 24 * n) / (spmv_ms * 1e-3) / 1e9,
+                              "frac_of_kernel_bytes": (8 * nnz * own_frac + 4 * nnz * own_frac / 9 + 24 * n) / (spmv_ms * 1e-3) / 1e9 / hbm,
                               "algorithmic_bytes": b_spmv, "kernel_ms": spmv_ms, "kernel": "spmv_block_fused_kernel<3,8,0> (node-block CSR: one column index per 3x3 block, 8 lanes per node)"
                                         + (" + halo exchange" if world > 1 else ""),
                               "note": "algorithmic bytes are those of scalar CSR (12 B/nnz, SURVEY 8d); the kernel reads 8.44 B/nnz, "
-                                      "so a fraction above 1 is possible"},
+                                      "so `frac` can exceed 1; `frac_of_kernel_bytes` is the fraction on the kernel's own traffic"},
             "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": "DOF/s", "h2d_bytes_per_step": n_local * 8,
                     "d2h_bytes_per_step": n_local * 8, "ms_per_step": e2e_ms},
             "gpu_launches": args.steps * 4 * world, "clocks": clocks, "setup_s": setup_s,
@@ -552,6 +618,8 @@ def main():
             line["newton_solve"] = newton
         if adjoint:
             line["adjoint"] = adjoint
+        if cfg2:
+            line["cfg2_100cube"] = cfg2
         if not args.no_cpu_baseline and world == 1:
             log(f"timing the CPU oracle on {args.ref_size}^3")
             v, info = cpu_oracle_assembly(args.ref_size)
@@ -562,6 +630,7 @@ def main():
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
+        comm.close()
         dist.destroy_process_group()
 
 

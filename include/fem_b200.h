@@ -223,6 +223,43 @@ int fem_dcg_update(int64_t n_owned, int64_t n_local, const double* diag, const d
 int fem_dcg_direction(int64_t n_owned, const double* diag, const double* r, double* p, double* workspace,
                       void* stream);
 
+/* ---- (e) multi-GPU, whole loop in the library: NCCL plumbing, halo exchange, distributed Jacobi-CG / BiCGSTAB.
+ *      Replaces what the reference's MPI demo does through PETSc (applications/parallel/poisson_mpi.py:123-164,214-437)
+ *      and, per rank, jax_solve (jax_fem/solver.py:63-92) / the adjoint solve (solver.py:1409).
+ *
+ *      libnccl.so.2 is resolved at run time (dlopen: the copy the process already loaded, e.g. PyTorch's; FEM_NCCL_LIB
+ *      overrides), so the library has no link-time NCCL dependency.  `comm` arguments are ncclComm_t passed as void*.
+ *      fem_nccl_unique_id / fem_nccl_comm_create wrap ncclGetUniqueId / ncclCommInitRank (current CUDA device) for callers
+ *      that do not have a communicator yet; a communicator made elsewhere (any ncclComm_t) is accepted as well.
+ *
+ *      Halo plan of one rank: local vectors hold the owned dofs first, then the ghosts grouped by owner rank.  Neighbour k
+ *      (rank peer_host[k]) receives the owned nodes send_idx[send_ptr_host[k] .. send_ptr_host[k+1]) (device array of
+ *      local node ids) and fills the local nodes [recv_start_host[k], recv_start_host[k] + recv_count_host[k]).  sendbuf:
+ *      device scratch of vec * send_ptr_host[n] doubles.  fem_halo_exchange = one pack kernel + ncclGroupStart /
+ *      ncclSend / ncclRecv / ncclGroupEnd on `stream`.  fem_allreduce_sum: ncclAllReduce(sum, double) in place.          */
+int fem_nccl_unique_id(void* id128_host);
+int fem_nccl_comm_create(int world, int rank, const void* id128_host, void** comm_out);
+int fem_nccl_comm_destroy(void* comm);
+int fem_halo_create(void* nccl_comm, int vec, int n_neighbours, const int32_t* peer_host,
+                    const int64_t* send_ptr_host, const int32_t* send_idx, const int64_t* recv_start_host,
+                    const int64_t* recv_count_host, double* sendbuf, void** halo_out);
+int fem_halo_destroy(void* halo);
+int fem_halo_exchange(void* halo, double* x, void* stream);
+int fem_allreduce_sum(void* halo, double* buf, int count, void* stream);
+/* Distributed Jacobi-CG / BiCGSTAB on the rank's owned rows (CSR rows 0..n_owned-1 complete, columns index the local
+ * vector of n_local entries).  Same recurrences, stopping rule and info_host as fem_pcg / fem_pbicgstab; per iteration
+ * CG issues 1 halo exchange + 2 all-reduces (1 and 2 doubles), BiCGSTAB 2 halo exchanges + 4 all-reduces, all on
+ * `stream`; the host only polls the (all-reduced, hence rank-uniform) convergence flag every check_every iterations.
+ * b, x: local vectors (x: x0 on entry, solution with up-to-date ghosts on exit); workspace: fem_krylov_workspace(n_local). */
+int fem_dist_pcg(void* halo, int64_t n_owned, int64_t n_local, const int32_t* indptr, const int32_t* indices,
+                 const double* data, int vec, const int32_t* brow_ptr, const int32_t* bcol, const double* diag,
+                 const double* b, double* x, double tol, double atol, int maxiter, int check_every,
+                 double* workspace, double* info_host, void* stream);
+int fem_dist_pbicgstab(void* halo, int64_t n_owned, int64_t n_local, const int32_t* indptr, const int32_t* indices,
+                       const double* data, int vec, const int32_t* brow_ptr, const int32_t* bcol, const double* diag,
+                       const double* b, double* x, double tol, double atol, int maxiter, int check_every,
+                       double* workspace, double* info_host, void* stream);
+
 /* ---- (4) implicit adjoint: -lambda^T dc/dtheta per quadrature point
  *      (jax_fem/solver.py:1386-1394,1414-1416) for per-quad parameters; lambda must already be
  *      zero on Dirichlet rows (BC rows of c do not depend on theta).  grad: (n_cells, NQ).       */

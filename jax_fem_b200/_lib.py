@@ -46,6 +46,15 @@ _SIGNATURES = {
     "fem_dcg_update": (_i, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fem_dcg_direction": (_i, [_i64, _vp, _vp, _vp, _vp, _vp]),
     "fem_axpy": (_i, [_i64, _d, _vp, _vp, _vp]),
+    "fem_nccl_unique_id": (_i, [_vp]),
+    "fem_nccl_comm_create": (_i, [_i, _i, _vp, _vp]),
+    "fem_nccl_comm_destroy": (_i, [_vp]),
+    "fem_halo_create": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fem_halo_destroy": (_i, [_vp]),
+    "fem_halo_exchange": (_i, [_vp, _vp, _vp]),
+    "fem_allreduce_sum": (_i, [_vp, _vp, _i, _vp]),
+    "fem_dist_pcg": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _vp, _vp, _vp]),
+    "fem_dist_pbicgstab": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfem_b200.so")
-SOURCES = ["element.cu", "element_hex27.cu", "fused.cu", "staged.cu", "plan_host.cpp", "sparse.cu", "krylov.cu"]
+SOURCES = ["element.cu", "element_hex27.cu", "fused.cu", "staged.cu", "plan_host.cpp", "sparse.cu", "krylov.cu", "dist.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -31,7 +31,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES + ["-ldl"]
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)

@@ -1,0 +1,49 @@
+// Multi-GPU plumbing of libfem_b200: NCCL (resolved at run time from the libnccl.so.2 the process already has, normally
+// the copy PyTorch loaded) and the halo plan of one rank.
+#pragma once
+#include <nccl.h>
+#include "common.cuh"
+
+namespace femb200 {
+
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
+  const char* (*GetErrorString)(ncclResult_t);
+};
+const NcclApi* nccl_api();   // nullptr (and fem_last_error set) when libnccl cannot be loaded
+
+#define FEM_NCCL_CHECK(expr)                                                                              \
+  do {                                                                                                    \
+    ncclResult_t _r = (expr);                                                                             \
+    if (_r != ncclSuccess) {                                                                              \
+      femb200::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, nccl_api()->GetErrorString(_r)); \
+      return FEM_ECUDA;                                                                                   \
+    }                                                                                                     \
+  } while (0)
+
+// One rank's halo plan.  Local vectors hold the owned dofs first, then the ghosts grouped by owner rank, so that every
+// neighbour's ghost block is one contiguous slice that ncclRecv writes into directly; what a neighbour needs from this
+// rank is gathered into `sendbuf` by one pack kernel.
+struct HaloPlan {
+  ncclComm_t comm;
+  int vec;
+  int n_nb;
+  int peer[16];
+  int64_t send_ptr[17];     // neighbour k sends nodes send_idx[send_ptr[k] .. send_ptr[k+1])
+  int64_t recv_start[16];   // first local node of the ghost block received from neighbour k
+  int64_t recv_count[16];
+  const int32_t* send_idx;  // device: local ids of the owned nodes to pack, all neighbours concatenated
+  double* sendbuf;          // device: vec * send_ptr[n_nb] doubles
+};
+
+int halo_exchange(const HaloPlan* h, double* x, cudaStream_t st);
+int allreduce_sum(const HaloPlan* h, double* buf, int count, cudaStream_t st);
+
+}  // namespace femb200

@@ -12,6 +12,7 @@
 // reduced in a fixed order (warp butterfly -> per-block partial -> last block sums partials by index),
 // so results are bit-reproducible run to run.
 #include "common.cuh"
+#include "dist.cuh"
 
 namespace femb200 {
 int launch_spmv(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data, const double* x,
@@ -44,6 +45,8 @@ enum {
   S_SUM1 = 17,
   S_SUM2 = 18,
   S_SUM3 = 19,
+  S_SUM4 = 20,
+  S_SUM5 = 21,
   S_TICKET = 32  // unsigned counter (reinterpreted)
 };
 
@@ -103,7 +106,8 @@ __device__ __forceinline__ bool solver_done(const double* S) { return __ldcg(S +
 // MODE 0: plain.  MODE 1 (CG): dot0 = d1[row]*y[row] -> alpha = gamma/dot0.
 // MODE 2 (BiCGSTAB q = A phat): dot0 = rhat.q -> alpha = rho_new/dot0.
 // MODE 3 (BiCGSTAB t = A shat): dot0 = t.s, dot1 = t.t -> omega = dot0/dot1.
-// MODE 4 (distributed CG): dot0 = d1.y over the rank's owned rows -> S[S_SUM0] (all-reduced by the caller).
+// MODE 4 (distributed CG / BiCGSTAB): dot0 = d1.y over the rank's owned rows -> S[S_SUM0] (all-reduced by the caller).
+// MODE 5 (distributed BiCGSTAB t = A shat): rank-local t.s -> S[S_SUM2], t.t -> S[S_SUM3].
 template <int LPR, int MODE>
 __global__ void __launch_bounds__(kThreads) spmv_fused_kernel(int64_t n, const int32_t* __restrict__ indptr,
                                                               const int32_t* __restrict__ indices,
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(kThreads) spmv_fused_kernel(int64_t n, const i
     if (valid && sub == 0) {
       y[row] = acc;
       if (MODE == 1 || MODE == 2 || MODE == 4) dots[0] = fma(d1[row], acc, dots[0]);
-      if (MODE == 3) {
+      if (MODE == 3 || MODE == 5) {
         dots[0] = fma(acc, d1[row], dots[0]);
         dots[1] = fma(acc, acc, dots[1]);
       }
@@ -155,6 +159,8 @@ __global__ void __launch_bounds__(kThreads) spmv_fused_kernel(int64_t n, const i
   } else if constexpr (MODE == 4) {   // distributed CG: rank-local p.Ap, all-reduced by the caller
     double v[1] = {dots[0]};
     reduce_and_finalize<1>(v, S, partial, [&](double (&t)[1]) { S[S_SUM0] = t[0]; });
+  } else if constexpr (MODE == 5) {
+    reduce_and_finalize<2>(dots, S, partial, [&](double (&t)[2]) { S[S_SUM2] = t[0]; S[S_SUM3] = t[1]; });
   }
 }
 
@@ -209,7 +215,7 @@ __global__ void __launch_bounds__(kThreads) spmv_block_fused_kernel(int64_t n_no
         const int64_t row = VEC * nd + i;
         y[row] = acc[i];
         if (MODE == 1 || MODE == 2 || MODE == 4) dots[0] = fma(d1[row], acc[i], dots[0]);
-        if (MODE == 3) {
+        if (MODE == 3 || MODE == 5) {
           dots[0] = fma(acc[i], d1[row], dots[0]);
           dots[1] = fma(acc[i], acc[i], dots[1]);
         }
@@ -227,6 +233,8 @@ __global__ void __launch_bounds__(kThreads) spmv_block_fused_kernel(int64_t n_no
   } else if constexpr (MODE == 4) {
     double v[1] = {dots[0]};
     reduce_and_finalize<1>(v, S, partial, [&](double (&t)[1]) { S[S_SUM0] = t[0]; });
+  } else if constexpr (MODE == 5) {
+    reduce_and_finalize<2>(dots, S, partial, [&](double (&t)[2]) { S[S_SUM2] = t[0]; S[S_SUM3] = t[1]; });
   }
 }
 
@@ -467,6 +475,113 @@ __global__ void __launch_bounds__(kThreads) bicg_x_kernel(int64_t n, const doubl
   });
 }
 
+// ------------------------------------------- distributed BiCGSTAB (one rank's share) -------------
+// Same recurrences as above (jax.scipy.sparse.linalg._bicgstab_solve) on the rank's owned dofs.  Every kernel leaves
+// rank-local partial sums in S[S_SUM*]; the driver all-reduces the slots of that phase (ncclAllReduce, same stream) and
+// the next kernel derives alpha / omega from the reduced values on the device:
+//   SUM0 = rhat.q, SUM1 = s.s, SUM2 = t.s, SUM3 = t.t, SUM4 = r.r, SUM5 = rhat.r (b.b at start-up).
+__global__ void __launch_bounds__(kThreads) dbicg_init_kernel(int64_t n, const double* __restrict__ b,
+                                                              const double* __restrict__ ax, double* __restrict__ r,
+                                                              double* __restrict__ rhat, double* __restrict__ p,
+                                                              double* __restrict__ q, double* __restrict__ S,
+                                                              double* __restrict__ partial) {
+  double v[2] = {0.0, 0.0};
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    const double bi = b[i], ri = bi - ax[i];
+    r[i] = ri;
+    rhat[i] = ri;
+    p[i] = ri;
+    q[i] = ri;
+    v[0] = fma(ri, ri, v[0]);
+    v[1] = fma(bi, bi, v[1]);
+  }
+  reduce_and_finalize<2>(v, S, partial, [&](double (&t)[2]) { S[S_SUM4] = t[0]; S[S_SUM5] = t[1]; });
+}
+
+__global__ void dbicg_scalars_init_kernel(double* __restrict__ S) {
+  const double rr = S[S_SUM4];
+  S[S_GAMMA] = 1.0;
+  S[S_ALPHA] = 1.0;
+  S[S_OMEGA] = 1.0;
+  S[S_RR] = rr;
+  S[S_RHO_NEW] = rr;
+  S[S_BETA] = rr;
+  const double atol2 = fmax(S[S_TOL2] * S[S_SUM5], S[S_ATOLIN2]);
+  S[S_ATOL2] = atol2;
+  S[S_K] = 0.0;
+  S[S_DONE] = (rr > atol2 && 0.0 < S[S_MAXIT]) ? 0.0 : 1.0;
+}
+
+__global__ void __launch_bounds__(kThreads) dbicg_s_kernel(int64_t n, const double* __restrict__ diag,
+                                                           const double* __restrict__ r, const double* __restrict__ q,
+                                                           double* __restrict__ s, double* __restrict__ shat,
+                                                           double* __restrict__ S, double* __restrict__ partial) {
+  if (solver_done(S)) return;
+  const double alpha = __ldcg(S + S_RHO_NEW) / __ldcg(S + S_SUM0);
+  double v[1] = {0.0};
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    const double si = r[i] - alpha * q[i];
+    s[i] = si;
+    shat[i] = precond(diag, i, si);
+    v[0] = fma(si, si, v[0]);
+  }
+  reduce_and_finalize<1>(v, S, partial, [&](double (&t)[1]) { S[S_SUM1] = t[0]; });
+}
+
+__global__ void __launch_bounds__(kThreads) dbicg_x_kernel(int64_t n, const double* __restrict__ phat,
+                                                           const double* __restrict__ shat, const double* __restrict__ s,
+                                                           const double* __restrict__ t, const double* __restrict__ rhat,
+                                                           double* __restrict__ x, double* __restrict__ r,
+                                                           double* __restrict__ S, double* __restrict__ partial) {
+  if (solver_done(S)) return;
+  const double alpha = __ldcg(S + S_RHO_NEW) / __ldcg(S + S_SUM0);
+  const double omega = __ldcg(S + S_SUM2) / __ldcg(S + S_SUM3);
+  const bool early = __ldcg(S + S_SUM1) < __ldcg(S + S_ATOL2);
+  double v[2] = {0.0, 0.0};
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    double xi, ri;
+    if (early) {
+      xi = x[i] + alpha * phat[i];
+      ri = s[i];
+    } else {
+      xi = x[i] + (alpha * phat[i] + omega * shat[i]);
+      ri = s[i] - omega * t[i];
+    }
+    x[i] = xi;
+    r[i] = ri;
+    v[0] = fma(ri, ri, v[0]);
+    v[1] = fma(rhat[i], ri, v[1]);
+  }
+  reduce_and_finalize<2>(v, S, partial, [&](double (&tt)[2]) { S[S_SUM4] = tt[0]; S[S_SUM5] = tt[1]; });
+}
+
+__global__ void dbicg_scalars_step_kernel(double* __restrict__ S) {
+  if (S[S_DONE] != 0.0) return;
+  const double rho_ = S[S_RHO_NEW], al = rho_ / S[S_SUM0], om = S[S_SUM2] / S[S_SUM3];
+  double k = (om == 0.0 || al == 0.0) ? -11.0 : S[S_K] + 1.0;
+  if (rho_ == 0.0) k = -10.0;
+  S[S_K] = k;
+  S[S_GAMMA] = rho_;
+  S[S_ALPHA] = al;
+  S[S_OMEGA] = om;
+  S[S_RR] = S[S_SUM4];
+  S[S_RHO_NEW] = S[S_SUM5];
+  S[S_BETA] = S[S_SUM5] / rho_ * al / om;
+  S[S_DONE] = (S[S_SUM4] > S[S_ATOL2] && k < S[S_MAXIT] && k >= 0.0) ? 0.0 : 1.0;
+}
+
+// rank-local sum of (A x - b)^2 over the owned rows -> S[S_SUM0]
+__global__ void __launch_bounds__(kThreads) dresnorm_kernel(int64_t n, const double* __restrict__ ax,
+                                                            const double* __restrict__ b, double* __restrict__ S,
+                                                            double* __restrict__ partial) {
+  double v[1] = {0.0};
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    const double d = ax[i] - b[i];
+    v[0] = fma(d, d, v[0]);
+  }
+  reduce_and_finalize<1>(v, S, partial, [&](double (&t)[1]) { S[S_SUM0] = t[0]; });
+}
+
 // ||A x - b|| for the reference's post-solve check (solver.py:87)
 __global__ void __launch_bounds__(kThreads) resnorm_kernel(int64_t n, const double* __restrict__ ax,
                                                            const double* __restrict__ b, double* __restrict__ S,
@@ -484,18 +599,20 @@ constexpr int kLPR = 8;
 // Persistent grid = resident CTAs per SM (from the occupancy API) x SM count: exactly one wave.
 template <class K>
 int persistent_grid(K kernel) {
-  static int cached = 0;
-  if (!cached) {
-    int per_sm = 0, dev = 0, sms = kNumSM;
-    cudaGetDevice(&dev);
+  static int cached[64] = {0};   // per device (a process may drive several GPUs)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& c = cached[dev & 63];
+  if (!c) {
+    int per_sm = 0, sms = kNumSM;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
-    cached = per_sm * sms;
-    if (cached > kBlocks) cached = kBlocks;
+    c = per_sm * sms;
+    if (c > kBlocks) c = kBlocks;
   }
-  return cached;
+  return c;
 }
 #define FEM_PGRID(kernel) persistent_grid(kernel), kThreads, 0, st
 
@@ -711,4 +828,110 @@ extern "C" int fem_dcg_direction(int64_t n_owned, const double* diag, const doub
   dcg_direction_kernel<<<FEM_PGRID(dcg_direction_kernel)>>>(n_owned, diag, r, p, workspace);
   FEM_LAUNCH_CHECK();
   return FEM_OK;
+}
+
+// ---- distributed Krylov drivers: the whole loop (kernels, halo exchange, all-reduces) issued from C on one stream ----
+namespace femb200 {
+namespace {
+int dist_finish(const HaloPlan* h, const Mat& A, const double* b, double* x, const Ws& w, double* scratch,
+                double* info_host, cudaStream_t st) {
+  double hs[kScalars];
+  FEM_CUDA_CHECK(cudaMemcpyAsync(hs, w.s, sizeof(hs), cudaMemcpyDeviceToHost, st));
+  FEM_CUDA_CHECK(cudaStreamSynchronize(st));
+  info_host[0] = hs[S_K];
+  info_host[1] = hs[S_RR];
+  if (int e = halo_exchange(h, x, st)) return e;                 // the caller gets up-to-date ghosts
+  spmv_fused<0>(A, x, scratch, nullptr, w, st);
+  dresnorm_kernel<<<FEM_PGRID(dresnorm_kernel)>>>(A.n, scratch, b, w.s, w.partial);
+  FEM_LAUNCH_CHECK();
+  if (int e = allreduce_sum(h, w.s + S_SUM0, 1, st)) return e;
+  FEM_CUDA_CHECK(cudaMemcpyAsync(hs, w.s, sizeof(hs), cudaMemcpyDeviceToHost, st));
+  FEM_CUDA_CHECK(cudaStreamSynchronize(st));
+  info_host[2] = sqrt(hs[S_SUM0]);
+  return FEM_OK;
+}
+}  // namespace
+}  // namespace femb200
+
+extern "C" int fem_dist_pcg(void* halo, int64_t n_owned, int64_t n_local, const int32_t* indptr, const int32_t* indices,
+                            const double* data, int vec, const int32_t* brow_ptr, const int32_t* bcol, const double* diag,
+                            const double* b, double* x, double tol, double atol, int maxiter, int check_every,
+                            double* workspace, double* info_host, void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(halo && indptr && indices && data && b && x && workspace && info_host, "null pointer");
+  FEM_REQUIRE(n_owned > 0 && n_local >= n_owned && maxiter >= 0, "bad size");
+  const HaloPlan* h = reinterpret_cast<const HaloPlan*>(halo);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (check_every <= 0) check_every = 25;
+  const Ws w = carve(workspace, n_local);
+  const Mat A{n_owned, indptr, indices, data, vec, brow_ptr, bcol};
+  double *r = w.v[0], *p = w.v[1], *q = w.v[2];
+  if (int e = init_scalars(w, tol, atol, maxiter, st)) return e;
+  if (int e = halo_exchange(h, x, st)) return e;
+  spmv_fused<0>(A, x, q, nullptr, w, st);
+  dcg_init_kernel<<<FEM_PGRID(dcg_init_kernel)>>>(n_owned, b, diag, q, r, p, w.s, w.partial);
+  FEM_LAUNCH_CHECK();
+  if (int e = allreduce_sum(h, w.s + S_SUM0, 3, st)) return e;
+  dcg_scalars_init_kernel<<<1, 1, 0, st>>>(w.s);
+  bool done = false;
+  if (int e = poll_done(w, &done, st)) return e;
+  for (int it = 0; !done && it < maxiter; it += check_every) {
+    for (int j = 0; j < check_every; ++j) {
+      if (int e = halo_exchange(h, p, st)) return e;
+      spmv_fused<4>(A, p, q, p, w, st);                                        // q = A p ; rank-local p.Ap
+      if (int e = allreduce_sum(h, w.s + S_SUM0, 1, st)) return e;
+      dcg_update_kernel<<<FEM_PGRID(dcg_update_kernel)>>>(n_owned, diag, p, q, x, r, w.s, w.partial);
+      if (int e = allreduce_sum(h, w.s + S_SUM1, 2, st)) return e;
+      dcg_direction_kernel<<<FEM_PGRID(dcg_direction_kernel)>>>(n_owned, diag, r, p, w.s);
+      dcg_scalars_step_kernel<<<1, 1, 0, st>>>(w.s);
+    }
+    FEM_LAUNCH_CHECK();
+    if (int e = poll_done(w, &done, st)) return e;
+  }
+  return dist_finish(h, A, b, x, w, q, info_host, st);
+}
+
+extern "C" int fem_dist_pbicgstab(void* halo, int64_t n_owned, int64_t n_local, const int32_t* indptr,
+                                  const int32_t* indices, const double* data, int vec, const int32_t* brow_ptr,
+                                  const int32_t* bcol, const double* diag, const double* b, double* x, double tol,
+                                  double atol, int maxiter, int check_every, double* workspace, double* info_host,
+                                  void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(halo && indptr && indices && data && b && x && workspace && info_host, "null pointer");
+  FEM_REQUIRE(n_owned > 0 && n_local >= n_owned && maxiter >= 0, "bad size");
+  const HaloPlan* h = reinterpret_cast<const HaloPlan*>(halo);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (check_every <= 0) check_every = 25;
+  const Ws w = carve(workspace, n_local);
+  const Mat A{n_owned, indptr, indices, data, vec, brow_ptr, bcol};
+  double *r = w.v[0], *rhat = w.v[1], *p = w.v[2], *q = w.v[3], *s = w.v[4], *t = w.v[5], *phat = w.v[6],
+         *shat = w.v[7];
+  if (int e = init_scalars(w, tol, atol, maxiter, st)) return e;
+  if (int e = halo_exchange(h, x, st)) return e;
+  spmv_fused<0>(A, x, t, nullptr, w, st);
+  dbicg_init_kernel<<<FEM_PGRID(dbicg_init_kernel)>>>(n_owned, b, t, r, rhat, p, q, w.s, w.partial);
+  FEM_LAUNCH_CHECK();
+  if (int e = allreduce_sum(h, w.s + S_SUM4, 2, st)) return e;
+  dbicg_scalars_init_kernel<<<1, 1, 0, st>>>(w.s);
+  bool done = false;
+  if (int e = poll_done(w, &done, st)) return e;
+  for (int it = 0; !done && it < maxiter; it += check_every) {
+    for (int j = 0; j < check_every; ++j) {
+      bicg_p_kernel<<<FEM_PGRID(bicg_p_kernel)>>>(n_owned, diag, r, q, p, phat, w.s);
+      if (int e = halo_exchange(h, phat, st)) return e;
+      spmv_fused<4>(A, phat, q, rhat, w, st);                                  // q = A phat ; rank-local rhat.q
+      if (int e = allreduce_sum(h, w.s + S_SUM0, 1, st)) return e;
+      dbicg_s_kernel<<<FEM_PGRID(dbicg_s_kernel)>>>(n_owned, diag, r, q, s, shat, w.s, w.partial);
+      if (int e = allreduce_sum(h, w.s + S_SUM1, 1, st)) return e;
+      if (int e = halo_exchange(h, shat, st)) return e;
+      spmv_fused<5>(A, shat, t, s, w, st);                                     // t = A shat ; rank-local t.s, t.t
+      if (int e = allreduce_sum(h, w.s + S_SUM2, 2, st)) return e;
+      dbicg_x_kernel<<<FEM_PGRID(dbicg_x_kernel)>>>(n_owned, phat, shat, s, t, rhat, x, r, w.s, w.partial);
+      if (int e = allreduce_sum(h, w.s + S_SUM4, 2, st)) return e;
+      dbicg_scalars_step_kernel<<<1, 1, 0, st>>>(w.s);
+    }
+    FEM_LAUNCH_CHECK();
+    if (int e = poll_done(w, &done, st)) return e;
+  }
+  return dist_finish(h, A, b, x, w, t, info_host, st);
 }

@@ -246,7 +246,7 @@ __global__ void csr_diag_kernel(int64_t n, const int32_t* __restrict__ indptr, c
   int lo = indptr[row], hi = indptr[row + 1] - 1;
   double d = 0.0;
   while (lo <= hi) {
-    const int mid = (lo + hi) >> 1;
+    const int mid = lo + ((hi - lo) >> 1);      // lo + hi overflows int32 once nnz > 2^30 (200^3 HEX8: nnz = 1.95e9)
     const int c = indices[mid];
     if (c == row) { d = data[mid]; break; }
     if (c < row) lo = mid + 1; else hi = mid - 1;
@@ -329,11 +329,14 @@ int launch_gather(int n_items, const int32_t* gdesc, const int32_t* emeta, const
   constexpr int ROW = (NN * VEC * VEC + 1) / 2 * 2;
   const size_t smem = sizeof(double) * 2 * MAXC * ROW + sizeof(int) * MAXC * NN;
   auto k = gather_csr_kernel<VEC, NN>;
-  static int grid = 0;                      // persistent grid: resident CTAs x SMs (per template instance)
+  // persistent grid: resident CTAs x SMs, cached per device (the shared-memory attribute is per device too)
+  static int grids[64] = {0};
+  int dev = 0;
+  FEM_CUDA_CHECK(cudaGetDevice(&dev));
+  int& grid = grids[dev & 63];
   if (!grid) {
     FEM_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0, dev = 0, sms = kNumSM;
-    cudaGetDevice(&dev);
+    int per_sm = 0, sms = kNumSM;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kGatherThreads, smem);
     grid = (per_sm < 1 ? 1 : per_sm) * sms;

@@ -89,14 +89,19 @@ def partition_mesh(cells, num_nodes, rank, world):
     for s in np.unique(owner):
         idx = np.flatnonzero(owner == s)
         part.recv[int(s)] = (len(owned) + int(idx[0]), len(owned) + int(idx[-1]) + 1)
-    # what the others need from me: their ghost nodes that I own (same grouping rule => same order on both sides)
-    for s in range(world):
+    # What the others need from me.  Rank s holds every cell that touches one of its nodes, so my owned nodes inside a cell
+    # that also contains a node of s are exactly the ghosts of s that I own; s lists them grouped by owner in ascending
+    # global order (the rule above), which is the order used here -- no look at the other ranks' partitions is needed.
+    lc = cells[local_cells]
+    own = np.searchsorted(ranges, lc, side='right') - 1
+    mine = own == rank
+    for s in np.unique(own):
         if s == rank:
             continue
-        _, g_s, o_s = _rank_view(cells, ranges, s)
-        mine = g_s[o_s == rank]
-        if len(mine):
-            part.send[s] = (mine - lo).astype(np.int64)
+        sel = (own == s).any(axis=1)
+        nodes = np.unique(lc[sel][mine[sel]])
+        if len(nodes):
+            part.send[int(s)] = (nodes - lo).astype(np.int64)
     return part
 
 
@@ -130,6 +135,51 @@ class TorchDistComm:
 
     def barrier(self):
         self.dist.barrier(group=self.group)
+
+
+class NcclComm:
+    """The library's own NCCL communicator (csrc/dist.cu): halo exchange, all-reduces and the whole distributed Krylov loop
+    are issued from C on the current CUDA stream.  ``torch.distributed`` (any backend) is only used once, to hand the
+    ncclUniqueId of rank 0 to the other ranks."""
+    native = True
+
+    def __init__(self, group=None):
+        import ctypes
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        lib = _lib.load()
+        uid = (ctypes.c_char * 128)()
+        if self.rank == 0:
+            _lib.check(lib.fem_nccl_unique_id(uid))
+        box = [bytes(uid)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        uid = (ctypes.c_char * 128).from_buffer_copy(box[0])
+        self.handle = ctypes.c_void_p()
+        _lib.check(lib.fem_nccl_comm_create(self.world, self.rank, uid, ctypes.byref(self.handle)))
+        self._scalar_halo = ctypes.c_void_p()          # a plan without neighbours: carries the communicator for all-reduces
+        _lib.check(lib.fem_halo_create(self.handle, 1, 0, None, None, None, None, None, None, ctypes.byref(self._scalar_halo)))
+
+    def allreduce(self, t):
+        assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+        _lib.check(_lib.load().fem_allreduce_sum(self._scalar_halo, _lib.ptr(t), t.numel(), _lib.stream_ptr()))
+
+    def exchange(self, sends, recvs):
+        raise RuntimeError("NcclComm exchanges halos through Halo.update (fem_halo_exchange)")
+
+    def barrier(self):
+        torch.cuda.synchronize()
+        self.dist.barrier(group=self.group)
+
+    def close(self):
+        lib = _lib.load()
+        if self._scalar_halo:
+            lib.fem_halo_destroy(self._scalar_halo)
+            self._scalar_halo = None
+        if self.handle:
+            torch.cuda.synchronize()
+            lib.fem_nccl_comm_destroy(self.handle)
+            self.handle = None
 
 
 class ThreadComm:
@@ -175,20 +225,50 @@ class ThreadComm:
 
 
 class Halo:
-    """Ghost update of a (n_local_nodes, vec) field: owners -> ghosts, neighbour ranks only."""
+    """Ghost update of a (n_local_nodes, vec) field: owners -> ghosts, neighbour ranks only.  With the library's NCCL
+    communicator the pack kernel and the grouped ncclSend / ncclRecv are issued from C (fem_halo_exchange)."""
 
     def __init__(self, part, comm, vec, device):
         self.part, self.comm, self.vec = part, comm, vec
         self.send_idx = {s: torch.as_tensor(idx, device=device) for s, idx in part.send.items()}
         self.bytes_per_exchange = sum(len(i) for i in part.send.values()) * vec * 8
+        self.handle = None
+        if getattr(comm, 'native', False):
+            import ctypes
+            peers = part.neighbours
+            n = len(peers)
+            send_ptr = np.zeros(n + 1, dtype=np.int64)
+            for k, s in enumerate(peers):
+                send_ptr[k + 1] = send_ptr[k] + len(part.send.get(s, ()))
+            idx = np.concatenate([np.asarray(part.send.get(s, np.zeros(0, np.int64))) for s in peers]) if n else np.zeros(0, np.int64)
+            self._idx = torch.as_tensor(idx.astype(np.int32), device=device)
+            self._buf = torch.empty(max(1, int(send_ptr[-1]) * vec), dtype=torch.float64, device=device)
+            recv_start = np.array([part.recv.get(s, (0, 0))[0] for s in peers], dtype=np.int64)
+            recv_count = np.array([part.recv.get(s, (0, 0))[1] - part.recv.get(s, (0, 0))[0] for s in peers], dtype=np.int64)
+            peer = np.array(peers, dtype=np.int32)
+            self.handle = ctypes.c_void_p()
+            as_p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+            _lib.check(_lib.load().fem_halo_create(comm.handle, vec, n, as_p(peer), as_p(send_ptr), _lib.ptr(self._idx),
+                                                   as_p(recv_start), as_p(recv_count), _lib.ptr(self._buf), ctypes.byref(self.handle)))
 
     def update(self, x):
         """x: flat (n_local*vec,) or (n_local, vec) tensor, updated in place."""
+        if self.handle is not None:
+            assert x.is_contiguous()
+            _lib.check(_lib.load().fem_halo_exchange(self.handle, _lib.ptr(x), _lib.stream_ptr()))
+            return x
         xv = x.view(self.part.n_local, self.vec)
         sends = {s: xv.index_select(0, idx).contiguous() for s, idx in self.send_idx.items()}
         recvs = {s: xv[a:b] for s, (a, b) in self.part.recv.items()}          # contiguous row blocks
         self.comm.exchange(sends, recvs)
         return x
+
+    def __del__(self):
+        if getattr(self, 'handle', None) is not None:
+            try:
+                _lib.load().fem_halo_destroy(self.handle)
+            except Exception:
+                pass
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -227,6 +307,29 @@ def _post_check(A, x, b, part, halo, comm, vec, info, ops=None):
     return info
 
 
+_native_ws = {}
+
+
+def _native_krylov(fn, A, b, x, diag, part, halo, vec, tol, atol, maxiter, check_every):
+    """The whole distributed Krylov loop in the library (fem_dist_pcg / fem_dist_pbicgstab): kernels, halo exchanges and
+    all-reduces are issued from C on the current stream; the host only polls the convergence flag."""
+    lib, P = _lib.load(), _lib.ptr
+    n_owned, n_local = part.n_owned * vec, part.n_local * vec
+    indptr, indices, data = A.getValuesCSR()
+    key = (n_local, b.device, threading.get_ident())
+    if key not in _native_ws:
+        _native_ws[key] = torch.zeros(lib.fem_krylov_workspace(n_local), dtype=torch.float64, device=b.device)
+    ws = _native_ws[key]
+    info = (_lib.ctypes.c_double * 4)()
+    b = b.reshape(-1).contiguous()
+    _lib.check(fn(halo.handle, n_owned, n_local, P(indptr), P(indices), P(data), A.plan.vec, P(A.plan.brow_ptr),
+                  P(A.plan.bcol), P(diag), P(b), P(x), float(tol), float(atol), int(maxiter), int(check_every), P(ws), info,
+                  _lib.stream_ptr()))
+    out = {'iterations': int(info[0]), 'rr': float(info[1]), 'err': float(info[2])}
+    assert out['err'] < 0.1, f"distributed linear solver failed to converge with err = {out['err']}"
+    return x, out
+
+
 def distributed_cg(A, b, x0, part, halo, comm, vec, tol=1e-10, atol=1e-10, maxiter=10000, check_every=25,
                    precond=True):
     """Jacobi-CG on the rank's owned rows; same recurrences / stopping rule as fem_pcg (jax's cg).
@@ -240,6 +343,8 @@ def distributed_cg(A, b, x0, part, halo, comm, vec, tol=1e-10, atol=1e-10, maxit
     dev = b.device
     x = x0.reshape(-1).clone().contiguous()
     diag = A.diagonal() if precond else None
+    if halo.handle is not None:
+        return _native_krylov(lib.fem_dist_pcg, A, b, x, diag, part, halo, vec, tol, atol, maxiter, check_every)
     ws = torch.zeros(lib.fem_krylov_workspace(n_local), dtype=torch.float64, device=dev)
     sums = ws[16:20]
     r, p, q = (torch.zeros(n_local, dtype=torch.float64, device=dev) for _ in range(3))
@@ -282,6 +387,10 @@ def distributed_bicgstab(A, b, x0, part, halo, comm, vec, tol=1e-10, atol=1e-10,
 
     A: local CSRMatrix (rows of owned nodes complete); b, x0: flat local vectors (owned first, then ghosts; x0 may be
     None).  Returns (x with up-to-date ghosts, info)."""
+    if halo.handle is not None and ops is None:
+        x = torch.zeros(part.n_local * vec, dtype=torch.float64, device=b.device) if x0 is None else x0.reshape(-1).clone().contiguous()
+        return _native_krylov(_lib.load().fem_dist_pbicgstab, A, b, x, A.diagonal() if precond else None, part, halo, vec,
+                              tol, atol, maxiter, 25)
     ops = ops or _LibraryOps(A, part, vec)
     n_owned, n_local = part.n_owned * vec, part.n_local * vec
     dev = b.device
@@ -411,6 +520,7 @@ class ShardedProblem:
         v = torch.as_tensor(v, dtype=torch.float64, device=pb.device).reshape(-1).contiguous()
         lam, info = distributed_bicgstab(A_T, v, None, self.part, self.halo, self.comm, self.vec, **solver_options)
         self.last_info = info
+        self.last_lambda = lam
         lam = assign_zeros_bc(lam, pb)
         fe, law, iv = pb.fes[0], pb._law, pb._internal_var()
         if iv is None:

@@ -134,3 +134,26 @@ def test_partition_single_rank_has_no_ghosts():
     part = partition_mesh(m.cells_dict['hexahedron'], len(m.points), 0, 1)
     assert part.n_owned == len(m.points) and len(part.ghosts) == 0 and not part.neighbours
     assert np.array_equal(part.cells_local, m.cells_dict['hexahedron'])
+
+
+def test_send_lists_from_local_cells_equal_the_other_ranks_ghost_lists():
+    """partition_mesh derives what a rank sends from its own cells only; by definition it must be exactly the ghost
+    nodes the neighbour lists for this owner, in the neighbour's order (ascending global id)."""
+    import numpy as np
+    from jax_fem_b200.distributed import _rank_view, node_ranges, partition_mesh
+    from jax_fem_b200.generate_mesh import box_mesh
+    m = box_mesh(9, 4, 3, 3.0, 1.0, 0.8)
+    cells = m.cells_dict['hexahedron'].astype(np.int64)
+    n = len(m.points)
+    perm = np.random.default_rng(3).permutation(n)
+    for conn in (cells, perm[cells]):                     # x-slabs, and a numbering without spatial order
+        for world in (2, 3, 5):
+            ranges = node_ranges(n, world)
+            for rank in range(world):
+                part = partition_mesh(conn, n, rank, world)
+                for s in range(world):
+                    if s == rank:
+                        continue
+                    _, g_s, o_s = _rank_view(conn, ranges, s)
+                    mine = g_s[o_s == rank] - ranges[rank]
+                    assert np.array_equal(part.send.get(s, np.zeros(0, np.int64)), mine)

@@ -477,6 +477,28 @@ def test_ring_assembly_recycles_rows_correctly(ring_kb, tile, slack, margin, mon
     prob.check_assembly_status()
 
 
+def test_csr_diagonal_beyond_2_30_nonzeros():
+    """The Jacobi preconditioner of the 200^3 mesh (nnz = 1.95e9): row offsets above 2^30 must not overflow the binary search
+    for the diagonal entry (lo + hi in int32 did: the first 200^3 solve on one GPU hung).  Synthetic banded matrix with
+    nnz = 1.09e9 whose value at (i, j) is j, so diag[i] must be i."""
+    from jax_fem_b200 import _lib
+    n, w = 39_000_000, 28
+    dev = 'cuda'
+    start = (torch.arange(n, device=dev, dtype=torch.int64) - 14).clamp_(0, n - w)
+    indptr = (torch.arange(n + 1, device=dev, dtype=torch.int64) * w).to(torch.int32)
+    assert int(indptr[-1]) > 2 ** 30
+    indices = torch.empty(n * w, dtype=torch.int32, device=dev)
+    for a in range(0, n, 1 << 22):
+        b = min(n, a + (1 << 22))
+        indices[a * w:b * w] = (start[a:b, None] + torch.arange(w, device=dev)[None, :]).reshape(-1).to(torch.int32)
+    data = indices.to(torch.float64)
+    diag = torch.empty(n, dtype=torch.float64, device=dev)
+    P = _lib.ptr
+    _lib.check(_lib.load().fem_csr_diagonal(n, P(indptr), P(indices), P(data), P(diag), None))
+    torch.cuda.synchronize()
+    assert torch.equal(diag, torch.arange(n, device=dev, dtype=torch.float64))
+
+
 # ---- full-size (BASELINE.json configs[1]) checks through size-independent properties -------------------------------
 def test_full_size_cfg2_properties(monkeypatch):
     """HEX8 100^3 linear elasticity (3.09 M DOF, nnz 245 M) -- too large for the oracle, so the assembled operator is
