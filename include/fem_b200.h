@@ -46,6 +46,45 @@ int fem_version(void);
 /* number of CUDA devices visible, or FEM_ENODEV */
 int fem_device_count(void);
 
+/* ---- (0) the assembly plan: the (I, J) COO pattern of Problem.__post_init__ (jax_fem/problem.py:86-107) and PETSc's
+ *      setPreallocationCOO (jax_fem/solver.py:476-478), built ON THE DEVICE from the raw connectivity: sparsity pattern
+ *      (int32 indptr / indices exactly as PETSc produces them: every (I, J) pair kept, columns ascending), node-block graph,
+ *      the node-sorted corner order of the element tangents, the deterministic gather schedule and the transpose map.
+ *      The handle owns its tables (cudaMalloc); no Python and no torch are involved.
+ * cells: device (n_cells, nodes_per_cell) int32.  Fails with FEM_EINVAL when nnz or n_cells*N*N exceed int32 (shard the
+ * mesh) or a node belongs to more than 16 cells (8 for 27-node cells).
+ * fem_plan_sizes: [0] nnzb (node-block entries) [1] nnz [2] gather work items (n_blocks of fem_gather_csr) [3] emeta rows
+ *                 [4] sources (= n_cells*N*N) [5] n_dofs [6] doubles per corner row block of Ke [7] row blocks of Ke.
+ * fem_plan_table: device pointer + length of one table (FEM_PLAN_*); the tables are the arguments of the entry points below
+ *                 (corner_pos -> fem_element_residual_jacobian; gdesc, src -> fem_gather_csr; nc_ptr, nc -> fem_gather_residual;
+ *                 indptr, indices, brow_ptr, bcol -> fem_spmv / fem_pcg / fem_pbicgstab; tperm -> fem_csr_transpose_values).
+ * fem_plan_entry_meta: the emeta argument of fem_gather_csr (n_rows x 4 int32, 16-byte aligned) for a Dirichlet mask
+ *                 bc_flag (n_dofs bytes, 1 = Dirichlet row; NULL = none): rows -> zeroed, unit diagonal, pattern kept
+ *                 (Mat.zeroRows, jax_fem/solver.py:477,527-528).                                                        */
+#define FEM_PLAN_BROW_PTR 0
+#define FEM_PLAN_BCOL 1
+#define FEM_PLAN_INDPTR 2
+#define FEM_PLAN_INDICES 3
+#define FEM_PLAN_CORNER_POS 4
+#define FEM_PLAN_NC_PTR 5
+#define FEM_PLAN_NC 6
+#define FEM_PLAN_GDESC 7
+#define FEM_PLAN_SRC 8
+#define FEM_PLAN_SRC_PTR 9
+#define FEM_PLAN_TPERM 10
+#define FEM_PLAN_M_SB 11
+#define FEM_PLAN_M_SE 12
+#define FEM_PLAN_M_ENT 13
+#define FEM_PLAN_M_ADD 14
+#define FEM_PLAN_EDST 15
+#define FEM_PLAN_EROW 16
+int fem_plan_create(const int32_t* cells, int64_t n_cells, int64_t n_nodes, int nodes_per_cell, int vec,
+                    void* stream, void** plan_out);
+int fem_plan_destroy(void* plan);
+int fem_plan_sizes(const void* plan, int64_t* sizes_host);
+int fem_plan_table(const void* plan, int which, const int32_t** table_out, int64_t* count_out);
+int fem_plan_entry_meta(const void* plan, const uint8_t* bc_flag, int32_t* emeta, void* stream);
+
 /* ---- (1) element kernels: Problem.compute_residual_vars / compute_newton_vars
  *      (jax_fem/problem.py:439-460) with the geometry of FiniteElement.get_shape_grads
  *      (jax_fem/fe.py:112-141) recomputed in-kernel instead of materialised.

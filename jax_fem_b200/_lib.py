@@ -20,6 +20,11 @@ _SIGNATURES = {
     "fem_last_error": (ctypes.c_char_p, []),
     "fem_version": (_i, []),
     "fem_device_count": (_i, []),
+    "fem_plan_create": (_i, [_vp, _i64, _i64, _i, _i, _vp, _vp]),
+    "fem_plan_destroy": (_i, [_vp]),
+    "fem_plan_sizes": (_i, [_vp, _vp]),
+    "fem_plan_table": (_i, [_vp, _i, _vp, _vp]),
+    "fem_plan_entry_meta": (_i, [_vp, _vp, _vp, _vp]),
     "fem_element_residual_jacobian": (_i, [_i, _i, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fem_hex27_residual_jacobian": (_i, [_i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "fem_assemble_fused": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64] + [_vp] * 18 + [_i, _vp]),

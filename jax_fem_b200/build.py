@@ -7,9 +7,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfem_b200.so")
-SOURCES = ["element.cu", "element_hex27.cu", "fused.cu", "staged.cu", "plan_host.cpp", "sparse.cu", "krylov.cu", "dist.cu"]
-NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared"]
+SOURCES = ["element.cu", "element_hex27.cu", "fused.cu", "staged.cu", "plan_host.cpp", "sparse.cu", "krylov.cu", "dist.cu", "plan.cu"]
+OBJDIR = os.path.join(LIBDIR, "obj")
+COMPILE_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
+LINK_FLAGS = ["-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
 
 
 def _nvcc():
@@ -28,17 +29,36 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Compile every source to an object file (in parallel; only sources newer than their object unless `force`) and link."""
     if not force and not needs_build():
         return LIB
-    os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES + ["-ldl"]
-    proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJDIR, exist_ok=True)
+    nvcc = _nvcc()
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + [os.path.join(HERE, "..", "include", "fem_b200.h")]
+    newest_header = max(os.path.getmtime(h) for h in headers)
+
+    def compile_one(src):
+        obj = os.path.join(OBJDIR, os.path.splitext(src)[0] + ".o")
+        path = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(path), newest_header):
+            return obj, ""
+        cmd = [nvcc] + COMPILE_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+        proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + proc.stdout + proc.stderr)
+        return obj, proc.stderr
+
+    with ThreadPoolExecutor(max(1, min(len(SOURCES), os.cpu_count() or 1))) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    proc = subprocess.run([nvcc] + LINK_FLAGS + ["-o", LIB] + [o for o, _ in results] + ["-ldl"], cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+        raise RuntimeError("link failed:\n" + proc.stdout + proc.stderr)
     if verbose:
-        print(proc.stderr)
+        print("".join(log for _, log in results))
     return LIB
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -72,6 +72,8 @@ class AssemblyPlan:
     def entry_meta(self, bc_flag):
         """emeta of fem_gather_csr: (source begin, source end, CSR destination, info) per gather row in processing
         order; info = entry_info | bit 20 for the second half of a split entry (added to the first half's result)."""
+        if getattr(self, 'native', None) is not None:
+            return native_entry_meta(self, bc_flag)
         e = self.m_ent.long()
         info = self.entry_info(bc_flag).long()[e] | (self.m_add.long() << 20)
         return torch.stack([self.m_sb.long(), self.m_se.long(), self.edst.long()[e], info], dim=1).to(torch.int32).contiguous()
@@ -225,3 +227,62 @@ def build_plan(cells, num_nodes, vec):
     del counts
     return AssemblyPlan(m_sb=m_sb, m_se=m_se, m_ent=m_ent, m_add=m_add, corner_pos=corner_pos, gdesc=gdesc, eorder=eorder, edst=edst, erow=erow, num_nodes=num_nodes, num_cells=C, nodes_per_cell=N, vec=vec, brow_ptr=brow_ptr, bcol=bcol,
                         src_ptr=src_ptr, src=src, nc_ptr=nc_ptr, nc=nc, indptr=indptr, indices=indices)
+
+
+# ---- the same plan built by the library (csrc/plan.cu, fem_plan_create): no torch operators involved ------------------------
+class _DeviceTable:
+    """A device table owned by a fem_plan handle, exposed through __cuda_array_interface__ so that torch wraps it without a copy."""
+
+    def __init__(self, ptr, count, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<i4", "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+class _PlanHandle:
+    def __init__(self, handle):
+        self.handle = handle
+
+    def __del__(self):
+        try:
+            from . import _lib
+            if self.handle:
+                _lib.load().fem_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+_TABLES = {"brow_ptr": 0, "bcol": 1, "indptr": 2, "indices": 3, "corner_pos": 4, "nc_ptr": 5, "nc": 6, "gdesc": 7, "src": 8,
+           "src_ptr": 9, "_tperm": 10, "m_sb": 11, "m_se": 12, "m_ent": 13, "m_add": 14, "edst": 15, "erow": 16}
+
+
+def build_plan_native(cells, num_nodes, vec):
+    """AssemblyPlan whose tables are built by fem_plan_create on the device of `cells` (int32 CUDA tensor (C, N))."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    cells = cells.to(torch.int32).contiguous()
+    C, N = cells.shape
+    handle = ctypes.c_void_p()
+    _lib.check(lib.fem_plan_create(_lib.ptr(cells), C, num_nodes, N, vec, _lib.stream_ptr(), ctypes.byref(handle)))
+    owner = _PlanHandle(handle)
+    tables = {}
+    for name, which in _TABLES.items():
+        p, n = ctypes.c_void_p(), ctypes.c_int64()
+        _lib.check(lib.fem_plan_table(handle, which, ctypes.byref(p), ctypes.byref(n)))
+        if n.value == 0:
+            tables[name] = torch.zeros(0, dtype=torch.int32, device=cells.device)
+        else:
+            tables[name] = torch.as_tensor(_DeviceTable(p.value, n.value, owner), device=cells.device)
+    plan = AssemblyPlan(num_nodes=num_nodes, num_cells=C, nodes_per_cell=N, vec=vec, eorder=None, **tables)
+    plan.native = owner
+    return plan
+
+
+def native_entry_meta(plan, bc_flag):
+    """emeta of fem_gather_csr from the library (fem_plan_entry_meta) for a plan built by build_plan_native."""
+    from . import _lib
+    emeta = torch.empty((plan.m_ent.numel(), 4), dtype=torch.int32, device=plan.bcol.device)
+    flag = None if bc_flag is None else bc_flag.to(torch.uint8).contiguous()
+    _lib.check(_lib.load().fem_plan_entry_meta(plan.native.handle, _lib.ptr(flag), _lib.ptr(emeta), _lib.stream_ptr()))
+    return emeta

@@ -27,7 +27,7 @@ from . import _lib, laws, logger
 from .fe import FiniteElement, evaluate_point_fn
 from .generate_mesh import Mesh
 from .patch_plan import DEFAULT_CONFIG, build_patch_plan
-from .plan import build_plan
+from .plan import build_plan, build_plan_native
 from .stage_plan import StageConfig, build_stage_plan
 
 
@@ -94,7 +94,11 @@ class Problem:
         self._points = torch.from_numpy(fe.points).to(dev)
         self._cells = torch.from_numpy(fe.cells).to(dev)
         self._ref = torch.from_numpy(np.concatenate([fe.shape_grads_ref.reshape(-1), fe.quad_weights])).to(dev)
-        self.plan = build_plan(self._cells, fe.num_total_nodes, fe.vec)
+        # the plan is built by the library (fem_plan_create, csrc/plan.cu); FEM_PLAN=torch selects the torch construction
+        # of plan.py (the one the CPU tests exercise), both give identical tables
+        import os
+        builder = build_plan if os.environ.get('FEM_PLAN', 'native') == 'torch' else build_plan_native
+        self.plan = builder(self._cells, fe.num_total_nodes, fe.vec)
         self._Ke = None
         self._Re = None
         self._patch_plan = None

@@ -4,6 +4,8 @@ C ABI of include/fem_b200.h), against the CPU oracle on the same inputs.
 Tolerances (BASELINE.json north_star): CSR pattern / index arrays / BC masks bit-exact; residual and
 Jacobian values <= 1e-12 relative max-norm; solutions and adjoint gradients <= 1e-8 relative.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -475,6 +477,53 @@ def test_ring_assembly_recycles_rows_correctly(ring_kb, tile, slack, margin, mon
         prob.newton_update([sol])
         assert torch.equal(jf.get_A(prob).data, data)
     prob.check_assembly_status()
+
+
+@pytest.mark.parametrize("case", ["box", "renumbered", "quad4", "hex27", "cylinder"])
+def test_native_plan_equals_torch_plan(case):
+    """fem_plan_create (csrc/plan.cu: Thrust on raw device buffers) must produce exactly the tables of the torch construction
+    (jax_fem_b200/plan.py, the one the CPU tests pin against the oracle's COO pattern): pattern, node-block graph, corner
+    order, gather schedule, transpose map and, for a Dirichlet mask, the emeta rows -- bit for bit."""
+    import jax_fem_b200 as jf
+    from jax_fem_b200.plan import build_plan, build_plan_native
+    rng = np.random.default_rng(4)
+    vec = 3
+    if case == "quad4":
+        m = jf.rectangle_mesh(13, 9, 1.3, 0.9)
+        cells, n_nodes, vec = m.cells_dict['quad'], len(m.points), 2
+    elif case == "hex27":
+        m = jf.box_mesh_hex27(4, 3, 3, 1., 1., 1.)
+        cells, n_nodes = m.cells_dict['hexahedron27'], len(m.points)
+    elif case == "cylinder":
+        g = cases.load_golden("linear_elasticity_cylinder")
+        cells, n_nodes = g["cells"], len(g["points"])
+    else:
+        m = jf.box_mesh(11, 7, 5, 1., 1., 1.)
+        cells, n_nodes = m.cells_dict['hexahedron'], len(m.points)
+        if case == "renumbered":
+            perm = rng.permutation(n_nodes)
+            cells = perm[cells][rng.permutation(len(cells))]
+    ct = torch.from_numpy(np.ascontiguousarray(cells).astype(np.int32)).cuda()
+    a, b = build_plan(ct, n_nodes, vec), build_plan_native(ct, n_nodes, vec)
+    for name in ("brow_ptr", "bcol", "src_ptr", "src", "nc_ptr", "nc", "corner_pos", "indptr", "indices", "gdesc", "m_sb", "m_se",
+                 "m_ent", "m_add", "edst", "erow"):
+        assert torch.equal(getattr(a, name).to(torch.int32), getattr(b, name)), name
+    assert torch.equal(a.tperm, b.tperm)
+    flag = torch.from_numpy((rng.uniform(size=n_nodes * vec) < 0.2).astype(np.uint8)).cuda()
+    assert torch.equal(a.entry_meta(flag), b.entry_meta(flag)) and torch.equal(a.entry_meta(None), b.entry_meta(None))
+    assert (a.nnz, a.nnzb, a.n_gather_blocks) == (b.nnz, b.nnzb, b.n_gather_blocks)
+
+
+def test_c_abi_pipeline_without_torch():
+    """plan -> element kernel -> gathers -> Dirichlet rows -> Jacobi-CG through ctypes on cudaMalloc'd buffers, in an
+    interpreter that never imports torch (tests/no_torch_pipeline.py), against the oracle."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "no_torch_pipeline.py")], cwd=root, capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-3000:])
+    assert "C_ABI_PIPELINE_OK" in out.stdout
 
 
 def test_csr_diagonal_beyond_2_30_nonzeros():
