@@ -4,7 +4,7 @@ Mirror of the interface of jax_fem/basis.py (get_elements :19-114, get_shape_val
 :141-175, get_face_shape_vals_and_grads :178-250).  The reference obtains these numbers from
 fenics-basix; here they are closed-form tensor products of 1-D Lagrange polynomials on the
 lattice {0, 1/p, ..., 1} evaluated at Gauss-Legendre points, emitted directly in meshio/VTK node
-order (so no ``re_order`` gather is needed afterwards).  tests/test_host_tables.py checks them
+order (so no ``re_order`` gather is needed afterwards).  tests/test_host_logic.py checks them
 entry by entry against the oracle's basix restatement.
 """
 import numpy as np

@@ -16,27 +16,30 @@ from . import logger
 from .basis import get_face_shape_vals_and_grads, get_shape_vals_and_grads
 from .generate_mesh import Mesh
 
-_SAMPLE = 24
-
-
-def _sample_ids(n):
-    if n <= 2 * _SAMPLE:
-        return np.arange(n)
-    rng = np.random.default_rng(12345)
-    return np.unique(np.concatenate([np.arange(_SAMPLE // 2), rng.integers(0, n, _SAMPLE), [n - 1]]))
-
-
 def _arg_count(fn):
-    return fn.__code__.co_argcount
+    """Number of positional parameters of a user predicate (functions, functools.partial, callable objects)."""
+    code = getattr(fn, '__code__', None)
+    if code is not None:
+        return code.co_argcount
+    import inspect
+    params = inspect.signature(fn).parameters.values()
+    return sum(p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD) for p in params)
+
+
+def _pointwise_equal(call_one, batch, n, same):
+    """True when the batched result equals the per-point calls at EVERY point (the reference vmaps per point,
+    fe.py:252; a predicate that mixes per-point values with reductions over the batch must not slip through)."""
+    return all(same(call_one(i), batch[i]) for i in range(n))
 
 
 def evaluate_location_fn(fn, points, inds=None):
     """Boolean flag per point for a reference-style predicate ``fn(point[, ind])``.
 
-    The reference vmaps the predicate over points (fe.py:252, 312-318).  Here the predicate is first
-    called once on the transposed array (point[d] becomes the vector of d-coordinates, which is what
-    NumPy-style predicates such as ``np.isclose(point[0], 0., atol=1e-5)`` need), the result is
-    verified against per-point calls on a sample, and the slow per-point loop is used otherwise.
+    The reference vmaps the predicate over points (fe.py:252, 312-318).  Here the predicate is first called once on
+    the transposed array (point[d] becomes the vector of d-coordinates, which is what NumPy-style predicates such as
+    ``np.isclose(point[0], 0., atol=1e-5)`` need).  The batched result is only used if it agrees with the per-point
+    call at every point where either says True and on a deterministic spread of the others; a predicate that cannot be
+    batched is evaluated point by point.
     """
     n = len(points)
     inds = np.arange(n) if inds is None else inds
@@ -47,30 +50,41 @@ def evaluate_location_fn(fn, points, inds=None):
     try:
         flags = np.asarray(call(points.T, inds))
         if flags.shape == (n,) and flags.dtype == np.bool_:
-            ids = _sample_ids(n)
-            if all(bool(call(points[i], inds[i])) == bool(flags[i]) for i in ids):
-                return flags
+            # Dirichlet / load sets are small against the mesh: check every selected point, every point of a shuffled copy
+            # of the batch (a reduction over the batch changes with the batch), and a spread of unselected points
+            perm = np.random.default_rng(12345).permutation(n)
+            shuffled = np.asarray(call(points[perm].T, inds[perm]))
+            if shuffled.shape == (n,) and np.array_equal(shuffled, flags[perm]):
+                check = np.union1d(np.flatnonzero(flags)[:4096], np.linspace(0, n - 1, min(n, 256)).astype(np.int64))
+                if all(bool(call(points[i], inds[i])) == bool(flags[i]) for i in check):
+                    return flags
     except Exception:
         pass
     return np.array([bool(call(points[i], inds[i])) for i in range(n)], dtype=bool)
 
 
 def evaluate_point_fn(fn, points, out_shape=()):
-    """Values of ``fn(point)`` for every point -> (n, *out_shape), vectorised like evaluate_location_fn."""
+    """Values of ``fn(point)`` for every point -> (n, *out_shape), batched like evaluate_location_fn (same safeguards:
+    the batched values must not change when the batch is shuffled and must equal per-point calls on a spread of points)."""
     n = len(points)
     if n == 0:
         return np.zeros((0,) + tuple(out_shape))
-    try:
-        val = np.asarray(fn(points.T), dtype=np.float64)
+
+    def batched(pts):
+        val = np.asarray(fn(pts.T), dtype=np.float64)
         if val.shape == tuple(out_shape):
-            full = np.broadcast_to(val, (n,) + tuple(out_shape)).copy()
-        elif val.shape == tuple(out_shape) + (n,):
-            full = np.moveaxis(val, -1, 0).copy()
-        else:
-            raise ValueError
-        ids = _sample_ids(n)
-        if all(np.allclose(np.asarray(fn(points[i]), dtype=np.float64), full[i], rtol=1e-14, atol=0) for i in ids):
-            return full
+            return np.broadcast_to(val, (len(pts),) + tuple(out_shape)).copy()
+        if val.shape == tuple(out_shape) + (len(pts),):
+            return np.moveaxis(val, -1, 0).copy()
+        raise ValueError
+
+    try:
+        full = batched(points)
+        perm = np.random.default_rng(12345).permutation(n)
+        if np.array_equal(batched(points[perm]), full[perm]):
+            check = np.linspace(0, n - 1, min(n, 256)).astype(np.int64)
+            if all(np.allclose(np.asarray(fn(points[i]), dtype=np.float64), full[i], rtol=1e-14, atol=0) for i in check):
+                return full
     except Exception:
         pass
     return np.array([np.asarray(fn(p), dtype=np.float64) for p in points]).reshape((n,) + tuple(out_shape))

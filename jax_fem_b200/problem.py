@@ -70,10 +70,15 @@ class Problem:
             if len(self.mesh) != 1:
                 raise NotImplementedError("multi-variable problems are outside the B200 hot path (SURVEY.md 8)")
             self.mesh, self.vec, self.ele_type = self.mesh[0], self.vec[0], self.ele_type[0]
-            for name in ('quadrature_rule', 'quadrature_order', 'dirichlet_bc_info'):
+            for name in ('quadrature_rule', 'quadrature_order'):
                 v = getattr(self, name)
-                if isinstance(v, list) and name != 'dirichlet_bc_info':
+                if isinstance(v, list):
                     setattr(self, name, v[0])
+            # the reference indexes dirichlet_bc_info[i] per variable (problem.py:56-75): [info] -> info
+            d = self.dirichlet_bc_info
+            if isinstance(d, list) and len(d) == 1 and (d[0] is None or (isinstance(d[0], (list, tuple)) and len(d[0]) == 3
+                                                                           and isinstance(d[0][0], (list, tuple)))):
+                self.dirichlet_bc_info = d[0]
         for hook in ('get_universal_kernel', 'get_universal_kernels_surface'):
             if hasattr(self, hook):
                 raise NotImplementedError(f"{hook} is not registered on the B200 hot path; it does not fall back")
@@ -172,25 +177,33 @@ class Problem:
 
     # ---- Dirichlet rows, merged with the reference's "later groups overwrite" rule --------------------
     def bc_data(self):
-        """(rows int32, vals float64, flag uint8 per dof) on the device; rebuilt when fe.*_list objects change
-        (same identity test as _PetscTangentCache._refresh_bc_rows_if_needed, solver.py:494-520)."""
+        """(rows int32, vals float64, flag uint8 per dof) on the device.  The row set (and everything derived from it) is
+        cached on the identity of the index arrays, as _PetscTangentCache._refresh_bc_rows_if_needed does
+        (solver.py:494-520); the VALUES are read from fe.vals_list on every call, as the reference's apply_bc_vec does
+        (solver.py:297-301), so editing them in place takes effect."""
         fe = self.fes[0]
-        key = tuple(id(a) for lst in (fe.node_inds_list, fe.vec_inds_list, fe.vals_list) for a in lst)
+        key = tuple(id(a) for lst in (fe.node_inds_list, fe.vec_inds_list) for a in lst)
         if self._bc_cache is None or self._bc_cache[0] != key:
-            n = self.num_total_dofs_all_vars
-            val = np.zeros(n)
-            flag = np.zeros(n, dtype=np.uint8)
+            flag = np.zeros(self.num_total_dofs_all_vars, dtype=np.uint8)
             for i in range(len(fe.node_inds_list)):
-                rows = np.asarray(fe.node_inds_list[i]) * fe.vec + np.asarray(fe.vec_inds_list[i])
-                val[rows] = np.asarray(fe.vals_list[i], dtype=np.float64)          # last group wins
-                flag[rows] = 1
+                flag[np.asarray(fe.node_inds_list[i]) * fe.vec + np.asarray(fe.vec_inds_list[i])] = 1
             rows = np.flatnonzero(flag).astype(np.int32)
             dev = self.device
             flag_dev = torch.from_numpy(flag).to(dev)
-            self._bc_cache = (key, torch.from_numpy(rows).to(dev), torch.from_numpy(val[rows]).to(dev), flag_dev,
-                              (fe.node_inds_list, fe.vec_inds_list, fe.vals_list),   # keep refs alive
-                              self.plan.entry_meta(flag_dev))
-        return self._bc_cache[1], self._bc_cache[2], self._bc_cache[3]
+            # position of every group's entries in the merged, ascending row list
+            pos = [np.searchsorted(rows, np.asarray(fe.node_inds_list[i]) * fe.vec + np.asarray(fe.vec_inds_list[i]))
+                   for i in range(len(fe.node_inds_list))]
+            self._bc_cache = [key, torch.from_numpy(rows).to(dev), None, flag_dev,
+                              (list(fe.node_inds_list), list(fe.vec_inds_list)),   # keep the arrays alive: ids stay unique
+                              self.plan.entry_meta(flag_dev), pos, None]
+        c = self._bc_cache
+        host_vals = np.zeros(c[1].numel())
+        for i, pos in enumerate(c[6]):
+            host_vals[pos] = np.asarray(fe.vals_list[i], dtype=np.float64)      # later groups overwrite earlier ones
+        if c[7] is None or not np.array_equal(c[7], host_vals):
+            c[7] = host_vals
+            c[2] = torch.from_numpy(host_vals).to(self.device)
+        return c[1], c[2], c[3]
 
     def entry_meta(self):
         """Per-entry (source range, CSR destination, row stride / diagonal / Dirichlet bits) of the CSR gather kernel."""

@@ -10,6 +10,7 @@ the documented ``custom_solver`` hook.  ``petsc_solver`` / ``amgx_solver`` / ``s
 arc-length and dynamic relaxation are outside the hot path and raise NotImplementedError.
 """
 import math
+import threading
 import time
 
 import numpy as np
@@ -22,24 +23,26 @@ from .sparse import CSRMatrix
 # logging helpers (same buckets as the reference: local_assembly / global_matrix / linear)
 
 
-def _timing_record(timing, name, dt):
-    timing[name] += dt
+class _Stopwatch:
+    """Wall time per bucket of a Newton solve; the buckets are the ones the reference reports (local_assembly: element
+    kernels, global_matrix: CSR assembly, linear: Krylov solve)."""
+    BUCKETS = ('local_assembly', 'global_matrix', 'linear')
 
+    def __init__(self):
+        self.seconds = dict.fromkeys(self.BUCKETS, 0.)
+        self._t0 = time.perf_counter()
 
-def _log_newton_iter_summary(iter_num, local_s, global_s, res_val, rel_res_val, linear_s=None):
-    logger.info("  iter %d  nonlinear residual: L2 norm = %.3g (relative to initial = %.3g)", iter_num, res_val, rel_res_val)
-    if linear_s is None:
-        logger.info("           timing: local assembly %6.3f s, global matrix %6.3f s", local_s, global_s)
-    else:
-        logger.info("           timing: linear solve %6.3f s, local assembly %6.3f s, global matrix %6.3f s",
-                    linear_s, local_s, global_s)
+    def add(self, bucket, dt):
+        self.seconds[bucket] += dt
 
+    def report_iteration(self, k, res, rel, spent):
+        parts = ", ".join(f"{name} {spent[name]:.3f} s" for name in self.BUCKETS if name in spent)
+        logger.info("Newton %d: |res| = %.3g (%.3g of the first one); %s", k, res, rel, parts)
 
-def _log_timing_table(n_iters, parts, wall_s):
-    logger.info("Timing summary -- %d Newton iter, %.3f s wall", n_iters, wall_s)
-    for key, label in (('local_assembly', 'local'), ('global_matrix', 'global'), ('linear', 'linear')):
-        dt = parts[key]
-        logger.info("  %-8s %7.3f s  %5.1f%%", label, dt, 100. * dt / wall_s if wall_s > 0 else 0.)
+    def report_total(self, n_iters):
+        wall = time.perf_counter() - self._t0
+        share = "; ".join(f"{name} {dt:.3f} s ({100. * dt / wall if wall > 0 else 0.:.0f}%)" for name, dt in self.seconds.items())
+        logger.info("Newton finished after %d iteration(s) in %.3f s: %s", n_iters, wall, share)
 
 
 def _sync_time():
@@ -140,12 +143,14 @@ _workspaces = {}
 
 
 def _krylov_workspace(n, device):
-    key = (n, device)
-    if key not in _workspaces:
-        size = _lib.load().fem_krylov_workspace(n)
-        _workspaces.clear()
-        _workspaces[key] = torch.zeros(size, dtype=torch.float64, device=device)
-    return _workspaces[key]
+    """Scratch of the device-resident Krylov solvers (scalars, ticket counter, 8 vectors), one per (thread, stream, size):
+    concurrent solves from different threads or streams never share it.  Only the most recent size of a thread is kept."""
+    key = (threading.get_ident(), torch.cuda.current_stream(device).cuda_stream, device)
+    hit = _workspaces.get(key)
+    if hit is None or hit[0] != n:
+        hit = (n, torch.zeros(_lib.load().fem_krylov_workspace(n), dtype=torch.float64, device=device))
+        _workspaces[key] = hit
+    return hit[1]
 
 
 def jax_solve(A, b, x0, precond, method='bicgstab', tol=1e-10, atol=1e-10, maxiter=10000, check_every=25,
@@ -190,27 +195,30 @@ def linear_solver(A, b, x0, linear_options):
 ################################################################################
 # Newton
 
-_METHOD_KEYS = frozenset({'newton', 'arc_length', 'dynamic_relax'})
-_LINEAR_OPTION_KEYS = frozenset({'jax_solver', 'amgx_solver', 'spsolve_solver', 'petsc_solver', 'custom_solver'})
-_NEWTON_OPTION_KEYS = frozenset({'tol', 'rel_tol', 'line_search_flag', 'initial_guess'})
+# option schema of solver(problem, solver_options) (jax_fem/solver.py:1079-1106): either one nonlinear method holding its
+# own configuration, or -- the older flat form -- Newton options and linear back-ends side by side
+NONLINEAR_METHODS = ('newton', 'arc_length', 'dynamic_relax')
+LINEAR_BACKENDS = ('jax_solver', 'amgx_solver', 'spsolve_solver', 'petsc_solver', 'custom_solver')
+NEWTON_SETTINGS = ('tol', 'rel_tol', 'line_search_flag', 'initial_guess')
 
 
 def _resolve_solver_options(solver_options):
-    """(method, cfg); legacy flat dicts become Newton (solver.py:1088-1106)."""
-    opts = solver_options or {}
-    methods = [m for m in _METHOD_KEYS if m in opts]
-    if not methods:
-        linear = {k: opts[k] for k in _LINEAR_OPTION_KEYS if k in opts}
-        cfg = {k: opts[k] for k in _NEWTON_OPTION_KEYS if k in opts}
-        if linear:
-            cfg['linear'] = linear
-        return 'newton', cfg
-    if len(methods) > 1:
-        raise ValueError(f"Pick one nonlinear method, got {methods}.")
-    method = methods[0]
-    if not isinstance(opts[method], dict):
-        raise ValueError(f"solver_options['{method}'] must be a dict.")
-    return method, opts[method]
+    """-> (nonlinear method, its configuration).  A flat dictionary is read as a Newton configuration whose linear
+    back-ends are collected under 'linear'."""
+    given = dict(solver_options or {})
+    chosen = [name for name in NONLINEAR_METHODS if name in given]
+    if len(chosen) > 1:
+        raise ValueError(f"solver_options names {len(chosen)} nonlinear methods ({', '.join(chosen)}); exactly one is allowed")
+    if chosen:
+        cfg = given[chosen[0]]
+        if not isinstance(cfg, dict):
+            raise ValueError(f"solver_options[{chosen[0]!r}] has to be a dictionary of settings, got {type(cfg).__name__}")
+        return chosen[0], cfg
+    cfg = {name: given[name] for name in NEWTON_SETTINGS if name in given}
+    backends = {name: given[name] for name in LINEAR_BACKENDS if name in given}
+    if backends:
+        cfg['linear'] = backends
+    return 'newton', cfg
 
 
 def newton_step(problem, res_vec, A, dofs, newton_cfg, timing):
@@ -223,32 +231,29 @@ def newton_step(problem, res_vec, A, dofs, newton_cfg, timing):
     t0 = _sync_time()
     inc = linear_solver(A, b, x0, newton_cfg.get('linear', {}))
     linear_s = _sync_time() - t0
-    _timing_record(timing, 'linear', linear_s)
+    timing['linear'] += linear_s
     if newton_cfg.get('line_search_flag', False):
         return line_search(problem, dofs, inc), linear_s
     return dofs + inc, linear_s
 
 
-def line_search(problem, dofs, inc):
-    """Step halving of the reference (solver.py:424-462): alpha = 1, then up to three halvings, each kept only while the
-    norm of the residual with Dirichlet rows keeps decreasing.  Residual-only evaluations (no tangent)."""
-    def res_norm_fn(alpha):
-        d = dofs + alpha * inc
-        res = problem.compute_residual(problem.unflatten_fn_sol_list(d))[0].reshape(-1)
-        return _norm(apply_bc_vec(res, d, problem))
+def line_search(problem, dofs, inc, halvings=3):
+    """Backtracking of the reference (solver.py:424-462): try the full Newton step, then halve the step up to three times
+    and keep halving only while the norm of the residual (Dirichlet rows included) still decreases.  Uses residual-only
+    evaluations (no tangent)."""
+    def norm_at(step):
+        trial = dofs + step * inc
+        res = problem.compute_residual(problem.unflatten_fn_sol_list(trial))[0].reshape(-1)
+        return _norm(apply_bc_vec(res, trial, problem))
 
-    alpha = 1.
-    res_norm = res_norm_fn(alpha)
-    for i in range(3):
-        alpha *= 0.5
-        res_norm_half = res_norm_fn(alpha)
-        logger.debug("Line search (step halving): i = %d, alpha = %g, res_norm = %g, res_norm_half = %g",
-                     i, alpha, res_norm, res_norm_half)
-        if res_norm_half > res_norm:
-            alpha *= 2.
+    step, best = 1., norm_at(1.)
+    for attempt in range(halvings):
+        candidate = norm_at(0.5 * step)
+        logger.debug("line search %d: step %g -> |res| %g, step %g -> |res| %g", attempt, step, best, 0.5 * step, candidate)
+        if candidate > best:
             break
-        res_norm = res_norm_half
-    return dofs + alpha * inc
+        step, best = 0.5 * step, candidate
+    return dofs + step * inc
 
 
 def solver(problem, solver_options={}):
@@ -261,8 +266,8 @@ def solver(problem, solver_options={}):
         raise NotImplementedError(f"linear back-end(s) {sorted(unsupported)} are outside the B200 hot path: only "
                                   "'jax_solver' (device Jacobi-BiCGSTAB/CG) and 'custom_solver' exist; no fallback")
     logger.info("Solving the nonlinear problem...")
-    timing = {'local_assembly': 0., 'global_matrix': 0., 'linear': 0.}
-    wall_start = time.perf_counter()
+    watch = _Stopwatch()
+    timing = watch.seconds
     n = problem.num_total_dofs_all_vars
     if 'initial_guess' in cfg:
         dofs = torch.cat([problem._as_sol([g]).reshape(-1) for g in cfg['initial_guess']]).clone()
@@ -275,19 +280,19 @@ def solver(problem, solver_options={}):
         t0 = _sync_time()
         res_list = problem.newton_update(problem.unflatten_fn_sol_list(dofs))
         local_s = _sync_time() - t0
-        _timing_record(timing, 'local_assembly', local_s)
+        watch.add('local_assembly', local_s)
         res_vec = apply_bc_vec(res_list[0].reshape(-1), dofs, problem)
         t0 = _sync_time()
         A = get_A(problem)
         global_s = _sync_time() - t0
-        _timing_record(timing, 'global_matrix', global_s)
+        watch.add('global_matrix', global_s)
         return res_vec, A, local_s, global_s
 
     res_vec, A, local_s, global_s = newton_update_helper(dofs)
     res_val = _norm(res_vec)
     res_val_initial = res_val
     rel_res_val = res_val / res_val_initial if res_val_initial > 0 else 0.
-    _log_newton_iter_summary(0, local_s, global_s, res_val, rel_res_val)
+    watch.report_iteration(0, res_val, rel_res_val, {'local_assembly': local_s, 'global_matrix': global_s})
     n_iters = 0
     while (rel_res_val > rel_tol) and (res_val > tol):
         n_iters += 1
@@ -295,11 +300,11 @@ def solver(problem, solver_options={}):
         res_vec, A, local_s, global_s = newton_update_helper(dofs)
         res_val = _norm(res_vec)
         rel_res_val = res_val / res_val_initial
-        _log_newton_iter_summary(n_iters, local_s, global_s, res_val, rel_res_val, linear_s)
+        watch.report_iteration(n_iters, res_val, rel_res_val, {'linear': linear_s, 'local_assembly': local_s, 'global_matrix': global_s})
     assert math.isfinite(res_val), "res_val contains NaN, stop the program!"
     assert bool(torch.isfinite(dofs).all()), "dofs contains NaN, stop the program!"
     problem.last_newton_info = {'iterations': n_iters, 'res_val': res_val, 'timing': dict(timing)}
-    _log_timing_table(n_iters, timing, time.perf_counter() - wall_start)
+    watch.report_total(n_iters)
     return problem.unflatten_fn_sol_list(dofs)
 
 
@@ -340,6 +345,10 @@ def ad_wrapper(problem, solver_options={}, adjoint_solver_options={}):
     ``set_params(params)`` (user code, torch ops) builds ``problem.internal_vars``; the solve is a custom
     autograd Function whose backward is the implicit adjoint, so ``objective(fwd_pred(params)).backward()``
     fills ``params.grad`` exactly as ``jax.grad`` does in the reference."""
+
+    if problem.ele_type == 'HEX27':
+        raise NotImplementedError("ad_wrapper: the parameter-gradient kernel is registered for HEX8 and QUAD4 only (HEX27 + SIMP "
+                                  "would fail in backward); it does not fall back")
 
     class _Solve(torch.autograd.Function):
         @staticmethod
