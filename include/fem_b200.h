@@ -199,6 +199,18 @@ int fem_patch_chunks_host(int64_t n_patches, const int64_t* cell_ptr_host, const
 int fem_gather_csr(int vec, int nn, int64_t n_blocks, const int32_t* gdesc, const int32_t* emeta,
                    const int32_t* src, const double* Ke, double* data, void* stream);
 
+/* The same two steps for HEX8 / vec 3 / {linear elasticity, SIMP, Neo-Hookean} with the element tangents staged in
+ * TILE-MAJOR rows: the FP64 tensor-core accumulator fragments are stored straight from registers (row of corner (c, a) =
+ * 9 tiles (I, J) of 8 doubles b = 0..7, at corner_pos[c*8 + a], 16-byte aligned), and for the isotropic laws the rows hold
+ * G = sum_q E_q w_q g_a (x) g_b; K = lam' G + mu' G^T + mu' tr(G) I is applied by the gather after the sum over the cells.
+ * post_host[3] (written by fem_element_tiles, passed to fem_gather_csr_tiles): {apply the map (0/1), lam', mu'}.
+ * All other arguments as in fem_element_residual_jacobian / fem_gather_csr.                                               */
+int fem_element_tiles(int law_id, const double* law_params_host, const double* points, const int32_t* cells,
+                      int64_t n_cells, const double* sol, const double* internal_var, const double* ref_tables,
+                      const int32_t* corner_pos, double* Ke_tiles, double* Re, double* post_host, void* stream);
+int fem_gather_csr_tiles(int64_t n_blocks, const int32_t* gdesc, const int32_t* emeta, const int32_t* src,
+                         const double* Ke_tiles, double* data, const double* post_host, void* stream);
+
 /* residual scatter-add of problem.py:426-437 as a per-node gather: nc_ptr (n_nodes+1) / nc codes
  * c*NN + a ascending; res = sum Re + f_ext (f_ext may be NULL).                                  */
 int fem_gather_residual(int vec, int nn, int64_t n_nodes, const int32_t* nc_ptr, const int32_t* nc,

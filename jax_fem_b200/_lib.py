@@ -33,6 +33,8 @@ _SIGNATURES = {
     "fem_staged_status": (_i, [_vp, _vp, _vp]),
     "fem_patch_chunks_host": (_i, [_i64, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "fem_gather_csr": (_i, [_i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fem_element_tiles": (_i, [_i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fem_gather_csr_tiles": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fem_gather_residual": (_i, [_i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fem_apply_bc_vec": (_i, [_i64, _vp, _vp, _d, _vp, _vp, _vp]),
     "fem_bc_initial_guess": (_i, [_i64, _i64, _vp, _vp, _vp, _vp, _vp]),

@@ -53,10 +53,12 @@ struct GatherMeta {
   int sb[EPT], se[EPT], dst[EPT], info[EPT];
 };
 
-template <int VEC, int NN>
+// TILES: the rows come from fem_element_tiles (tile-major: block (row r, b) = 9 doubles at r*72 + IJ*8 + b) and, with
+// post.x != 0, hold G: the isotropic map K = lam' G + mu' G^T + mu' tr(G) I (post.y = lam', post.z = mu') is applied to the sum.
+template <int VEC, int NN, bool TILES>
 __global__ void __launch_bounds__(kGatherThreads) gather_csr_kernel(
     int n_items, const int32_t* __restrict__ gdesc, const int4* __restrict__ emeta, const int32_t* __restrict__ src,
-    const double* __restrict__ Ke, double* __restrict__ data) {
+    const double* __restrict__ Ke, double* __restrict__ data, const double3 post) {
   constexpr int VV = VEC * VEC;
   constexpr int ROW = (NN * VV + 1) / 2 * 2;                      // doubles per corner row block (16-byte multiple)
   constexpr int MAXC = GatherCfg<NN>::CORNERS + GatherCfg<NN>::TAIL;
@@ -145,9 +147,27 @@ __global__ void __launch_bounds__(kGatherThreads) gather_csr_kernel(
       for (int j = 0; j < VV; ++j) res[r][j] = 0.0;
       for (int sidx = cur.sb[r] - cur.S0; sidx < cur.se[r] - cur.S0; ++sidx) {
         const int so = s_off[sidx];
-        const double* blk = (ROW == NN * VV) ? sh + so * VV : sh + (so / NN) * ROW + (so % NN) * VV;
+        if constexpr (TILES) {
+          const double* blk = sh + (so / NN) * ROW + (so % NN);
 #pragma unroll
-        for (int j = 0; j < VV; ++j) res[r][j] += blk[j];
+          for (int j = 0; j < VV; ++j) res[r][j] += blk[j * NN];
+        } else {
+          const double* blk = (ROW == NN * VV) ? sh + so * VV : sh + (so / NN) * ROW + (so % NN) * VV;
+#pragma unroll
+          for (int j = 0; j < VV; ++j) res[r][j] += blk[j];
+        }
+      }
+      if constexpr (TILES && VEC == 3) {
+        if (post.x != 0.0) {     // linear: applied to the sum (or to each half of a split entry)
+          double G[VV];
+#pragma unroll
+          for (int j = 0; j < VV; ++j) G[j] = res[r][j];
+          const double tr = post.z * (G[0] + G[4] + G[8]);
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int kk = 0; kk < 3; ++kk) res[r][i * 3 + kk] = post.y * G[i * 3 + kk] + post.z * G[kk * 3 + i] + (i == kk ? tr : 0.0);
+        }
       }
     }
     __syncthreads();
@@ -322,13 +342,13 @@ extern "C" int fem_device_count(void) {
 
 namespace femb200 {
 namespace {
-template <int VEC, int NN>
+template <int VEC, int NN, bool TILES = false>
 int launch_gather(int n_items, const int32_t* gdesc, const int32_t* emeta, const int32_t* src, const double* Ke,
-                  double* data, cudaStream_t st) {
+                  double* data, cudaStream_t st, double3 post = make_double3(0., 0., 0.)) {
   constexpr int MAXC = GatherCfg<NN>::CORNERS + GatherCfg<NN>::TAIL;
   constexpr int ROW = (NN * VEC * VEC + 1) / 2 * 2;
   const size_t smem = sizeof(double) * 2 * MAXC * ROW + sizeof(int) * MAXC * NN;
-  auto k = gather_csr_kernel<VEC, NN>;
+  auto k = gather_csr_kernel<VEC, NN, TILES>;
   // persistent grid: resident CTAs x SMs, cached per device (the shared-memory attribute is per device too)
   static int grids[64] = {0};
   int dev = 0;
@@ -341,7 +361,7 @@ int launch_gather(int n_items, const int32_t* gdesc, const int32_t* emeta, const
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kGatherThreads, smem);
     grid = (per_sm < 1 ? 1 : per_sm) * sms;
   }
-  k<<<grid < n_items ? grid : n_items, kGatherThreads, smem, st>>>(n_items, gdesc, reinterpret_cast<const int4*>(emeta), src, Ke, data);
+  k<<<grid < n_items ? grid : n_items, kGatherThreads, smem, st>>>(n_items, gdesc, reinterpret_cast<const int4*>(emeta), src, Ke, data, post);
   FEM_LAUNCH_CHECK();
   return FEM_OK;
 }
@@ -363,6 +383,16 @@ extern "C" int fem_gather_csr(int vec, int nn, int64_t n_blocks, const int32_t* 
 #undef FEM_G
   set_error("fem_gather_csr: unregistered (vec=%d, nodes/cell=%d)", vec, nn);
   return FEM_EINVAL;
+}
+
+extern "C" int fem_gather_csr_tiles(int64_t n_blocks, const int32_t* gdesc, const int32_t* emeta, const int32_t* src,
+                                    const double* Ke_tiles, double* data, const double* post_host, void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(gdesc && emeta && src && Ke_tiles && data && post_host, "null pointer");
+  FEM_REQUIRE((reinterpret_cast<uintptr_t>(emeta) & 15) == 0, "emeta must be 16-byte aligned");
+  if (n_blocks == 0) return FEM_OK;
+  return launch_gather<3, 8, true>((int)n_blocks, gdesc, emeta, src, Ke_tiles, data, (cudaStream_t)stream,
+                                   make_double3(post_host[0], post_host[1], post_host[2]));
 }
 
 extern "C" int fem_gather_residual(int vec, int nn, int64_t n_nodes, const int32_t* nc_ptr, const int32_t* nc,

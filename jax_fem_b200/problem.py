@@ -342,8 +342,18 @@ class Problem:
         self.bc_data()
         return self._A_data if self._A_bc_key == self._bc_cache[0] else None
 
-    def _run_element_kernel(self, sol, jac):
+    def tiles_enabled(self):
+        """HEX8 / vec 3 / {linear elasticity, SIMP, Neo-Hookean} on the FP64 tensor cores: the element tangents are staged as
+        tile-major rows written straight from the accumulator fragments (fem_element_tiles) and the isotropic map is applied by
+        the CSR gather after the sum (fem_gather_csr_tiles).  FEM_ELEMENT_PATH=dfma / blocks selects the reference-layout
+        kernels instead (A/B measurements; all paths are parity-tested)."""
+        import os
+        return (os.environ.get('FEM_ELEMENT_PATH', 'tiles') == 'tiles' and self.ele_type == 'HEX8' and self.fes[0].vec == 3
+                and self._law.law_id in (laws.LinearElasticity.law_id, laws.SIMP.law_id, laws.NeoHookean.law_id))
+
+    def _run_element_kernel(self, sol, jac, tiles=None):
         fe = self.fes[0]
+        tiles = (jac and self.tiles_enabled()) if tiles is None else tiles
         if self._Re is None:
             self._Re = torch.empty((self.num_cells, fe.num_nodes * fe.vec), dtype=torch.float64, device=self.device)
         if jac and self._Ke is None:
@@ -358,8 +368,17 @@ class Problem:
                 self._law.law_id, _lib.host_doubles(self._law.params()), _lib.ptr(self._points), _lib.ptr(self._cells),
                 self.num_cells, _lib.ptr(sol), _lib.ptr(iv), _lib.ptr(self._ref), fe.num_quads,
                 _lib.ptr(self.plan.corner_pos), _lib.ptr(self._Ke) if jac else None, _lib.ptr(self._Re), _lib.stream_ptr()))
+        elif tiles:
+            post = (_lib.ctypes.c_double * 3)()
+            _lib.check(lib.fem_element_tiles(
+                self._law.law_id, _lib.host_doubles(self._law.params()), _lib.ptr(self._points), _lib.ptr(self._cells),
+                self.num_cells, _lib.ptr(sol), _lib.ptr(iv), _lib.ptr(self._ref), _lib.ptr(self.plan.corner_pos),
+                _lib.ptr(self._Ke), _lib.ptr(self._Re), post, _lib.stream_ptr()))
+            self._Ke_post = post
         else:
             self._launch_element(lib, fe, sol, iv, jac)
+        if jac:
+            self._Ke_tiles = tiles
         res = torch.empty((fe.num_total_nodes, fe.vec), dtype=torch.float64, device=self.device)
         p = self.plan
         _lib.check(lib.fem_gather_residual(fe.vec, fe.num_nodes, fe.num_total_nodes, _lib.ptr(p.nc_ptr), _lib.ptr(p.nc),
@@ -400,10 +419,20 @@ class Problem:
             self._Ke_valid = True
         return self._Ke
 
+    def block_tangents(self):
+        """Element tangents as K blocks in the reference's V layout (row block of corner (c, a) = 8 blocks of 3 x 3): what
+        problem.V needs.  When the hot path staged tile-major rows, the reference-layout kernel is run on demand."""
+        if self._last_sol is None:
+            raise AttributeError("element tangents are defined after newton_update()")
+        if not getattr(self, '_Ke_valid', False) or getattr(self, '_Ke_tiles', False):
+            self._run_element_kernel(self._last_sol, jac=True, tiles=False)
+            self._Ke_valid = True
+        return self._Ke
+
     # ---- reference attributes, materialised on demand ---------------------------------------------------
     def element_tangents(self):
         """(num_cells, ndof, ndof) element tangents in the reference's layout (row = test dof)."""
-        Ke = self.staged_tangents()
+        Ke = self.block_tangents()
         fe = self.fes[0]
         N, v = fe.num_nodes, fe.vec
         rows = Ke[self.plan.corner_pos.long()][:, :N * v * v]              # (C*N, N*v*v) in (c, a) order

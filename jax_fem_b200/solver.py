@@ -131,8 +131,12 @@ def get_A(problem):
     Ke = problem.staged_tangents()
     emeta = problem.entry_meta()
     data = torch.empty(p.nnz, dtype=torch.float64, device=problem.device)
-    _lib.check(_lib.load().fem_gather_csr(fe.vec, fe.num_nodes, p.n_gather_blocks, _lib.ptr(p.gdesc), _lib.ptr(emeta),
-                                          _lib.ptr(p.src), _lib.ptr(Ke), _lib.ptr(data), _lib.stream_ptr()))
+    if getattr(problem, '_Ke_tiles', False):       # tile-major rows of fem_element_tiles; isotropic map applied after the sum
+        _lib.check(_lib.load().fem_gather_csr_tiles(p.n_gather_blocks, _lib.ptr(p.gdesc), _lib.ptr(emeta), _lib.ptr(p.src),
+                                                    _lib.ptr(Ke), _lib.ptr(data), problem._Ke_post, _lib.stream_ptr()))
+    else:
+        _lib.check(_lib.load().fem_gather_csr(fe.vec, fe.num_nodes, p.n_gather_blocks, _lib.ptr(p.gdesc), _lib.ptr(emeta),
+                                              _lib.ptr(p.src), _lib.ptr(Ke), _lib.ptr(data), _lib.stream_ptr()))
     return CSRMatrix(p, data)
 
 

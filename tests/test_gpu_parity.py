@@ -526,6 +526,40 @@ def test_c_abi_pipeline_without_torch():
     assert "C_ABI_PIPELINE_OK" in out.stdout
 
 
+@pytest.mark.parametrize("law", ["elastic", "simp", "neohookean"])
+def test_tile_major_staging_equals_block_staging(law, monkeypatch):
+    """The default HEX8 hot path stages tile-major rows written straight from the tensor-core fragments and applies the
+    isotropic map after the sum (fem_element_tiles + fem_gather_csr_tiles); FEM_ELEMENT_PATH=blocks stages K blocks in the
+    reference's V layout.  Same CSR values (1e-13: the map is applied to the sum instead of to every block), same residual,
+    and problem.V / element_tangents() keep the reference layout either way."""
+    import jax_fem_b200 as jf
+    import gpu_problems as gp
+    pts, cells = perturbed_box(8, seed=3)
+    rng = np.random.default_rng(17)
+    bc = [[lambda p: p[0] < 0.05] * 3, [0, 1, 2], [lambda p: 0., lambda p: 0.01, lambda p: -0.01]]
+    sol = torch.from_numpy(0.01 * rng.standard_normal((len(pts), 3))).cuda()
+    out = {}
+    for path in ("blocks", "tiles"):
+        monkeypatch.setenv("FEM_ELEMENT_PATH", path)
+        if law == "neohookean":
+            prob = gp.NeoHookeanInverse(jf.Mesh(pts, cells), vec=3, dim=3, dirichlet_bc_info=bc, location_fns=[lambda p: p[1] > 0.95])
+            prob.internal_vars = [torch.from_numpy(0.5 + rng.uniform(0, 1, (len(cells), 8))).cuda()] if path == "blocks" else out["iv"]
+            out["iv"] = prob.internal_vars
+        elif law == "simp":
+            prob = gp.SIMPElasticity(jf.Mesh(pts, cells), vec=3, dim=3, dirichlet_bc_info=bc, location_fns=[lambda p: p[0] > 0.95])
+            prob.internal_vars = [torch.from_numpy(0.2 + 0.7 * rng.uniform(0, 1, (len(cells), 8))).cuda()] if path == "blocks" else out["iv"]
+            out["iv"] = prob.internal_vars
+        else:
+            prob = gp.PlainElasticity(jf.Mesh(pts, cells), vec=3, dim=3, dirichlet_bc_info=bc)
+        assert prob.tiles_enabled() == (path == "tiles")
+        res = prob.newton_update([sol])[0]
+        A = jf.get_A(prob)
+        out[path] = (host(res), host(A.data), host(prob.element_tangents()))
+    assert relmax(out["tiles"][1], out["blocks"][1]) <= 1e-13
+    assert relmax(out["tiles"][0], out["blocks"][0]) <= 1e-13
+    assert np.array_equal(out["tiles"][2], out["blocks"][2])
+
+
 def test_csr_diagonal_beyond_2_30_nonzeros():
     """The Jacobi preconditioner of the 200^3 mesh (nnz = 1.95e9): row offsets above 2^30 must not overflow the binary search
     for the diagonal entry (lo + hi in int32 did: the first 200^3 solve on one GPU hung).  Synthetic banded matrix with
