@@ -16,6 +16,7 @@ from .fe import FiniteElement                                   # noqa: E402
 from .problem import Problem                                    # noqa: E402
 from .solver import solver, ad_wrapper, get_A, apply_bc_vec, linear_solver   # noqa: E402
 from .utils import save_sol                                     # noqa: E402
+from .mesh_io import read_mesh                                  # noqa: E402
 
 __all__ = ["Problem", "solver", "ad_wrapper", "get_A", "apply_bc_vec", "linear_solver", "FiniteElement", "Mesh",
-           "box_mesh", "box_mesh_hex27", "rectangle_mesh", "get_meshio_cell_type", "laws", "logger", "save_sol"]
+           "box_mesh", "box_mesh_hex27", "rectangle_mesh", "get_meshio_cell_type", "laws", "logger", "save_sol", "read_mesh"]

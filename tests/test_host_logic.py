@@ -408,3 +408,52 @@ def test_xla_ffi_shim_compiles_against_the_stub_headers_and_fails_loudly_without
             xla_ffi.build()
         with pytest.raises(RuntimeError):
             xla_ffi.register()
+
+
+def test_mesh_files_round_trip_through_the_three_readers(tmp_path):
+    """read_mesh (the meshio.read replacement: Gmsh MSH 2.2 as the reference's gmsh generators write it, Abaqus .inp, ASCII
+    .vtu) must return the generator's points and connectivity; the .vtu golden of the reference is read identically by
+    the product reader and by the oracle's reader; higher-order cells are refused, never silently permuted."""
+    import os
+    import numpy as np
+    import pytest
+    from jax_fem_b200.generate_mesh import box_mesh, rectangle_mesh
+    from jax_fem_b200.mesh_io import read_mesh
+    from oracle import vtu as ovtu
+    m = box_mesh(3, 2, 2, 1.5, 1.0, 1.0)
+    pts, cells = m.points, m.cells_dict['hexahedron']
+    ids = 10 + 3 * np.arange(len(pts))                     # non-contiguous node numbers, as files in the wild have
+    msh = tmp_path / "box.msh"
+    with open(msh, "w") as f:
+        f.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n%d\n" % len(pts))
+        f.write("".join("%d %.17g %.17g %.17g\n" % (i, *p) for i, p in zip(ids, pts)))
+        f.write("$EndNodes\n$Elements\n%d\n" % (len(cells) + 1))
+        f.write("1 15 2 0 1 %d\n" % ids[0])                 # a point element, as gmsh emits for physical points
+        f.write("".join("%d 5 2 0 1 %s\n" % (k + 2, " ".join(str(ids[n]) for n in c)) for k, c in enumerate(cells)))
+        f.write("$EndElements\n")
+    got = read_mesh(str(msh))
+    assert np.array_equal(got.points, pts) and np.array_equal(got.cells_dict['hexahedron'], cells)
+    inp = tmp_path / "box.inp"
+    with open(inp, "w") as f:
+        f.write("*HEADING\n** comment\n*NODE\n" + "".join("%d, %.17g, %.17g, %.17g\n" % (i, *p) for i, p in zip(ids, pts)))
+        f.write("*ELEMENT, TYPE=C3D8, ELSET=ALL\n" + "".join("%d, %s\n" % (k + 1, ", ".join(str(ids[n]) for n in c)) for k, c in enumerate(cells)))
+        f.write("*END STEP\n")
+    got = read_mesh(str(inp))
+    assert np.array_equal(got.points, pts) and np.array_equal(got.cells_dict['hexahedron'], cells)
+    q = rectangle_mesh(4, 3, 1., 1.)
+    with open(inp, "w") as f:
+        f.write("*NODE\n" + "".join("%d, %.17g, %.17g\n" % (i + 1, *p) for i, p in enumerate(q.points)))
+        f.write("*ELEMENT, TYPE=CPS4\n" + "".join("%d, %s\n" % (k + 1, ", ".join(str(n + 1) for n in c)) for k, c in enumerate(q.cells_dict['quad'])))
+    got = read_mesh(str(inp))
+    assert np.array_equal(got.points[:, :2], q.points) and np.array_equal(got.cells_dict['quad'], q.cells_dict['quad'])
+    with open(inp, "w") as f:
+        f.write("*NODE\n1, 0, 0, 0\n*ELEMENT, TYPE=C3D20\n1, 1\n")
+    with pytest.raises(NotImplementedError):
+        read_mesh(str(inp))
+    golden = "/root/reference/tests/benchmarks/linear_elasticity_cube/fenicsx/sol_p0_000000.vtu"
+    if os.path.exists(golden):                              # only in the build container; the GPU box has no /root/reference
+        a, (p2, c2, pd2) = read_mesh(golden), ovtu.read_vtu(golden)
+        assert np.array_equal(a.points, p2) and np.array_equal(a.cells_dict['hexahedron'], c2)
+        assert all(np.array_equal(a.point_data[k], pd2[k]) for k in pd2)
+    with pytest.raises(NotImplementedError):
+        read_mesh("mesh.xdmf")
