@@ -151,7 +151,7 @@ int fem_assemble_fused(int ele_type, int vec, int law_id, const double* law_para
  *      nodes (the fem_gather_csr work item) once the E items holding the cells around its nodes are done.
  *      tdesc (n_e + n_gather, 32): one descriptor per ticket, in ticket order: [0] E: 0x80000000 | item, G: item; G only:
  *      [1] first staging row, [2..5] first corner / entry / source / emeta row, [6..9] their ends, [10] number of E items
- *      it waits for, [11] -1 or the offset of their list in gdep when they do not fit, [12..29] those E items, [30..31] first / last node.
+ *      it waits for, [11] -1 or the offset of their list in gdep when they do not fit, [12..31] those E items.
  *      The staging buffer `stage` (rows of 72 doubles, 128-byte aligned) is a ring that stays in L2 plus a spill area;
  *      jax_fem_b200/stage_plan.py builds the tables and checks that every wait is on an EARLIER ticket (no deadlock).
  *      Staging rows hold G = sum_q E_q w_q g_a (x) g_b as 9 tiles [I][J][b]; K = lam' G + mu' G^T + mu' tr(G) I is
@@ -166,22 +166,6 @@ int fem_assemble_staged(int law_id, const double* law_params_host, const double*
                         const int32_t* emeta, const int32_t* src, double* stage,
                         int32_t* ctrl, double* Re, double* data, void* stream);
 int fem_staged_status(const int32_t* ctrl, int32_t* status_host, void* stream);
-
-/* The same one-kernel staged assembly with WARP-sized work items and no CTA-wide barrier (csrc/staged_warp.cu): E item = 4
- * cells, G item = the fem_gather_csr work item walked node by node, tickets dealt round-robin to the resident warps
- * (fem_staged_warp_count(warps_per_sm) of them; warps_per_sm in {12, 16, 19}).  Tables as for fem_assemble_staged with
- * cells_per_item = 4 (tdesc[.][30..31] = first / last node of a G item), plus: corner_eitem (8 n_cells): E item of every corner
- * in node-sorted order; nc_ptr / brow_ptr of the plan; esrc (nnzb x 16 bytes, 16-byte aligned): the source blocks of every
- * block entry relative to the first corner of its row node (8 row + b; 255 = none; bit 7 of byte 0 = diagonal entry);
- * bc_flag (n_dofs bytes, 1 = Dirichlet row) or NULL.  The CSR gather needs no emeta here.                                   */
-int fem_staged_warp_count(int warps_per_sm);
-int fem_assemble_staged_warp(int law_id, const double* law_params_host, const double* points, const double* sol,
-                             const double* internal_var, const double* ref_tables, int64_t n_cells,
-                             const int32_t* cells_p, const int32_t* corder, const int32_t* dest_row,
-                             const int32_t* prev_g, int64_t n_gather, const int32_t* tdesc,
-                             const int32_t* corner_eitem, const int32_t* nc_ptr, const int32_t* brow_ptr,
-                             const uint8_t* esrc, const uint8_t* bc_flag, double* stage, int32_t* ctrl, double* Re,
-                             double* data, int warps_per_sm, void* stream);
 
 /* Plan construction helper (HOST pointers, no CUDA): greedy split of every patch's cells into chunks of <= chunk
  * cells in which no owned node occurs more than rmax times.  cell_ptr (n_patches+1); owned_idx (M, nodes_per_cell):

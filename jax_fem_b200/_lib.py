@@ -30,8 +30,6 @@ _SIGNATURES = {
     "fem_assemble_fused": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64] + [_vp] * 18 + [_i, _vp]),
     "fem_staged_ctrl_ints": (_i64, [_i64, _i64]),
     "fem_assemble_staged": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64] + [_vp] * 9),
-    "fem_staged_warp_count": (_i, [_i]),
-    "fem_assemble_staged_warp": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64] + [_vp] * 10 + [_i, _vp]),
     "fem_staged_status": (_i, [_vp, _vp, _vp]),
     "fem_patch_chunks_host": (_i, [_i64, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "fem_gather_csr": (_i, [_i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),

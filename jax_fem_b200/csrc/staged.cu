@@ -237,8 +237,8 @@ constexpr int kEPT = (kMaxS + kSThreads - 1) / kSThreads;   // 3
 
 // Ticket descriptor (32 ints, one 128-byte line per ticket, in ticket order): [0] E: 0x80000000 | item, G: item;
 // G only: [1] first staging row, [2..5] first corner / entry / source / emeta row, [6..9] their ends, [10] number of E
-// items holding cells around the item's nodes, [11] -1 or their offset in `gdep` when they do not fit, [12..29] those E items.
-constexpr int kDescInts = 32, kDescInline = 18, kDescSlots = 3;   // [30], [31] belong to staged_warp.cu
+// items holding cells around the item's nodes, [11] -1 or their offset in `gdep` when they do not fit, [12..31] those E items.
+constexpr int kDescInts = 32, kDescInline = 20, kDescSlots = 3;
 enum { D_CODE = 0, D_ROW0, D_C0, D_E0, D_S0, D_M0, D_C1, D_E1, D_S1, D_M1, D_NDEP, D_OVF, D_DEPS };
 
 struct GMeta {   // per-thread share of an item's metadata, prefetched one item ahead

@@ -28,7 +28,7 @@ from .fe import FiniteElement, evaluate_point_fn
 from .generate_mesh import Mesh
 from .patch_plan import DEFAULT_CONFIG, build_patch_plan
 from .plan import build_plan, build_plan_native
-from .stage_plan import StageConfig, build_stage_plan, warp_config
+from .stage_plan import StageConfig, build_stage_plan
 
 
 def _device():
@@ -241,16 +241,14 @@ class Problem:
                       in an L2-resident ring (csrc/staged.cu; HEX8 / vec 3 / isotropic elasticity).  HBM traffic drops from
                       12.1 to 3.4 GB per assembly at 100^3 (ncu), but the kernel is latency-bound and measures 3.4 ms
                       against 2.45 ms for 'staged' (profiles/r02_ring_assembly.md), so it is opt-in;
-           'warp'   : the same one-kernel staged assembly with warp-sized work items and no CTA-wide barrier
-                      (csrc/staged_warp.cu);
            'fused'  : owner-computes patches (csrc/fused.cu; measured slower).
         FEM_ASSEMBLY in the environment selects the mode; every mode is parity-tested."""
         import os
         eligible = (self.ele_type == 'HEX8' and self.fes[0].vec == 3
                     and self._law.law_id in (laws.LinearElasticity.law_id, laws.SIMP.law_id))
         mode = os.environ.get('FEM_ASSEMBLY', 'staged')
-        if mode not in ('ring', 'warp', 'staged', 'fused'):
-            raise ValueError(f"FEM_ASSEMBLY={mode!r}: registered modes are 'staged', 'ring', 'warp', 'fused'")
+        if mode not in ('ring', 'staged', 'fused'):
+            raise ValueError(f"FEM_ASSEMBLY={mode!r}: registered modes are 'ring', 'staged', 'fused'")
         return mode if eligible else 'staged'
 
     def fused_assembly_enabled(self):
@@ -260,16 +258,12 @@ class Problem:
     def stage_plan(self):
         if self._stage_plan is None:
             import os
-            warp = self.assembly_mode() == 'warp'
-            self._warps = int(os.environ.get('FEM_WARPS', '16'))
-            cfg = warp_config(_lib.load().fem_staged_warp_count(self._warps)) if warp else StageConfig()
+            cfg = StageConfig()
             for name in ('ring_bytes', 'tile_cells', 'slack', 'margin', 'in_flight'):
                 v = os.environ.get('FEM_RING_' + name.upper())
                 if v is not None:
                     setattr(cfg, name, int(v))
             self._stage_plan = build_stage_plan(self.plan, self._cells, self._points, cfg)
-            if warp and self._stage_plan.esrc is None:
-                raise NotImplementedError("FEM_ASSEMBLY=warp needs nodes with at most 16 cells; use 'staged'")
         return self._stage_plan
 
     def _run_ring(self, sol):
@@ -287,18 +281,10 @@ class Problem:
         iv = self._internal_var()
         emeta = self.entry_meta()
         data = torch.empty(p.nnz, dtype=torch.float64, device=dev)
-        if sp.cells_per_item == 4:
-            _, _, flag = self.bc_data()
-            _lib.check(lib.fem_assemble_staged_warp(
-                self._law.law_id, _lib.host_doubles(self._law.params()), P(self._points), P(sol), P(iv), P(self._ref),
-                self.num_cells, P(sp.cells_p), P(sp.corder), P(sp.dest_row), P(sp.prev_g), sp.n_g, P(sp.tdesc),
-                P(sp.corner_eitem), P(p.nc_ptr), P(p.brow_ptr), P(sp.esrc), P(flag), P(stage), P(ctrl), P(self._Re), P(data),
-                self._warps, _lib.stream_ptr()))
-        else:
-            _lib.check(lib.fem_assemble_staged(
-                self._law.law_id, _lib.host_doubles(self._law.params()), P(self._points), P(sol), P(iv), P(self._ref),
-                self.num_cells, P(sp.cells_p), P(sp.corder), P(sp.dest_row), P(sp.prev_g), sp.n_g, P(sp.tdesc), P(sp.gdep),
-                P(emeta), P(p.src), P(stage), P(ctrl), P(self._Re), P(data), _lib.stream_ptr()))
+        _lib.check(lib.fem_assemble_staged(
+            self._law.law_id, _lib.host_doubles(self._law.params()), P(self._points), P(sol), P(iv), P(self._ref),
+            self.num_cells, P(sp.cells_p), P(sp.corder), P(sp.dest_row), P(sp.prev_g), sp.n_g, P(sp.tdesc), P(sp.gdep),
+            P(emeta), P(p.src), P(stage), P(ctrl), P(self._Re), P(data), _lib.stream_ptr()))
         status.copy_(ctrl[3:4], non_blocking=True)
         event.record()
         self._ring_pending = True
@@ -419,7 +405,7 @@ class Problem:
         mode = self.assembly_mode()
         if mode != 'staged':
             self._Ke_valid = False
-            return [self._run_fused(sol) if mode == 'fused' else self._run_ring(sol)]       # 'ring' and 'warp' share the plumbing
+            return [self._run_fused(sol) if mode == 'fused' else self._run_ring(sol)]
         self._Ke_valid = True
         return [self._run_element_kernel(sol, jac=True)]
 

@@ -31,8 +31,7 @@ import torch
 CELLS_PER_ITEM = 16
 MAX_ITEM_CORNERS = 48          # csrc/staged.cu::kMaxC
 E_FLAG = -(2 ** 31)            # 0x80000000 as int32
-DESC_INTS, DESC_INLINE = 32, 18  # csrc/staged.cu::kDescInts, kDescInline
-DESC_NODE0 = 30                  # [30], [31]: first / last node of a G item (csrc/staged_warp.cu)
+DESC_INTS, DESC_INLINE = 32, 20  # csrc/staged.cu::kDescInts, kDescInline
 
 
 @dataclass
@@ -43,15 +42,6 @@ class StageConfig:
     margin: int = 2560             # tickets between a G item and the E item that recycles its rows
     in_flight: int = 512           # E items that may be running or queued on resident CTAs (sizes the ring pre-filter)
     row_bytes: int = 576
-    cells_per_item: int = 16       # 16: one CTA per item (csrc/staged.cu); 4: one WARP per item (csrc/staged_warp.cu)
-
-
-def warp_config(n_warps=148 * 16):
-    """Defaults of the warp-item kernel (csrc/staged_warp.cu): tickets are dealt round-robin to `n_warps` resident warps, so
-    a G item is scheduled two rounds after the last E item it needs and rows are recycled another two rounds later."""
-    per_round = n_warps // 5                      # E items per round (one ticket in five is an E item of 4 cells)
-    return StageConfig(ring_bytes=64 << 20, tile_cells=2000, slack=2 * per_round, margin=2 * n_warps, in_flight=per_round + 64,
-                       cells_per_item=4)
 
 
 @dataclass
@@ -67,9 +57,6 @@ class StagePlan:
     ring_rows: int
     n_rows: int                    # rows of the staging buffer (ring + 48 + spill)
     spill_fraction: float
-    corner_eitem: torch.Tensor = None   # (C*8) E item of every corner in node-sorted order (what a G item waits for)
-    esrc: torch.Tensor = None           # (nnzb, 16) uint8: source blocks of every entry relative to its node's first corner
-    cells_per_item: int = 16
 
     @property
     def staging_bytes(self):
@@ -116,8 +103,7 @@ def build_stage_plan(plan, cells, points, config=None):
     corder = _sweep_order(points, cells, cfg.tile_cells)
     slot_of_cell = torch.empty_like(corder)
     slot_of_cell[corder] = torch.arange(C, device=dev)
-    cpi = cfg.cells_per_item
-    n_e = -(-C // cpi)
+    n_e = -(-C // CELLS_PER_ITEM)
 
     gd = plan.gdesc.view(-1, 4).long()
     n_g = gd.shape[0] - 1
@@ -127,7 +113,7 @@ def build_stage_plan(plan, cells, points, config=None):
     n_corners = int(c0[-1])
     pos = torch.arange(n_corners, device=dev)
     item_of_pos = torch.bucketize(pos, c0[1:].contiguous(), right=True)
-    e_of_pos = torch.div(slot_of_cell[torch.div(plan.nc.long(), N, rounding_mode='floor')], cpi, rounding_mode='floor')
+    e_of_pos = torch.div(slot_of_cell[torch.div(plan.nc.long(), N, rounding_mode='floor')], CELLS_PER_ITEM, rounding_mode='floor')
     maxdep = _seg_reduce(e_of_pos, item_of_pos, n_g, 'amax')
     mindep = _seg_reduce(e_of_pos, item_of_pos, n_g, 'amin')
     mindep = torch.where(maxdep < 0, torch.zeros_like(mindep), mindep)
@@ -149,7 +135,7 @@ def build_stage_plan(plan, cells, points, config=None):
     # ---- ring allocation ----------------------------------------------------------------------------------------------
     ring_rows = max(0, cfg.ring_bytes // cfg.row_bytes)
     ring_rows = min(ring_rows, n_corners)
-    life_limit = ring_rows // (cpi * N) - cfg.slack - cfg.in_flight
+    life_limit = ring_rows // (CELLS_PER_ITEM * N) - cfg.slack - cfg.in_flight
     if ring_rows >= n_corners:
         life_limit = n_e                             # everything fits in one lap
     spill = (maxdep - mindep) > life_limit
@@ -219,27 +205,9 @@ def build_stage_plan(plan, cells, points, config=None):
     li = torch.arange(dep_item.numel(), device=dev) - dep_ptr[dep_item]
     inl = li < DESC_INLINE
     tdesc[tick_g[dep_item[inl]], 12 + li[inl]] = dep_e[inl]
-    # first / last node of every G item (the warp-item kernel walks an item node by node)
-    node0 = torch.searchsorted(plan.nc_ptr[:-1].long().contiguous(), c0)
-    tdesc[tick_g, DESC_NODE0] = node0[:-1]
-    tdesc[tick_g, DESC_NODE0 + 1] = node0[1:]
     assert n_rows * 72 < 2 ** 31 * 8 and int(dest_row.max()) < 2 ** 31
     i32 = lambda t: t.to(torch.int32).contiguous()
     gdep = i32(dep_e) if dep_e.numel() else torch.zeros(1, dtype=torch.int32, device=dev)
-    # source blocks of every block entry as bytes relative to the first corner of its row node; bit 7 of byte 0 = diagonal
-    esrc = None
-    sp = plan.src_ptr.long()
-    cnt = sp[1:] - sp[:-1]
-    erow = plan.erow.long()
-    if int(cnt.max()) <= 16 and int((plan.nc_ptr[1:] - plan.nc_ptr[:-1]).max()) <= 16:
-        ent_of_src = torch.repeat_interleave(torch.arange(cnt.numel(), device=dev), cnt)
-        rel = plan.src.long() - plan.nc_ptr.long()[erow[ent_of_src]] * N
-        esrc = torch.full((cnt.numel(), 16), 255, dtype=torch.uint8, device=dev)
-        esrc[ent_of_src, torch.arange(ent_of_src.numel(), device=dev) - sp[ent_of_src]] = rel.to(torch.uint8)
-        diag = plan.bcol.long() == erow
-        esrc[:, 0] = esrc[:, 0] | (diag.to(torch.uint8) << 7)
-        esrc = esrc.contiguous()
     return StagePlan(corder=i32(corder), cells_p=i32(cells_p), dest_row=i32(dest_row), prev_g=i32(prev_g), tdesc=i32(tdesc),
                      gdep=gdep, n_e=n_e, n_g=n_g, ring_rows=ring_rows if n_ring else 0, n_rows=max(n_rows, 1),
-                     spill_fraction=float(size[sp_items].sum()) / max(n_corners, 1), corner_eitem=i32(e_of_pos), esrc=esrc,
-                     cells_per_item=cpi)
+                     spill_fraction=float(size[sp_items].sum()) / max(n_corners, 1))

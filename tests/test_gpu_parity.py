@@ -366,9 +366,8 @@ print('RELMAX', np.abs(K - Ko).max() / np.abs(Ko).max())
 def _assemble_both_ways(prob, sol, monkeypatch):
     import jax_fem_b200 as jf
     out = {}
-    for mode in ("fused", "staged", "ring", "warp"):
+    for mode in ("fused", "staged", "ring"):
         monkeypatch.setenv("FEM_ASSEMBLY", mode)
-        prob._stage_plan = prob._ring = None           # 'ring' and 'warp' use different schedules
         assert prob.assembly_mode() == mode and prob.fused_assembly_enabled() == (mode == "fused")
         res = prob.newton_update([torch.from_numpy(sol).cuda()])[0]
         A = jf.get_A(prob)
@@ -416,11 +415,10 @@ def test_fused_assembly_matches_oracle_and_staged_path(case, config, monkeypatch
     f_ext = host(prob._f_ext) if prob._f_ext is not None else 0.0
     opb.newton_update(sol)
     oA = fem.get_A(opb)
-    for mode in ("fused", "staged", "ring", "warp"):
+    for mode in ("fused", "staged", "ring"):
         res, data = out[mode]
         assert relmax(data, oA.data) <= VAL_TOL, mode
         assert relmax(res, ores + f_ext) <= VAL_TOL, mode
-    assert relmax(out["warp"][1], out["staged"][1]) <= 1e-13
     assert relmax(out["fused"][1], out["staged"][1]) <= 1e-13      # same blocks, different (fixed) summation order
     assert relmax(out["ring"][1], out["staged"][1]) <= 1e-13       # isotropic map applied after the sum instead of before
     # Dirichlet rows are exact unit rows in both
@@ -447,9 +445,8 @@ def test_fused_assembly_rejects_unregistered_combination():
     assert code == -1 and b"fused assembly is registered" in lib.fem_last_error()
 
 
-@pytest.mark.parametrize("mode", ["ring", "warp"])
 @pytest.mark.parametrize("ring_kb,tile,slack,margin", [(400, 64, 2, 8), (150, 10 ** 9, 0, 0), (4000, 200, 16, 64)])
-def test_ring_assembly_recycles_rows_correctly(ring_kb, tile, slack, margin, mode, monkeypatch):
+def test_ring_assembly_recycles_rows_correctly(ring_kb, tile, slack, margin, monkeypatch):
     """The one-kernel staged assembly with a ring far smaller than the element tangents (rows recycled many times, strip
     edges spilled) on a 24 x 12 x 10 non-affine box: CSR values and residual equal the two-kernel path bit for bit in the
     pattern and to 1e-13 in the values, every run gives the same bits, and no wait times out."""
@@ -467,9 +464,7 @@ def test_ring_assembly_recycles_rows_correctly(ring_kb, tile, slack, margin, mod
     ref = gp.PlainElasticity(jf.Mesh(pts, cells), vec=3, dim=3, dirichlet_bc_info=bc)
     res0 = ref.newton_update([sol])[0]
     data0 = jf.get_A(ref).data
-    monkeypatch.setenv("FEM_ASSEMBLY", mode)
-    if mode == "warp":                       # E items of 4 cells: the same ring holds 4x as many of them
-        monkeypatch.setenv("FEM_RING_SLACK", str(4 * slack))
+    monkeypatch.setenv("FEM_ASSEMBLY", "ring")
     prob = gp.PlainElasticity(jf.Mesh(pts, cells), vec=3, dim=3, dirichlet_bc_info=bc)
     sp = prob.stage_plan
     if ring_kb == 400:
@@ -641,20 +636,7 @@ def test_full_size_cfg2_properties(monkeypatch):
         free.newton_update([u])
         assert torch.equal(jf.get_A(free).data, data_r)
     free.check_assembly_status()
-    # ... and with warp-sized work items and no CTA-wide barrier (csrc/staged_warp.cu)
-    monkeypatch.setenv("FEM_ASSEMBLY", "warp")
-    free._stage_plan = free._ring = None
-    res_w = free.newton_update([u])[0]
-    data_w = jf.get_A(free).data.clone()
-    free.check_assembly_status()
-    assert free.stage_plan.ring_rows > 0 and free.stage_plan.spill_fraction < 0.2
-    assert float((data_w - data0).abs().max()) <= 1e-13 * scale
-    assert float((res_w - res_u).abs().max()) <= 1e-12 * float(res_u.abs().max())
-    for _ in range(3):
-        free.newton_update([u])
-        assert torch.equal(jf.get_A(free).data, data_w)
-    free.check_assembly_status()
-    del free, A, data0, data_r, data_w
+    del free, A, data0, data_r
     torch.cuda.empty_cache()
 
     # cfg 2 proper: u = 0 on x = 0, traction on x = 1, Jacobi-CG to 1e-10 (default assembly mode)
@@ -743,7 +725,7 @@ def test_quad4_elasticity_and_plane_stress_simp_match_oracle(law_name):
         laws.resolve(laws.LinearElasticity(1., .3, plane_stress=True), 'HEX8', 3)
 
 
-@pytest.mark.parametrize("mode", ["staged", "fused", "ring", "warp"])
+@pytest.mark.parametrize("mode", ["staged", "fused", "ring"])
 def test_assembly_on_randomly_renumbered_mesh(mode, monkeypatch):
     """Generality of the plans: a non-affine box whose nodes and cells are randomly renumbered (no tensor-grid structure in
     the numbering, scattered CSR rows, bin-based patches) must assemble to the oracle's operator in both assembly modes."""

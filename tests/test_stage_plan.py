@@ -8,11 +8,10 @@ import torch
 
 from jax_fem_b200.generate_mesh import box_mesh
 from jax_fem_b200.plan import build_plan
-from jax_fem_b200.stage_plan import StageConfig, build_stage_plan
+from jax_fem_b200.stage_plan import StageConfig, build_stage_plan, CELLS_PER_ITEM
 
 
-def emulate(plan, sp, workers, seed, lookahead=3, static=False):
-    CELLS_PER_ITEM = sp.cells_per_item
+def emulate(plan, sp, workers, seed, lookahead=3):
     rng = np.random.default_rng(seed)
     td = sp.tdesc.numpy().astype(np.int64)
     gdep = sp.gdep.numpy()
@@ -31,12 +30,9 @@ def emulate(plan, sp, workers, seed, lookahead=3, static=False):
 
     def refill(q):
         nonlocal nxt_ticket
-        while not static and len(q) < lookahead and nxt_ticket < n_t:
+        while len(q) < lookahead and nxt_ticket < n_t:
             q.append(nxt_ticket)
             nxt_ticket += 1
-
-    if static:                        # tickets dealt round-robin to the workers (csrc/staged_warp.cu), processed in order
-        queues = [list(range(w, n_t, workers)) for w in range(workers)]
 
     def deps(t):
         d = td[t]
@@ -117,33 +113,3 @@ def test_renumbered_mesh_degrades_to_spill_but_stays_correct():
     plan, cells, pts = _plan(8, 7, 6, renumber=5)
     sp = build_stage_plan(plan, cells, pts, StageConfig(ring_bytes=400 * 576, tile_cells=50, slack=1, margin=4, in_flight=0))
     emulate(plan, sp, 9, 4)
-
-
-def test_warp_item_schedule_with_static_tickets():
-    """The warp-item kernel (csrc/staged_warp.cu): E items of 4 cells, tickets dealt round-robin to the resident warps; also
-    the per-entry source bytes and the per-corner E items it reads instead of the CTA kernel's tables."""
-    plan, cells, pts = _plan(16, 9, 8)
-    cfg = StageConfig(ring_bytes=2500 * 576, tile_cells=48, slack=8, margin=16, in_flight=0, cells_per_item=4)
-    sp = build_stage_plan(plan, cells, pts, cfg)
-    assert sp.cells_per_item == 4 and sp.n_e == -(-cells.shape[0] // 4)
-    assert sp.ring_rows > 0 and int(sp.prev_g.max()) >= 0
-    for workers, seed in ((5, 0), (37, 1)):
-        emulate(plan, sp, workers, seed, static=True)
-    # esrc: every source of every entry, relative to the first corner of the entry's row node
-    sp_ptr, src, erow, ncp = plan.src_ptr.numpy(), plan.src.numpy(), plan.erow.numpy(), plan.nc_ptr.numpy()
-    es = sp.esrc.numpy()
-    for e in np.random.default_rng(0).integers(0, len(erow), 200):
-        want = src[sp_ptr[e]:sp_ptr[e + 1]] - 8 * ncp[erow[e]]
-        got = es[e][:len(want)].astype(np.int64)
-        got[0] &= 127
-        assert np.array_equal(got, want) and np.all(es[e][len(want):] == 255)
-        assert bool(es[e][0] >> 7) == (plan.bcol.numpy()[e] == erow[e])
-    # corner_eitem: E item holding the cell of every node-sorted corner
-    slot = np.empty(cells.shape[0], dtype=np.int64)
-    slot[sp.corder.numpy()] = np.arange(cells.shape[0])
-    assert np.array_equal(sp.corner_eitem.numpy(), slot[plan.nc.numpy() // 8] // 4)
-    # node ranges of the G items tile the node set
-    td = sp.tdesc.numpy()
-    g = td[td[:, 0] >= 0]
-    g = g[np.argsort(g[:, 0])]
-    assert g[0, 30] == 0 and g[-1, 31] == len(pts) and np.array_equal(g[1:, 30], g[:-1, 31])
