@@ -638,11 +638,15 @@ __global__ void __launch_bounds__(NhDmmaLayout::WARPS * 32, 3) element_nh_dmma_k
     for (int s = 0; s < 2; ++s)
 #pragma unroll
       for (int d = 0; d < 3; ++d) dmma884(D, ga[s][d], gq[s][d]);
+    // The tangent is symmetric, K_ab[I][J] = K_ba[J][I]: with tile-major staging only the 6 tiles I <= J are computed (36 instead
+    // of 54 DMMA -- this kernel is FP64-bound); tile (J, I) is the transpose of tile (I, J) and is written by the lanes that hold
+    // it: lane (r, t) stores element [r][2t] to row 2t, column r and [r][2t+1] to row 2t+1, column r (8 lanes = 64 contiguous bytes).
     double C[3][3][2];
 #pragma unroll
     for (int I = 0; I < 3; ++I)
 #pragma unroll
       for (int J = 0; J < 3; ++J) {
+        if (TILES && J < I) continue;
         C[I][J][0] = (I == J) ? D[0] : 0.0;
         C[I][J][1] = (I == J) ? D[1] : 0.0;
 #pragma unroll
@@ -670,10 +674,18 @@ __global__ void __launch_bounds__(NhDmmaLayout::WARPS * 32, 3) element_nh_dmma_k
     if constexpr (TILES) {
       // tile-major row (9 tiles of 8 doubles): the fragments ARE the tiles, 16 bytes per lane and tile, no staging
       double* row = A.Ke + (int64_t)pos[j * 8 + n] * 72 + 2 * t;
+      double* rowT0 = A.Ke + (int64_t)pos[j * 8 + 2 * t] * 72 + n;          // transposed element [n][2t]   -> row 2t,   column n
+      double* rowT1 = A.Ke + (int64_t)pos[j * 8 + 2 * t + 1] * 72 + n;      // transposed element [n][2t+1] -> row 2t+1, column n
 #pragma unroll
       for (int I = 0; I < 3; ++I)
 #pragma unroll
-        for (int J = 0; J < 3; ++J) *reinterpret_cast<double2*>(row + (I * 3 + J) * 8) = make_double2(C[I][J][0], C[I][J][1]);
+        for (int J = I; J < 3; ++J) {
+          *reinterpret_cast<double2*>(row + (I * 3 + J) * 8) = make_double2(C[I][J][0], C[I][J][1]);
+          if (J > I) {
+            rowT0[(J * 3 + I) * 8] = C[I][J][0];
+            rowT1[(J * 3 + I) * 8] = C[I][J][1];
+          }
+        }
       continue;
     }
     // lane (n, t) holds K_{n,2t} and K_{n,2t+1}: 18 contiguous doubles of row block n; stage 4 row blocks at a time in

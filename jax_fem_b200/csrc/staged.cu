@@ -64,6 +64,12 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ int ld_relaxed(const int* p) {     // polling: ld.acquire would cost an L1 invalidation (CCTL.IVALL) per load
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -74,7 +80,7 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 // exceeds the limit is a plan bug: flag it and go on (wrong numbers, reported by the host) instead of hanging the GPU.
 __device__ __forceinline__ void wait_flag(const int* flag, int* err) {
   unsigned spins = 0;
-  while (ld_acquire(flag) == 0) {
+  while (ld_relaxed(flag) == 0) {        // relaxed: the caller issues one acquire fence after all of its flags are set
     __nanosleep(64);
     if ((++spins & 255u) == 0 && (spins > kSpinLimit || ld_acquire(err) != 0)) {
       atomicExch(err, 1);
@@ -178,6 +184,7 @@ __device__ __forceinline__ void run_element_item(const StagedArgs& A, int item, 
     if (pg >= 0) wait_flag(A.ctrl + kCtrlInts + A.n_e + pg, A.ctrl + 3);
   }
   __syncthreads();
+  fence_acq_rel();                       // the stores below are ordered after the flag reads
 
   // ---- phase 2: the warp walks its 4 cells; lane = (node n, t) ----
   const int n = l >> 2, t = l & 3;
@@ -223,10 +230,7 @@ __device__ __forceinline__ void run_element_item(const StagedArgs& A, int item, 
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    st_release(A.ctrl + kCtrlInts + item, 1);
-  }
+  if (threadIdx.x == 0) st_release(A.ctrl + kCtrlInts + item, 1);   // cumulative over the CTA's stores (ordered by the barrier)
 }
 
 // ---- G item -----------------------------------------------------------------------------------------------------------
@@ -277,6 +281,7 @@ __device__ __forceinline__ const int* g_dep_flag(const StagedArgs& A, const int*
 
 // one elected thread, once the item's E items are done: start the bulk copy of its staging rows
 __device__ __forceinline__ void g_issue(const StagedArgs& A, const int* d, double* stage_smem, uint64_t* bar) {
+  fence_acq_rel();                                 // acquire side of the E items' release stores (the flags were polled relaxed)
   fence_proxy_async_all();                         // generic-proxy writes of the E items -> async-proxy read below
   const uint32_t bytes = (uint32_t)(d[D_C1] - d[D_C0]) * kRow * sizeof(double);
   mbar_expect_tx(bar, bytes);
@@ -346,7 +351,7 @@ __global__ void __launch_bounds__(kSThreads, 4) staged_assembly_kernel(const Sta
     if (next_is_g) {
       g_load_meta(A, dn, nm);
       const int* f = g_dep_flag(A, dn);
-      if (f) nflag = ld_acquire(f);
+      if (f) nflag = ld_relaxed(f);
     }
     bool nxt_issued = false;
     if (code < 0) {
@@ -376,10 +381,7 @@ __global__ void __launch_bounds__(kSThreads, 4) staged_assembly_kernel(const Sta
       // the staging rows have landed in shared memory: they are dead in L2 and may be overwritten from now on
       discard_rows(A.stage + (int64_t)dc[D_ROW0] * kRow, dc[D_C1] - C0);
       __syncthreads();
-      if (threadIdx.x == 0) {
-        __threadfence();
-        st_release(flag_g + code, 1);
-      }
+      if (threadIdx.x == 0) st_release(flag_g + code, 1);
 
       // phase B: per entry, add its sources in the plan's fixed order; source block (row r, b) = sh[r*72 + IJ*8 + b]
       double res[kEPT][VV];

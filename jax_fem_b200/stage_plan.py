@@ -36,11 +36,11 @@ DESC_INTS, DESC_INLINE = 32, 20  # csrc/staged.cu::kDescInts, kDescInline
 
 @dataclass
 class StageConfig:
-    ring_bytes: int = 80 << 20     # staging ring; must stay well below the 126 MB L2
+    ring_bytes: int = 112 << 20    # staging ring; must stay well below the 126 MB L2
     tile_cells: int = 2000         # cells per sweep layer of a tile (frontier width)
-    slack: int = 128               # E items between the last E item a G item needs and the G item's ticket
-    margin: int = 2560             # tickets between a G item and the E item that recycles its rows
-    in_flight: int = 512           # E items that may be running or queued on resident CTAs (sizes the ring pre-filter)
+    slack: int = 512               # E items between the last E item a G item needs and the G item's ticket
+    margin: int = 2048             # tickets between a G item and the E item that recycles its rows
+    in_flight: int = 200           # E items that may be running or queued on resident CTAs (sizes the ring pre-filter)
     row_bytes: int = 576
 
 
