@@ -6,7 +6,7 @@
 // 262-266) and FiniteElement.get_shape_grads (jax_fem/fe.py:112-141).  The reference would materialise
 // shape_grads (C,216,27,3) = 30 GB at 60^3; here geometry is recomputed per cell.
 //
-// One CTA (8 warps) per cell:
+// One CTA (10 warps) per cell:
 //   phase 1  thread = quadrature point: J, J^-1, JxW, grad u, stress  ->  shared {J^-1, E w, S = sigma JxW}
 //   phase 2  for chunks of 32 quadrature points:
 //              all threads: g[q][n][:] = dN[q][n] J^-1(q)                     -> shared Gq[q][3n+d]
@@ -38,6 +38,7 @@ struct Hex27Args {
   const double* sol;
   const double* iv;          // (C, nq) or nullptr
   const double* ref;         // [nq*27*3] dN, [nq] w
+  const double* ref_t;       // [27*3][nq] the same dN with the point index fastest (coalesced reads when thread = point) or nullptr
   const int32_t* corner_pos;
   double* Ke;                // (C*27, 244)
   double* Re;                // (C, 81)
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(H27_THREADS, 2) hex27_kernel(const Hex27Args A
   double* R = U + H27_ND;                  // [81] residual
   double* work = R + H27_ND + 1;           // even offset (244) => 16-byte aligned
   double* QP = work;                       // [nq_pad][19]
-  double* Gq = QP + nq_pad * H27_QP + (nq_pad * H27_QP) % 2;   // [32][100]
+  double* Gq = QP + nq_pad * H27_QP + (nq_pad * H27_QP) % 2;   // 2 x [32][100]
   double* G = work;                        // [88][89] overlays QP + Gq after the main loop
   __shared__ int pos[H27_NN];
   const int64_t c = blockIdx.x;
@@ -125,32 +126,37 @@ __global__ void __launch_bounds__(H27_THREADS, 2) hex27_kernel(const Hex27Args A
       for (int j = 0; j < H27_QP; ++j) rec[j] = 0.0;
       continue;
     }
+    // dN of point q: consecutive threads are consecutive points, so the table is read with q fastest when the caller supplies
+    // the transposed copy (one coalesced 256-byte request per warp instead of 32 different cache lines)
     const double* dN = A.ref + (int64_t)q * H27_ND;
-    double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    const double* dT = A.ref_t ? A.ref_t + q : nullptr;
+    auto dn = [&](int n, int d) { return dT ? __ldg(dT + (int64_t)(n * 3 + d) * nq) : __ldg(dN + n * 3 + d); };
+    // One pass over the 27 nodes gives both J = sum_n x_n (x) dN_n (fe.py:132) and the reference gradient of u,
+    // Gu = sum_n u_n (x) dN_n: 18 independent accumulation chains.  grad u = Gu J^-1 then costs 27 FMA per point instead of
+    // forming every physical shape gradient here (problem.py:204-205 with fe.py:138-139 substituted).
+    double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, Gu[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll 3
     for (int n = 0; n < H27_NN; ++n) {
-      const double d0 = __ldg(dN + n * 3), d1 = __ldg(dN + n * 3 + 1), d2 = __ldg(dN + n * 3 + 2);
+      const double d0 = dn(n, 0), d1 = dn(n, 1), d2 = dn(n, 2);
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        const double x = X[n * 3 + d];
+        const double x = X[n * 3 + d], u = U[n * 3 + d];
         J[d][0] = fma(x, d0, J[d][0]);
         J[d][1] = fma(x, d1, J[d][1]);
-        J[d][2] = fma(x, d2, J[d][2]);                    // fe.py:132
+        J[d][2] = fma(x, d2, J[d][2]);
+        Gu[d][0] = fma(u, d0, Gu[d][0]);
+        Gu[d][1] = fma(u, d1, Gu[d][1]);
+        Gu[d][2] = fma(u, d2, Gu[d][2]);
       }
     }
     double inv[3][3];
     const double det = det_inv3(J, inv);                  // fe.py:134-135
     const double w = det * __ldg(A.ref + (int64_t)nq * H27_ND + q);        // fe.py:140
-    double ug[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    for (int n = 0; n < H27_NN; ++n) {
-      const double d0 = __ldg(dN + n * 3), d1 = __ldg(dN + n * 3 + 1), d2 = __ldg(dN + n * 3 + 2);
-      double g[3];
+    double ug[3][3];
 #pragma unroll
-      for (int d = 0; d < 3; ++d) g[d] = d0 * inv[0][d] + d1 * inv[1][d] + d2 * inv[2][d];   // fe.py:138-139
+    for (int i = 0; i < 3; ++i)
 #pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int d = 0; d < 3; ++d) ug[i][d] = fma(U[n * 3 + i], g[d], ug[i][d]);            // problem.py:204-205
-    }
+      for (int d = 0; d < 3; ++d) ug[i][d] = Gu[i][0] * inv[0][d] + Gu[i][1] * inv[1][d] + Gu[i][2] * inv[2][d];
     double E;
     if (A.law == FEM_LAW_SIMP) E = A.p[1] + (A.p[0] - A.p[1]) * pow(A.iv[c * nq + q], A.p[3]);
     else E = A.p[0];
@@ -167,7 +173,7 @@ __global__ void __launch_bounds__(H27_THREADS, 2) hex27_kernel(const Hex27Args A
       for (int d = 0; d < 3; ++d) rec[10 + i * 3 + d] = (mu * (ug[i][d] + ug[d][i]) + (i == d ? lam * tr : 0.0)) * w;
   }
   // zero the padding columns 81..99 of Gq once
-  for (int j = tid; j < H27_QC * (H27_GS - H27_ND); j += H27_THREADS)
+  for (int j = tid; j < 2 * H27_QC * (H27_GS - H27_ND); j += H27_THREADS)
     Gq[(j / (H27_GS - H27_ND)) * H27_GS + H27_ND + j % (H27_GS - H27_ND)] = 0.0;
   __syncthreads();
 
@@ -184,9 +190,12 @@ __global__ void __launch_bounds__(H27_THREADS, 2) hex27_kernel(const Hex27Args A
   for (int k = 0; k < H27_TPW; ++k) Cacc[k][0] = Cacc[k][1] = 0.0;
   double racc = 0.0;
 
-  for (int q0 = 0; q0 < nq_pad; q0 += H27_QC) {
-    // g[q][n][:] = dN[q][n] J^-1(q)
-    for (int j = tid; j < H27_QC * H27_NN; j += H27_THREADS) {
+  // g[q][n][:] = dN[q][n] J^-1(q) of one chunk -> Gq buffer; done by the warps with the fewest tiles (3..9: the three warps that
+  // own 9 tiles each are the critical path of the DMMA step and get none of it)
+  constexpr int G_FIRST = 96, G_THREADS = H27_THREADS - G_FIRST;
+  auto fill_chunk = [&](int q0, double* Gb) {
+    if (tid < G_FIRST) return;
+    for (int j = tid - G_FIRST; j < H27_QC * H27_NN; j += G_THREADS) {
       const int ql = j / H27_NN, n = j % H27_NN, q = q0 + ql;
       double g[3] = {0.0, 0.0, 0.0};
       if (q < nq) {
@@ -197,31 +206,39 @@ __global__ void __launch_bounds__(H27_THREADS, 2) hex27_kernel(const Hex27Args A
         for (int d = 0; d < 3; ++d) g[d] = d0 * inv[d] + d1 * inv[3 + d] + d2 * inv[6 + d];
       }
 #pragma unroll
-      for (int d = 0; d < 3; ++d) Gq[ql * H27_GS + n * 3 + d] = g[d];
+      for (int d = 0; d < 3; ++d) Gb[ql * H27_GS + n * 3 + d] = g[d];
     }
-    __syncthreads();
+  };
+  // Two Gq buffers: while the slower warps still multiply chunk k, the others already fill chunk k+1 -- ONE barrier per chunk.
+  fill_chunk(0, Gq);
+  __syncthreads();
+  const int rt = tid - (H27_THREADS - 96);                   // residual rows on the three lightest warps (7, 8, 9)
+  for (int q0 = 0, kc = 0; q0 < nq_pad; q0 += H27_QC, ++kc) {
+    const double* Gc = Gq + (kc & 1) * (H27_QC * H27_GS);
     {
       const double* ew = QP + (q0 + (l & 3)) * H27_QP + 9;
       if (!bdiag) {                                        // warp-uniform
-        if (bnc == 3) h27_block_chunk<3, 3, false>(Gq, ew, I0, J0, l, Cacc);
-        else h27_block_chunk<3, 2, false>(Gq, ew, I0, J0, l, Cacc);
+        if (bnc == 3) h27_block_chunk<3, 3, false>(Gc, ew, I0, J0, l, Cacc);
+        else h27_block_chunk<3, 2, false>(Gc, ew, I0, J0, l, Cacc);
       } else {
-        if (bnc == 3) h27_block_chunk<3, 3, true>(Gq, ew, I0, J0, l, Cacc);
-        else h27_block_chunk<2, 2, true>(Gq, ew, I0, J0, l, Cacc);
+        if (bnc == 3) h27_block_chunk<3, 3, true>(Gc, ew, I0, J0, l, Cacc);
+        else h27_block_chunk<2, 2, true>(Gc, ew, I0, J0, l, Cacc);
       }
     }
-    // residual r_(a,i) += sum_q S_q[i][:] . g_a(q)
-    if (tid < H27_ND) {
-      const int a = tid / 3, i = tid % 3;
+    // residual r_(a,i) += sum_q S_q[i][:] . g_a(q).  Tried and reverted: from the reference table instead of the shared
+    // gradients (dependent global loads: 38.4 -> 43.7 ms); 4 lanes per row with 11 warps x 6 tiles (more fragment loads: 40.8 ms)
+    if (rt >= 0 && rt < H27_ND) {
+      const int a = rt / 3, i = rt % 3;
       for (int ql = 0; ql < H27_QC; ++ql) {
         const double* S = QP + (q0 + ql) * H27_QP + 10 + i * 3;
-        const double* g = Gq + ql * H27_GS + a * 3;
+        const double* g = Gc + ql * H27_GS + a * 3;
         racc = fma(S[0], g[0], fma(S[1], g[1], fma(S[2], g[2], racc)));                   // problem.py:210
       }
     }
+    if (q0 + H27_QC < nq_pad) fill_chunk(q0 + H27_QC, Gq + ((kc + 1) & 1) * (H27_QC * H27_GS));
     __syncthreads();
   }
-  if (tid < H27_ND) A.Re[c * H27_ND + tid] = racc;
+  if (rt >= 0 && rt < H27_ND) A.Re[c * H27_ND + rt] = racc;
   if (A.Ke == nullptr) return;                             // residual only (block-uniform)
 
   // ---- phase 3: tiles -> G (mirrored); fragment: row = l/4, cols = 2(l%4), 2(l%4)+1 ----
@@ -275,7 +292,8 @@ using namespace femb200;
 
 extern "C" int fem_hex27_residual_jacobian(int law_id, const double* law_params_host, const double* points,
                                            const int32_t* cells, int64_t n_cells, const double* sol,
-                                           const double* internal_var, const double* ref_tables, int n_quad,
+                                           const double* internal_var, const double* ref_tables,
+                                           const double* ref_tables_t, int n_quad,
                                            const int32_t* corner_pos, double* Ke, double* Re, void* stream) {
   if (int e = check_device()) return e;
   FEM_REQUIRE(points && cells && sol && ref_tables && Re && law_params_host, "null pointer");
@@ -285,11 +303,11 @@ extern "C" int fem_hex27_residual_jacobian(int law_id, const double* law_params_
   FEM_REQUIRE(n_quad > 0 && n_quad <= 512, "unsupported number of quadrature points");
   if (n_cells == 0) return FEM_OK;
   Hex27Args A{};
-  A.points = points; A.cells = cells; A.sol = sol; A.iv = internal_var; A.ref = ref_tables;
+  A.points = points; A.cells = cells; A.sol = sol; A.iv = internal_var; A.ref = ref_tables; A.ref_t = ref_tables_t;
   A.corner_pos = corner_pos; A.Ke = Ke; A.Re = Re; A.C = n_cells; A.nq = n_quad; A.law = law_id;
   for (int i = 0; i < 8; ++i) A.p[i] = law_params_host[i];
   const int nq_pad = (n_quad + H27_QC - 1) / H27_QC * H27_QC;
-  const size_t work = (size_t)nq_pad * H27_QP + (nq_pad * H27_QP) % 2 + H27_QC * H27_GS;
+  const size_t work = (size_t)nq_pad * H27_QP + (nq_pad * H27_QP) % 2 + 2 * H27_QC * H27_GS;
   const size_t gsz = (size_t)88 * H27_GSS;
   const size_t smem = sizeof(double) * (3 * H27_ND + 1 + (work > gsz ? work : gsz));
   FEM_CUDA_CHECK(cudaFuncSetAttribute(hex27_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -99,6 +99,8 @@ class Problem:
         self._points = torch.from_numpy(fe.points).to(dev)
         self._cells = torch.from_numpy(fe.cells).to(dev)
         self._ref = torch.from_numpy(np.concatenate([fe.shape_grads_ref.reshape(-1), fe.quad_weights])).to(dev)
+        # the same dN with the point index fastest (HEX27 kernel: coalesced reads when thread = quadrature point)
+        self._ref_t = torch.from_numpy(np.ascontiguousarray(fe.shape_grads_ref.reshape(fe.num_quads, -1).T)).to(dev)
         # the plan is built by the library (fem_plan_create, csrc/plan.cu); FEM_PLAN=torch selects the torch construction
         # of plan.py (the one the CPU tests exercise), both give identical tables
         import os
@@ -366,7 +368,7 @@ class Problem:
         if self.ele_type == 'HEX27':
             _lib.check(lib.fem_hex27_residual_jacobian(
                 self._law.law_id, _lib.host_doubles(self._law.params()), _lib.ptr(self._points), _lib.ptr(self._cells),
-                self.num_cells, _lib.ptr(sol), _lib.ptr(iv), _lib.ptr(self._ref), fe.num_quads,
+                self.num_cells, _lib.ptr(sol), _lib.ptr(iv), _lib.ptr(self._ref), _lib.ptr(self._ref_t), fe.num_quads,
                 _lib.ptr(self.plan.corner_pos), _lib.ptr(self._Ke) if jac else None, _lib.ptr(self._Re), _lib.stream_ptr()))
         elif tiles:
             post = (_lib.ctypes.c_double * 3)()
