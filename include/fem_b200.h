@@ -217,6 +217,25 @@ int fem_gather_csr_tiles(int64_t n_blocks, const int32_t* gdesc, const int32_t* 
 int fem_gather_residual(int vec, int nn, int64_t n_nodes, const int32_t* nc_ptr, const int32_t* nc,
                         const double* Re, const double* f_ext, double* res, void* stream);
 
+/* ---- (1b) solution-dependent surface maps: get_surface_kernel (jax_fem/problem.py:238-259) and its tangent
+ *      (problem.py:289-325) for the registered surface law val_i(u) = coef_i (u_i - uref_i)^power (Robin / convection / spring
+ *      foundation; applications/robin_bc/example.py:59-67 is coef 5, power 2).  law_host[7] = coef[3], uref[3], power.
+ *      One boundary set per call: its F faces (face_cell, face_lid = local face of the cell), nanson (F, fq) = Nanson scale x
+ *      face weight (fe.py:180-182, precomputed: independent of u), face_vals (local faces, fq, nn) = face shape values
+ *      (basis.py:178-250); bnode: the set's boundary nodes with their incident (face, local node) pairs in bf_ptr / bf_face /
+ *      bf_local, ascending face order.  fem_face_residual ADDS the face residual to res (nodes, vec); fem_face_tangent ADDS the
+ *      face tangent to the assembled CSR values (rows flagged in bc_flag stay unit rows).  Each output is written by one
+ *      thread in a fixed order: deterministic, no atomics.                                                            */
+int fem_face_residual(int vec, int nn, int fq, int64_t n_bnodes, const int32_t* bnode, const int32_t* bf_ptr,
+                      const int32_t* bf_face, const int32_t* bf_local, const int32_t* face_cell,
+                      const int32_t* face_lid, const double* nanson, const double* face_vals, const int32_t* cells,
+                      const double* sol, const double* law_host, double* res, void* stream);
+int fem_face_tangent(int vec, int nn, int fq, int64_t n_bnodes, const int32_t* bnode, const int32_t* bf_ptr,
+                     const int32_t* bf_face, const int32_t* bf_local, const int32_t* face_cell,
+                     const int32_t* face_lid, const double* nanson, const double* face_vals, const int32_t* cells,
+                     const double* sol, const double* law_host, const int32_t* brow_ptr, const int32_t* bcol,
+                     const uint8_t* bc_flag, double* data, void* stream);
+
 /* ---- (3) Dirichlet operations (jax_fem/solver.py:290-363) on merged (last-wins) row lists    */
 /* apply_bc_vec: res[row] = sol[row] - val*scale                                                  */
 int fem_apply_bc_vec(int64_t n_bc, const int32_t* bc_rows, const double* bc_vals, double scale,

@@ -36,6 +36,8 @@ _SIGNATURES = {
     "fem_element_tiles": (_i, [_i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fem_gather_csr_tiles": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fem_gather_residual": (_i, [_i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fem_face_residual": (_i, [_i, _i, _i, _i64] + [_vp] * 13),
+    "fem_face_tangent": (_i, [_i, _i, _i, _i64] + [_vp] * 16),
     "fem_apply_bc_vec": (_i, [_i64, _vp, _vp, _d, _vp, _vp, _vp]),
     "fem_bc_initial_guess": (_i, [_i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "fem_spmv": (_i, [_i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),

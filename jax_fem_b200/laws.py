@@ -89,6 +89,40 @@ class SIMP(Law):
         return [self.Emax, self.Emin, self.nu, self.penal, 1.0 if self.plane_stress else 0.0]
 
 
+class SurfaceLaw:
+    """A solution-dependent surface map with hand-written face kernels (csrc/faces.cu).  The reference accepts any callable
+    ``surface_map(u, x)`` and differentiates it (problem.py:238-259, 289-325); here a u-dependent map must be one of the
+    registered objects below -- plain callables stay supported as long as they do not depend on u."""
+
+    def law_host(self, vec):
+        raise NotImplementedError
+
+
+class RobinPower(SurfaceLaw):
+    """val_i(u) = coef_i (u_i - u_ref_i)^power on a boundary set: convective / Robin boundary condition or elastic foundation
+    (power 1), the nonlinear Robin map ``5 * u**2`` of applications/robin_bc/example.py:59-67 (coef 5, power 2)."""
+
+    def __init__(self, coef, power=1.0, u_ref=0.0):
+        import numpy as np
+        self.coef = np.atleast_1d(np.asarray(coef, dtype=np.float64))
+        self.u_ref = np.atleast_1d(np.asarray(u_ref, dtype=np.float64))
+        self.power = float(power)
+
+    def law_host(self, vec):
+        import numpy as np
+        coef = np.broadcast_to(self.coef, (vec,)) if self.coef.size in (1, vec) else None
+        uref = np.broadcast_to(self.u_ref, (vec,)) if self.u_ref.size in (1, vec) else None
+        if coef is None or uref is None:
+            raise ValueError(f"RobinPower: coef / u_ref must be scalars or have {vec} components")
+        out = np.zeros(7)
+        out[:vec], out[3:3 + vec], out[6] = coef, uref, self.power
+        return out
+
+    def value(self, u):
+        """NumPy evaluation (host-side post-processing only)."""
+        return self.coef * (u - self.u_ref) ** self.power
+
+
 REGISTERED = {
     ('HEX8', 1, Poisson), ('HEX8', 3, LinearElasticity), ('HEX8', 3, NeoHookean), ('HEX8', 3, SIMP),
     ('QUAD4', 1, Poisson), ('QUAD4', 2, LinearElasticity), ('QUAD4', 2, SIMP),

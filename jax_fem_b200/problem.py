@@ -48,8 +48,9 @@ def _eval_load_map(fn, u, x, vec):
     f0 = at(np.zeros((len(x), vec)))
     f1 = at(np.full((len(x), vec), 0.37))
     if not np.array_equal(f0, f1):
-        raise NotImplementedError("solution-dependent mass/surface maps are not registered on the B200 hot path "
-                                  "(their tangent would need a kernel of its own); they do not fall back")
+        raise NotImplementedError("a mass / surface map given as a Python callable must not depend on u; solution-dependent "
+                                  "surface maps are registered as jax_fem_b200.laws.RobinPower (csrc/faces.cu), "
+                                  "solution-dependent mass maps are not registered; nothing falls back")
     return f0
 
 
@@ -158,9 +159,13 @@ class Problem:
             for i in range(fe.vec):
                 f[:, i] += np.bincount(fe.cells.reshape(-1), weights=contrib[:, :, i].reshape(-1), minlength=fe.num_total_nodes)
             used = True
+        self._face_sets = []
         if hasattr(self, 'get_surface_maps'):
             for k, b in enumerate(self.boundary_inds_list):
                 if len(b) == 0:
+                    continue
+                if isinstance(self.get_surface_maps()[k], laws.SurfaceLaw):       # u-dependent: device face kernels
+                    self._face_sets.append(self._build_face_set(k, b, self.get_surface_maps()[k]))
                     continue
                 x = fe.get_physical_surface_quad_points(b)
                 _, nanson = fe.get_face_shape_grads(b)
@@ -172,6 +177,46 @@ class Problem:
                     f[:, i] += np.bincount(nodes, weights=contrib[:, :, i].reshape(-1), minlength=fe.num_total_nodes)
                 used = True
         return torch.from_numpy(f).to(self.device) if used else None
+
+    def _build_face_set(self, k, b, law):
+        """Device tables of one boundary set for fem_face_residual / fem_face_tangent: its faces, the (u-independent) Nanson
+        scale x weight per face quadrature point, and for every boundary node its (face, local node) pairs."""
+        fe, dev = self.fes[0], self.device
+        _, nanson = fe.get_face_shape_grads(b)                                     # (F, FQ)
+        face_nodes = fe.face_inds[b[:, 1]]                                         # (F, V) local nodes of the cell on the face
+        glob = fe.cells[b[:, 0][:, None], face_nodes]                              # (F, V) global nodes
+        fidx = np.repeat(np.arange(len(b)), face_nodes.shape[1])
+        order = np.lexsort((fidx, glob.reshape(-1)))                               # by node, then ascending face
+        nodes_sorted = glob.reshape(-1)[order]
+        bnode, counts = np.unique(nodes_sorted, return_counts=True)
+        i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+        f64 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+        return dict(k=k, law=law, n_bnodes=len(bnode), bnode=i32(bnode), bf_ptr=i32(np.concatenate([[0], np.cumsum(counts)])),
+                    bf_face=i32(fidx[order]), bf_local=i32(face_nodes.reshape(-1)[order]), face_cell=i32(b[:, 0]),
+                    face_lid=i32(b[:, 1]), nanson=f64(nanson), fvals=f64(fe.face_shape_vals), fq=fe.num_face_quads,
+                    law_host=law.law_host(fe.vec))
+
+    def _face_args(self, fs, sol):
+        fe, P = self.fes[0], _lib.ptr
+        law = (_lib.ctypes.c_double * 7)(*fs['law_host'])
+        return (fe.vec, fe.num_nodes, fs['fq'], fs['n_bnodes'], P(fs['bnode']), P(fs['bf_ptr']), P(fs['bf_face']), P(fs['bf_local']),
+                P(fs['face_cell']), P(fs['face_lid']), P(fs['nanson']), P(fs['fvals']), P(self._cells), P(sol), law)
+
+    def _add_face_residual(self, sol, res):
+        """+= surface kernel of the registered u-dependent surface maps (problem.py:238-259)."""
+        for fs in self._face_sets:
+            _lib.check(_lib.load().fem_face_residual(*self._face_args(fs, sol), _lib.ptr(res), _lib.stream_ptr()))
+        return res
+
+    def add_face_tangent(self, sol, data):
+        """+= d(surface kernel)/du in the assembled CSR values (the face blocks of problem.V, problem.py:456-458)."""
+        if self._face_sets:
+            p = self.plan
+            _, _, flag = self.bc_data()
+            for fs in self._face_sets:
+                _lib.check(_lib.load().fem_face_tangent(*self._face_args(fs, sol), _lib.ptr(p.brow_ptr), _lib.ptr(p.bcol),
+                                                        _lib.ptr(flag), _lib.ptr(data), _lib.stream_ptr()))
+        return data
 
     # ---- flat <-> list helpers (jax.flatten_util in the reference) -----------------------------------
     def unflatten_fn_sol_list(self, dofs):
@@ -293,8 +338,8 @@ class Problem:
         res = torch.empty((fe.num_total_nodes, fe.vec), dtype=torch.float64, device=dev)
         _lib.check(lib.fem_gather_residual(fe.vec, fe.num_nodes, fe.num_total_nodes, P(p.nc_ptr), P(p.nc),
                                            P(self._Re), P(self._f_ext), P(res), _lib.stream_ptr()))
-        self._A_data, self._A_bc_key = data, self._bc_cache[0]
-        return res
+        self._A_data, self._A_bc_key = self.add_face_tangent(sol, data), self._bc_cache[0]
+        return self._add_face_residual(sol, res)
 
     def check_assembly_status(self, block=True):
         """Raise if a wait of the last one-kernel assembly exceeded its limit (a schedule bug: the values are invalid).
@@ -333,8 +378,8 @@ class Problem:
             P(pp.pn_acc), P(pp.pn_info), P(pp.lnodes), P(pp.pc_cell), P(pp.pc_ln), P(pp.pc_lm), P(pp.ck_cell), P(pp.ck_lane),
             P(pp.ck_rnd), P(pp.ln_desc), P(pp.ln_slot), P(flag), P(self._f_ext), P(data), P(res), pp.config,
             _lib.stream_ptr()))
-        self._A_data, self._A_bc_key = data, self._bc_cache[0]
-        return res
+        self._A_data, self._A_bc_key = self.add_face_tangent(sol, data), self._bc_cache[0]
+        return self._add_face_residual(sol, res)
 
     def assembled_values(self):
         """CSR values of the last newton_update for get_A: the fused kernel's output when it ran with the current
@@ -385,7 +430,7 @@ class Problem:
         p = self.plan
         _lib.check(lib.fem_gather_residual(fe.vec, fe.num_nodes, fe.num_total_nodes, _lib.ptr(p.nc_ptr), _lib.ptr(p.nc),
                                            _lib.ptr(self._Re), _lib.ptr(self._f_ext), _lib.ptr(res), _lib.stream_ptr()))
-        return res
+        return self._add_face_residual(sol, res)
 
     def _launch_element(self, lib, fe, sol, iv, jac):
         _lib.check(lib.fem_element_residual_jacobian(
@@ -445,8 +490,28 @@ class Problem:
         """COO values aligned with I/J: cell blocks, then (zero) face blocks (problem.py:453-458)."""
         Ke = self.element_tangents()
         ndof = Ke.shape[1]
-        nface = sum(len(b) for b in self.boundary_inds_list)
-        return torch.cat([Ke.reshape(-1), torch.zeros(nface * ndof * ndof, dtype=torch.float64, device=self.device)])
+        parts = [Ke.reshape(-1)]
+        laws_by_set = {fs['k']: fs for fs in self._face_sets}
+        for k, b in enumerate(self.boundary_inds_list):
+            parts.append(self._face_blocks(laws_by_set[k]).reshape(-1) if k in laws_by_set else
+                         torch.zeros(len(b) * ndof * ndof, dtype=torch.float64, device=self.device))
+        return torch.cat(parts)
+
+    def _face_blocks(self, fs):
+        """(F, ndof, ndof) face tangents of a registered surface law in the reference's V layout (host-side convenience:
+        the hot path adds them straight into the CSR values, fem_face_tangent)."""
+        fe = self.fes[0]
+        law, vec = fs['law_host'], fe.vec
+        coef = torch.tensor(law[:vec], dtype=torch.float64, device=self.device)
+        uref = torch.tensor(law[3:3 + vec], dtype=torch.float64, device=self.device)
+        N = fs['fvals'][fs['face_lid'].long()]                                      # (F, FQ, NN)
+        u = torch.einsum('fqn,fnv->fqv', N, self._last_sol[self._cells[fs['face_cell'].long()].long()])
+        d = coef * law[6] * (u - uref) ** (law[6] - 1.0)                            # (F, FQ, vec)
+        K = torch.einsum('fqi,fqa,fqb,fq->faib', d, N, N, fs['nanson'])
+        out = torch.zeros(K.shape[0], fe.num_nodes, vec, fe.num_nodes, vec, dtype=torch.float64, device=self.device)
+        for i in range(vec):
+            out[:, :, i, :, i] = K[:, :, i, :]
+        return out.reshape(K.shape[0], fe.num_nodes * vec, fe.num_nodes * vec)
 
     def _coo(self):
         fe = self.fes[0]

@@ -137,6 +137,7 @@ def get_A(problem):
     else:
         _lib.check(_lib.load().fem_gather_csr(fe.vec, fe.num_nodes, p.n_gather_blocks, _lib.ptr(p.gdesc), _lib.ptr(emeta),
                                               _lib.ptr(p.src), _lib.ptr(Ke), _lib.ptr(data), _lib.stream_ptr()))
+    problem.add_face_tangent(problem._last_sol, data)      # registered u-dependent surface maps (problem.py:456-458)
     return CSRMatrix(p, data)
 
 

@@ -183,12 +183,15 @@ class Problem:
     """
 
     def __init__(self, mesh, vec, dim, ele_type='HEX8', quadrature_order=None, dirichlet_bc_info=None,
-                 location_fns=None, law=None, mass_map=None, surface_maps=None, internal_vars=()):
+                 location_fns=None, law=None, mass_map=None, surface_maps=None, internal_vars=(), surface_map_jacs=None):
         self.fe = FiniteElement(mesh, vec, dim, ele_type, quadrature_order, dirichlet_bc_info)
         self.fes = [self.fe]
         fe = self.fe
         self.vec, self.dim, self.law = vec, dim, law
         self.mass_map, self.surface_maps = mass_map, surface_maps or []
+        # d(surface_map)/du (..., vec, vec) per boundary set, or None for a u-independent map (the reference gets it from jacfwd
+        # of the surface kernel, problem.py:299-301)
+        self.surface_map_jacs = surface_map_jacs or [None] * len(self.surface_maps)
         self.internal_vars = list(internal_vars)
         self.num_cells = fe.num_cells
         self.cells = fe.cells
@@ -257,6 +260,17 @@ class Problem:
         t = np.broadcast_to(self.surface_maps[k](u, x), u.shape)
         return np.einsum('fqv,fqn,fq->fnv', t, vals, nanson)
 
+    def face_jacobians(self, sol, k):
+        """d(face residual)/d(cell dofs) of boundary set k -> (S, ndof, ndof), row = test dof (problem.py:289-325)."""
+        b = self.boundary_inds_list[k]
+        vals, nanson, x = self.face_data[k]
+        if self.surface_map_jacs[k] is None:
+            return np.zeros((len(b), self.ndof, self.ndof))
+        u = np.einsum('fnv,fqn->fqv', sol[self.cells[b[:, 0]]], vals)
+        dt = np.broadcast_to(self.surface_map_jacs[k](u, x), u.shape + (self.vec,))          # (S,FQ,vec,vec)
+        K = np.einsum('fqik,fqa,fqb,fq->faibk', dt, vals, vals, nanson)
+        return K.reshape(len(b), self.ndof, self.ndof)
+
     def compute_residual(self, sol):
         """problem.py:426-445 -> (nodes, vec)."""
         res = np.zeros((self.fe.num_total_nodes, self.vec))
@@ -268,12 +282,14 @@ class Problem:
     def newton_update(self, sol):
         """problem.py:447-460: residual + COO values V (cells, then zero face blocks)."""
         self.V_cells = self.cell_jacobians(sol)
+        self.V_faces = [self.face_jacobians(sol, k) for k in range(len(self.boundary_inds_list))]
         return self.compute_residual(sol)
 
     def coo_values(self):
         V = self.V_cells.reshape(-1)
-        for b in self.boundary_inds_list:       # u-independent loads: exact zeros (problem.py:456-458)
-            V = np.hstack((V, np.zeros(len(b) * self.ndof ** 2)))
+        faces = getattr(self, 'V_faces', None)
+        for k, b in enumerate(self.boundary_inds_list):       # u-independent loads: exact zeros (problem.py:456-458)
+            V = np.hstack((V, faces[k].reshape(-1) if faces is not None else np.zeros(len(b) * self.ndof ** 2)))
         return V
 
     # solver.py:511-516

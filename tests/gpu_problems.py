@@ -69,3 +69,22 @@ class NeoHookeanInverse(Problem):             # hyperelastic3d_common.py:45-80
 
     def set_params(self, rho):
         self.internal_vars = [rho]
+
+
+class RobinPoisson(Problem):                   # applications/robin_bc/example.py:59-67: surface_map(u, x) = 5 u^2 on two faces
+    def get_tensor_map(self):
+        return laws.Poisson(1.0)
+
+    def get_mass_map(self):
+        return lambda u, x: -np.array([10. * np.exp(-((x[0] - .5) ** 2 + (x[1] - .5) ** 2) / 0.02)])
+
+    def get_surface_maps(self):
+        return [laws.RobinPower(5.0, power=2.0), laws.RobinPower(2.0, power=1.0, u_ref=0.3)]
+
+
+class SpringFoundation(Problem):               # elastic foundation k u on one face + a dead load on another
+    def get_tensor_map(self):
+        return laws.LinearElasticity(70e3, 0.3)
+
+    def get_surface_maps(self):
+        return [laws.RobinPower([3e3, 5e3, 7e3]), lambda u, x: np.array([0., 0., 100.])]

@@ -560,6 +560,58 @@ def test_tile_major_staging_equals_block_staging(law, monkeypatch):
     assert np.array_equal(out["tiles"][2], out["blocks"][2])
 
 
+@pytest.mark.parametrize("case", ["robin_poisson", "spring_elasticity", "robin_quad4"])
+@pytest.mark.parametrize("mode", ["staged", "ring", "fused"])
+def test_solution_dependent_surface_maps_match_oracle(case, mode, monkeypatch):
+    """registered u-dependent surface maps (laws.RobinPower; the reference's robin_bc map 5 u^2 and a
+    spring foundation).  Face residual and face tangent are added by csrc/faces.cu to the nodal residual and to the assembled CSR
+    values; residual, CSR values, problem.V (face blocks) and the Newton solution must equal the oracle's."""
+    import jax_fem_b200 as jf
+    import gpu_problems as gp
+    rng = np.random.default_rng(8)
+    if case == "robin_quad4":
+        if mode != "staged":
+            pytest.skip("one-kernel modes are registered for HEX8 elasticity")
+        m = jf.rectangle_mesh(9, 7, 1., 1.)
+        pts, cells, ele, dim, vec = m.points + 0.01 * rng.uniform(-1, 1, m.points.shape), m.cells_dict['quad'], 'QUAD4', 2, 1
+        m_pts = m.points
+    else:
+        m_pts, cells = perturbed_box(6, seed=2)
+        pts, ele, dim, vec = m_pts, 'HEX8', 3, (1 if case == "robin_poisson" else 3)
+    lo = lambda p: p[0] < 0.02
+    hi = lambda p: p[0] > 0.98
+    side = lambda p: p[1] > 0.98
+    monkeypatch.setenv("FEM_ASSEMBLY", mode)
+    if vec == 1:
+        bc = [[lo], [0], [lambda p: 0.4]]
+        cls = type("RobinQ", (gp.RobinPoisson,), {"get_mass_map": lambda self: (lambda u, x: -np.array([3.0]))}) if dim == 2 else gp.RobinPoisson
+        prob = cls(jf.Mesh(pts, cells), vec=1, dim=dim, ele_type=ele, dirichlet_bc_info=bc, location_fns=[hi, side])
+        mass = (lambda u, x: -3.0 + 0. * u) if dim == 2 else \
+            (lambda u, x: -10. * np.exp(-((x[..., 0] - .5) ** 2 + (x[..., 1] - .5) ** 2) / 0.02)[..., None] + 0. * u)
+        opb = fem.Problem(fem.Mesh(pts, cells), 1, dim, ele_type=ele, dirichlet_bc_info=bc, location_fns=[hi, side], law=olaws.Poisson(1.0),
+                          mass_map=mass, surface_maps=[lambda u, x: 5 * u ** 2, lambda u, x: 2.0 * (u - 0.3)],
+                          surface_map_jacs=[lambda u, x: (10 * u)[..., None], lambda u, x: 2.0 * np.ones(u.shape + (1,))])
+    else:
+        bc = [[lo] * 3, [0, 1, 2], [lambda p: 0., lambda p: 0.01, lambda p: 0.]]
+        k = np.array([3e3, 5e3, 7e3])
+        prob = gp.SpringFoundation(jf.Mesh(pts, cells), vec=3, dim=3, dirichlet_bc_info=bc, location_fns=[hi, side])
+        opb = fem.Problem(fem.Mesh(pts, cells), 3, 3, dirichlet_bc_info=bc, location_fns=[hi, side], law=olaws.LinearElastic(70e3, 0.3),
+                          surface_maps=[lambda u, x: k * u, lambda u, x: np.array([0., 0., 100.]) + 0. * u],
+                          surface_map_jacs=[lambda u, x: np.broadcast_to(np.diag(k), u.shape + (3,)), None])
+    if prob.assembly_mode() != mode:
+        pytest.skip(f"{mode} is not registered for this problem")
+    sol = 0.3 + 0.1 * rng.standard_normal((len(pts), vec))
+    res = prob.newton_update([torch.from_numpy(sol).cuda()])[0]
+    A = jf.get_A(prob)
+    ores = opb.newton_update(sol)
+    oA = fem.get_A(opb)
+    assert np.array_equal(host(A.getValuesCSR()[1]), oA.indices)
+    assert relmax(host(A.data), oA.data) <= VAL_TOL and relmax(host(res), ores) <= VAL_TOL
+    assert relmax(host(prob.V), opb.coo_values()) <= VAL_TOL                    # face blocks of the reference's V
+    x = jf.solver(prob, {'jax_solver': {}})[0]
+    assert relmax(host(x), fem.solver(opb)) <= SOL_TOL
+
+
 def test_csr_diagonal_beyond_2_30_nonzeros():
     """The Jacobi preconditioner of the 200^3 mesh (nnz = 1.95e9): row offsets above 2^30 must not overflow the binary search
     for the diagonal entry (lo + hi in int32 did: the first 200^3 solve on one GPU hung).  Synthetic banded matrix with

@@ -146,3 +146,32 @@ def test_newton_with_step_halving_line_search_reaches_the_same_equilibrium():
         sols.append(fem.solver(pb, log=log, line_search_flag=flag))
         its.append(len(log) - 1)
     assert its[1] > its[0] and np.abs(sols[0] - sols[1]).max() <= 1e-8 * np.abs(sols[0]).max()
+
+
+def test_oracle_face_tangent_is_the_derivative_of_the_face_residual():
+    """u-dependent surface maps (Robin terms, problem.py:238-259 + 289-325): the oracle's analytic face tangent must be the
+    central difference of its own residual, for the reference's nonlinear Robin map 5 u^2 (applications/robin_bc) and for a
+    vector spring foundation."""
+    import numpy as np
+    from oracle import fem, laws
+    m = fem.box_mesh(3, 2, 2, 1.5, 1.0, 1.0)
+    rng = np.random.default_rng(0)
+    pts = m.points + 0.03 * rng.uniform(-1, 1, m.points.shape)
+    right = lambda p: np.isclose(p[0], 1.5, atol=0.05)
+    top = lambda p: np.isclose(p[2], 1.0, atol=0.05)
+    for vec, law, maps, jacs in (
+            (1, laws.Poisson(1.0), [lambda u, x: 5 * u ** 2, lambda u, x: 2.0 * (u - 0.3)],
+             [lambda u, x: (10 * u)[..., None], lambda u, x: 2.0 * np.ones(u.shape + (1,))]),
+            (3, laws.LinearElastic(70e3, 0.3), [lambda u, x: np.array([3., 5., 7.]) * u, lambda u, x: 0. * u + np.array([0., 0., 1.])],
+             [lambda u, x: np.broadcast_to(np.diag([3., 5., 7.]), u.shape + (3,)), None])):
+        pb = fem.Problem(fem.Mesh(pts, m.cells), vec, 3, location_fns=[right, top], law=law, surface_maps=maps, surface_map_jacs=jacs)
+        sol = 0.2 + 0.1 * rng.standard_normal((len(pts), vec))
+        pb.newton_update(sol)
+        A = fem.get_A(pb).toarray()
+        n = A.shape[0]
+        h = 1e-6
+        for j in rng.integers(0, n, 12):
+            e = np.zeros(n)
+            e[j] = h
+            col = (pb.compute_residual(sol + e.reshape(sol.shape)) - pb.compute_residual(sol - e.reshape(sol.shape))).reshape(-1) / (2 * h)
+            assert np.abs(col - A[:, j]).max() <= 1e-6 * max(np.abs(A[:, j]).max(), 1.0)
