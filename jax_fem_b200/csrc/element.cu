@@ -532,18 +532,17 @@ struct NhDmmaLayout {
   static constexpr int NN = 8, NQ = 8, DIM = 3, VEC = 3;
   static constexpr int TAB_STRIDE = 25, TAB_SIZE = NQ * TAB_STRIDE + NQ;
   static constexpr int GS = 28;                        // per-q stride of g[n][d] (conflict-free fragments)
-  static constexpr int OFF_X = 0, OFF_U = 24;          // X[8][3], U[8][3]
-  static constexpr int OFF_G = 48;                     // g[q][n][d]
+  static constexpr int OFF_X = 0, OFF_U = 24;          // X[8][3], U[8][3]: dead once every lane of the cell holds g and grad u,
+  static constexpr int OFF_G = 0;                      // g[q][n][d] is written over them
   static constexpr int OFF_FH = OFF_G + NQ * GS;       // F[q][3][3], H[q][3][3] = F^-T (f = F g and h = H g are formed in phase 2)
-  static constexpr int OFF_S = OFF_FH + NQ * 18;       // S[q][i][d] = P JxW
-  static constexpr int OFF_C = OFF_S + NQ * 9;         // c1..c4 per q
-  static constexpr int CELL = OFF_C + NQ * 4 + 2;      // 522 = 10 (mod 16); >= 4 * 72 doubles of output staging
+  static constexpr int OFF_C = OFF_FH + NQ * 18;       // c1..c4 per q
+  static constexpr int CELL = OFF_C + NQ * 4 + 10;     // 410 = 10 (mod 16); >= 4 * 72 doubles of output staging; 4 CTAs per SM
   static constexpr int WARP = 4 * CELL + 16;           // + 32 ints of corner positions
   static constexpr int WARPS = 4;
 };
 
 template <bool TILES>
-__global__ void __launch_bounds__(NhDmmaLayout::WARPS * 32, 3) element_nh_dmma_kernel(const ElemArgs A) {
+__global__ void __launch_bounds__(NhDmmaLayout::WARPS * 32, 4) element_nh_dmma_kernel(const ElemArgs A) {
   using L = NhDmmaLayout;
   constexpr int NN = 8, NQ = 8, DIM = 3, VEC = 3, ND = 24;
   extern __shared__ __align__(16) double sm[];
@@ -569,22 +568,18 @@ __global__ void __launch_bounds__(NhDmmaLayout::WARPS * 32, 3) element_nh_dmma_k
     pos[l] = A.corner_pos ? A.corner_pos[c1 * NN + q] : (int)(c1 * NN + q);
   }
   __syncthreads();
+  double g[NN][DIM], ug[VEC][DIM], w = 0.0;
   if (act1) {
-    double g[NN][DIM];
-    const double w = qp_geometry<NN, DIM>(cb + L::OFF_X, tab + q * L::TAB_STRIDE, tab[NQ * L::TAB_STRIDE + q], g);
-    double ug[VEC][DIM];
+    w = qp_geometry<NN, DIM>(cb + L::OFF_X, tab + q * L::TAB_STRIDE, tab[NQ * L::TAB_STRIDE + q], g);
     qp_grad_u<NN, DIM, VEC>(cb + L::OFF_U, g, ug);
+  }
+  __syncwarp();                                            // X / U of the warp's cells are consumed: g goes on top of them
+  if (act1) {
     const double* ivq = A.iv ? A.iv + c1 * NQ + q : nullptr;
     const double E = A.p[0] * (ivq ? *ivq : 1.0), nu = A.p[1];
     const double mu = E / (2.0 * (1.0 + nu)), kappa = E / (3.0 * (1.0 - 2.0 * nu));
     NHPoint k;
     nh_kinematics(ug, mu, A.p[2] != 0.0, k);
-    double P[3][3];
-    nh_stress(k, kappa, P);
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) cb[L::OFF_S + q * 9 + i * 3 + d] = P[i][d] * w;
 #pragma unroll
     for (int n = 0; n < NN; ++n)
 #pragma unroll
@@ -597,7 +592,7 @@ __global__ void __launch_bounds__(NhDmmaLayout::WARPS * 32, 3) element_nh_dmma_k
         cb[L::OFF_FH + q * 18 + 9 + i * 3 + j] = k.H[i][j];
       }
     double* cc = cb + L::OFF_C + q * 4;
-    cc[0] = k.m * w;                                                             // delta_ik (g_a . g_b)
+    cc[0] = k.m * w;                                                             // delta_ik (g_a . g_b); also P JxW = c1 F - c4 H
     cc[1] = -(2.0 / 3.0) * k.m * w;                                              // f_a h_b + h_a f_b
     cc[2] = ((2.0 / 9.0) * k.m * k.I1 + kappa * (2.0 * k.J - 1.0) * k.J) * w;    // h_a h_b
     cc[3] = (k.m * k.I1 / 3.0 - kappa * (k.J - 1.0) * k.J) * w;                  // h_b h_a (swapped)
@@ -612,6 +607,7 @@ __global__ void __launch_bounds__(NhDmmaLayout::WARPS * 32, 3) element_nh_dmma_k
     if (c >= A.C) break;                                   // warp-uniform
     const double* cj = wb + j * L::CELL;
     double gq[2][3], fq[2][3], hq[2][3], ga[2][3], pa[2][3], qa[2][3], ra[2][3];
+    double R[3] = {0.0, 0.0, 0.0};                          // P JxW g_a = c1 f_a - c4 h_a, summed over the lane's two points
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       const int qq = t + 4 * s;
@@ -631,6 +627,7 @@ __global__ void __launch_bounds__(NhDmmaLayout::WARPS * 32, 3) element_nh_dmma_k
         pa[s][d] = k2 * fq[s][d] + k3 * hq[s][d];
         qa[s][d] = k2 * hq[s][d];
         ra[s][d] = k4 * hq[s][d];
+        R[d] += fma(k1, fq[s][d], -ra[s][d]);
       }
     }
     double D[2] = {0.0, 0.0};
@@ -656,20 +653,17 @@ __global__ void __launch_bounds__(NhDmmaLayout::WARPS * 32, 3) element_nh_dmma_k
           dmma884(C[I][J], ra[s][J], hq[s][I]);
         }
       }
-    // residual: B[q][col] = S_q[i = col][d] for col < 3 (col = l/4), zero otherwise
-    double R[2] = {0.0, 0.0};
+    // residual r_n[i] = sum over the 8 points: the 4 lanes of node n hold two points each
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      const double b0 = (n < 3) ? cj[L::OFF_S + t * 9 + n * 3 + d] : 0.0;
-      const double b1 = (n < 3) ? cj[L::OFF_S + (t + 4) * 9 + n * 3 + d] : 0.0;
-      dmma884(R, gq[0][d], b0);
-      dmma884(R, gq[1][d], b1);
+      R[d] += __shfl_xor_sync(0xffffffffu, R[d], 1);
+      R[d] += __shfl_xor_sync(0xffffffffu, R[d], 2);
     }
     if (t == 0) {
       A.Re[c * ND + n * 3 + 0] = R[0];
       A.Re[c * ND + n * 3 + 1] = R[1];
     } else if (t == 1) {
-      A.Re[c * ND + n * 3 + 2] = R[0];
+      A.Re[c * ND + n * 3 + 2] = R[2];
     }
     if constexpr (TILES) {
       // tile-major row (9 tiles of 8 doubles): the fragments ARE the tiles, 16 bytes per lane and tile, no staging
