@@ -40,6 +40,8 @@ struct Hex27Args {
   const double* ref;         // [nq*27*3] dN, [nq] w
   const double* ref_t;       // [27*3][nq] the same dN with the point index fastest (coalesced reads when thread = point) or nullptr
   const int32_t* corner_pos;
+  const double* affine;      // [27][3] reference node coordinates, then [3][3][27][27] reference Gram tables; or nullptr
+  int32_t* list;             // [0] = number of cells left to the general kernel, [1..] their ids (written by the affine pass) or nullptr
   double* Ke;                // (C*27, 244)
   double* Re;                // (C, 81)
   int64_t C;
@@ -90,8 +92,7 @@ __device__ __forceinline__ void h27_block_chunk(const double* __restrict__ Gq, c
   }
 }
 
-__global__ void __launch_bounds__(H27_THREADS, 2) hex27_kernel(const Hex27Args A) {
-  extern __shared__ __align__(16) double sm[];
+__device__ __forceinline__ void hex27_cell(const Hex27Args& A, const int64_t c, double* sm) {
   const int nq = A.nq;
   const int nq_pad = (nq + H27_QC - 1) / H27_QC * H27_QC;
   double* X = sm;                          // [27][3]
@@ -102,7 +103,6 @@ __global__ void __launch_bounds__(H27_THREADS, 2) hex27_kernel(const Hex27Args A
   double* Gq = QP + nq_pad * H27_QP + (nq_pad * H27_QP) % 2;   // 2 x [32][100]
   double* G = work;                        // [88][89] overlays QP + Gq after the main loop
   __shared__ int pos[H27_NN];
-  const int64_t c = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
 
   if (tid < H27_NN) {
@@ -285,6 +285,154 @@ __global__ void __launch_bounds__(H27_THREADS, 2) hex27_kernel(const Hex27Args A
   }
 }
 
+// Persistent CTAs over the cells: all of them, or the list the affine pass left (its order does not matter: cells are independent).
+__global__ void __launch_bounds__(H27_THREADS, 2) hex27_kernel(const Hex27Args A) {
+  extern __shared__ __align__(16) double sm[];
+  const int64_t n = A.list ? A.list[0] : A.C;
+  for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+    hex27_cell(A, A.list ? A.list[1 + i] : i, sm);
+    __syncthreads();
+  }
+}
+
+
+// ---- affine cells ------------------------------------------------------------------------------------------
+// If the map x(xi) = sum_n X_n N_n(xi) of a cell is affine (every cell of a box / sheared / stretched mesh), J is constant and
+//   G_ab[I][J] = sum_q E w_q detJ (dN_a J^-1)_I (dN_b J^-1)_J = E detJ (J^-T Ghat_ab J^-1)[I][J],   Ghat_ab[e][f] = sum_q w_q dN_a^e dN_b^f,
+// with the 9 x 27 x 27 reference Gram tables Ghat computed once: 59 k FMA per cell instead of 912 k, exact up to the rounding of
+// the reassociated sum.  The test is exact and made per cell on every call: the Lagrange basis reproduces affine functions, so the
+// map is affine iff every node sits where the affine map through the corners xi = 0, e_1, e_2, e_3 puts its reference point,
+// X_n = X_0 + J xi_n with J = [X_1 - X_0, X_2 - X_0, X_3 - X_0]; with SIMP the density must also be constant over the cell's
+// points.  Everything else (curved cells, graded density) is listed for hex27_kernel.  The stress is linear in grad u for the
+// registered laws, so the element residual is K_e u_e (problem.py:204-210 with a constant tangent).
+constexpr int H27A_THREADS = 256;
+constexpr int H27A_NODE_TAB = H27_ND;                        // xi_n [27][3]
+constexpr int H27A_GRAM = 9 * H27_NN * H27_NN;               // Ghat[e][f][a][b]
+constexpr int H27A_ROW = 244;
+
+__global__ void __launch_bounds__(H27A_THREADS, 2) hex27_affine_kernel(const Hex27Args A) {
+  extern __shared__ __align__(16) double sm[];
+  double* gram = sm;                                         // 6561 (+1)
+  double* out = gram + H27A_GRAM + 1;                        // [27][244] row blocks of the cell
+  double* X = out + H27_NN * H27A_ROW;                       // [27][3]
+  double* U = X + H27_ND;                                    // [27][3]
+  double* XI = U + H27_ND;                                   // [27][3] (+1)
+  double* part = XI + H27_ND + 1;                            // [81][3] residual partial sums (+1)
+  __shared__ int pos[H27_NN];
+  __shared__ int corner[4];
+  __shared__ double Ecell;
+  const int tid = threadIdx.x;
+  const int nq = A.nq;
+  const double nu = A.law == FEM_LAW_SIMP ? A.p[2] : A.p[1];
+  const double mu1 = 1.0 / (2.0 * (1.0 + nu)), lam1 = nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
+  for (int i = tid; i < H27A_GRAM; i += H27A_THREADS) gram[i] = A.affine[H27A_NODE_TAB + i];
+  if (tid < H27_NN) {
+    const double x = A.affine[tid * 3], y = A.affine[tid * 3 + 1], z = A.affine[tid * 3 + 2];
+    XI[tid * 3] = x; XI[tid * 3 + 1] = y; XI[tid * 3 + 2] = z;
+    if (x + y + z == 0.0) corner[0] = tid;
+    if (x == 1.0 && y + z == 0.0) corner[1] = tid;
+    if (y == 1.0 && x + z == 0.0) corner[2] = tid;
+    if (z == 1.0 && x + y == 0.0) corner[3] = tid;
+  }
+
+  for (int64_t c = blockIdx.x; c < A.C; c += gridDim.x) {
+    if (tid < H27_NN) {
+      const int64_t node = A.cells[c * H27_NN + tid];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        X[tid * 3 + d] = A.points[node * 3 + d];
+        U[tid * 3 + d] = A.sol[node * 3 + d];
+      }
+      pos[tid] = A.corner_pos ? A.corner_pos[c * H27_NN + tid] : (int)(c * H27_NN + tid);
+    }
+    __syncthreads();
+    // J[d][e] = (X_corner(e+1) - X_corner(0))[d]: every thread forms it (and later its inverse) from shared memory
+    double J[3][3];
+    {
+      const double* x0 = X + corner[0] * 3;
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+        const double* xe = X + corner[e + 1] * 3;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) J[d][e] = xe[d] - x0[d];
+      }
+    }
+    int ok = 1;
+    if (tid < H27_NN) {
+      const double* x0 = X + corner[0] * 3;
+      double scale = 0.0, dev = 0.0;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const double pred = x0[d] + J[d][0] * XI[tid * 3] + J[d][1] * XI[tid * 3 + 1] + J[d][2] * XI[tid * 3 + 2];
+        dev = fmax(dev, fabs(X[tid * 3 + d] - pred));
+        scale = fmax(scale, fmax(fabs(J[d][0]), fmax(fabs(J[d][1]), fabs(J[d][2]))));
+      }
+      if (!(dev <= 1e-13 * scale)) ok = 0;
+    } else if (tid == 32) {
+      double E = A.p[0];
+      if (A.law == FEM_LAW_SIMP) E = A.p[1] + (A.p[0] - A.p[1]) * pow(A.iv[c * nq], A.p[3]);
+      Ecell = E;
+    } else if (tid >= 64 && A.law == FEM_LAW_SIMP) {
+      const double r0 = A.iv[c * nq];
+      for (int q = tid - 64; q < nq; q += H27A_THREADS - 64)
+        if (A.iv[c * nq + q] != r0) ok = 0;
+    }
+    double inv[3][3];
+    const double det = det_inv3(J, inv);
+    if (!(det > 0.0)) ok = 0;                                // inverted cell: let the general kernel reproduce the reference
+    ok = __syncthreads_and(ok);
+    if (!ok) {                                               // block-uniform
+      if (tid == 0) A.list[1 + atomicAdd(A.list, 1)] = (int)c;
+      continue;
+    }
+    const double cdet = Ecell * det;
+    for (int j = tid; j < H27_NN * H27_NN; j += H27A_THREADS) {
+      const int a = j / H27_NN, b = j % H27_NN;
+      double T[3][3], G[3][3];
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+        const double g0 = gram[(e * 3 + 0) * (H27_NN * H27_NN) + j], g1 = gram[(e * 3 + 1) * (H27_NN * H27_NN) + j],
+                     g2 = gram[(e * 3 + 2) * (H27_NN * H27_NN) + j];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) T[e][k] = g0 * inv[0][k] + g1 * inv[1][k] + g2 * inv[2][k];
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) G[i][k] = cdet * (inv[0][i] * T[0][k] + inv[1][i] * T[1][k] + inv[2][i] * T[2][k]);
+      const double tr = G[0][0] + G[1][1] + G[2][2];
+      double* o = out + a * H27A_ROW + b * 9;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) o[i * 3 + k] = lam1 * G[i][k] + mu1 * G[k][i] + (i == k ? mu1 * tr : 0.0);
+    }
+    if (tid < H27_NN) out[tid * H27A_ROW + 243] = 0.0;
+    __syncthreads();
+    // residual row (a, i) in three parts of nine column nodes each
+    if (tid < 3 * H27_ND) {
+      const int r = tid / 3, p = tid % 3, a = r / 3, i = r % 3;
+      const double* o = out + a * H27A_ROW + i * 3;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int b = 9 * p; b < 9 * p + 9; ++b) {
+        s0 = fma(o[b * 9], U[b * 3], s0);
+        s1 = fma(o[b * 9 + 1], U[b * 3 + 1], s1);
+        s2 = fma(o[b * 9 + 2], U[b * 3 + 2], s2);
+      }
+      part[tid] = (s0 + s1) + s2;
+    }
+    if (A.Ke) {
+      for (int j = tid; j < H27_NN * (H27A_ROW / 2); j += H27A_THREADS) {
+        const int a = j / (H27A_ROW / 2), w2 = j % (H27A_ROW / 2);
+        reinterpret_cast<double2*>(A.Ke + (int64_t)pos[a] * H27A_ROW)[w2] = reinterpret_cast<const double2*>(out + a * H27A_ROW)[w2];
+      }
+    }
+    __syncthreads();
+    if (tid < H27_ND) A.Re[c * H27_ND + tid] = (part[3 * tid] + part[3 * tid + 1]) + part[3 * tid + 2];
+  }
+}
+
 }  // namespace
 }  // namespace femb200
 
@@ -293,25 +441,46 @@ using namespace femb200;
 extern "C" int fem_hex27_residual_jacobian(int law_id, const double* law_params_host, const double* points,
                                            const int32_t* cells, int64_t n_cells, const double* sol,
                                            const double* internal_var, const double* ref_tables,
-                                           const double* ref_tables_t, int n_quad,
-                                           const int32_t* corner_pos, double* Ke, double* Re, void* stream) {
+                                           const double* ref_tables_t, int n_quad, const double* affine_tables,
+                                           int32_t* cell_list, const int32_t* corner_pos, double* Ke, double* Re,
+                                           void* stream) {
   if (int e = check_device()) return e;
   FEM_REQUIRE(points && cells && sol && ref_tables && Re && law_params_host, "null pointer");
   FEM_REQUIRE(law_id == FEM_LAW_LINEAR_ELASTIC || law_id == FEM_LAW_SIMP,
               "HEX27 is registered for isotropic elasticity (linear, SIMP) only");
   FEM_REQUIRE(!(law_id == FEM_LAW_SIMP && !internal_var), "SIMP needs the per-quadrature-point density");
   FEM_REQUIRE(n_quad > 0 && n_quad <= 512, "unsupported number of quadrature points");
+  FEM_REQUIRE(!affine_tables == !cell_list, "the affine pass needs both its tables and the cell-list workspace");
   if (n_cells == 0) return FEM_OK;
   Hex27Args A{};
   A.points = points; A.cells = cells; A.sol = sol; A.iv = internal_var; A.ref = ref_tables; A.ref_t = ref_tables_t;
   A.corner_pos = corner_pos; A.Ke = Ke; A.Re = Re; A.C = n_cells; A.nq = n_quad; A.law = law_id;
   for (int i = 0; i < 8; ++i) A.p[i] = law_params_host[i];
+  A.affine = affine_tables; A.list = cell_list;
+  static int grid_of[64] = {0};
+  int dev = 0;
+  FEM_CUDA_CHECK(cudaGetDevice(&dev));
+  FEM_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
   const int nq_pad = (n_quad + H27_QC - 1) / H27_QC * H27_QC;
   const size_t work = (size_t)nq_pad * H27_QP + (nq_pad * H27_QP) % 2 + 2 * H27_QC * H27_GS;
   const size_t gsz = (size_t)88 * H27_GSS;
   const size_t smem = sizeof(double) * (3 * H27_ND + 1 + (work > gsz ? work : gsz));
-  FEM_CUDA_CHECK(cudaFuncSetAttribute(hex27_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  hex27_kernel<<<(unsigned)n_cells, H27_THREADS, smem, (cudaStream_t)stream>>>(A);
+  const size_t asmem = sizeof(double) * (H27A_GRAM + 1 + H27_NN * H27A_ROW + 3 * H27_ND + 1 + 3 * H27_ND + 1);
+  if (grid_of[dev] == 0) {
+    int sms = 0;
+    FEM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    FEM_CUDA_CHECK(cudaFuncSetAttribute(hex27_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
+    FEM_CUDA_CHECK(cudaFuncSetAttribute(hex27_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    grid_of[dev] = 2 * sms;
+  }
+  FEM_REQUIRE(smem <= 200 * 1024, "quadrature rule too large for the HEX27 kernel's shared memory");
+  const unsigned grid = (unsigned)(n_cells < grid_of[dev] ? n_cells : grid_of[dev]);
+  if (affine_tables) {
+    FEM_CUDA_CHECK(cudaMemsetAsync(cell_list, 0, sizeof(int32_t), (cudaStream_t)stream));
+    hex27_affine_kernel<<<grid, H27A_THREADS, asmem, (cudaStream_t)stream>>>(A);
+    FEM_LAUNCH_CHECK();
+  }
+  hex27_kernel<<<grid, H27_THREADS, smem, (cudaStream_t)stream>>>(A);
   FEM_LAUNCH_CHECK();
   return FEM_OK;
 }

@@ -102,9 +102,18 @@ class Problem:
         self._ref = torch.from_numpy(np.concatenate([fe.shape_grads_ref.reshape(-1), fe.quad_weights])).to(dev)
         # the same dN with the point index fastest (HEX27 kernel: coalesced reads when thread = quadrature point)
         self._ref_t = torch.from_numpy(np.ascontiguousarray(fe.shape_grads_ref.reshape(fe.num_quads, -1).T)).to(dev)
+        # HEX27: tables of the affine-cell pass (fem_b200.h: reference node coordinates, then the reference Gram tables
+        # Ghat[e][f][a][b] = sum_q w_q dN_a^e dN_b^f); FEM_HEX27_AFFINE=0 sends every cell through the general kernel
+        self._hex27_affine = self._hex27_list = None
+        import os
+        if self.ele_type == 'HEX27' and os.environ.get('FEM_HEX27_AFFINE', '1') != '0':
+            from . import basis
+            xi = basis.get_elements('HEX27')[3] / 2.0
+            gram = np.einsum('q,qae,qbf->efab', fe.quad_weights, fe.shape_grads_ref, fe.shape_grads_ref)
+            self._hex27_affine = torch.from_numpy(np.concatenate([xi.reshape(-1), gram.reshape(-1)])).to(dev)
+            self._hex27_list = torch.zeros(fe.num_cells + 1, dtype=torch.int32, device=dev)
         # the plan is built by the library (fem_plan_create, csrc/plan.cu); FEM_PLAN=torch selects the torch construction
         # of plan.py (the one the CPU tests exercise), both give identical tables
-        import os
         builder = build_plan if os.environ.get('FEM_PLAN', 'native') == 'torch' else build_plan_native
         self.plan = builder(self._cells, fe.num_total_nodes, fe.vec)
         self._Ke = None
@@ -414,7 +423,7 @@ class Problem:
             _lib.check(lib.fem_hex27_residual_jacobian(
                 self._law.law_id, _lib.host_doubles(self._law.params()), _lib.ptr(self._points), _lib.ptr(self._cells),
                 self.num_cells, _lib.ptr(sol), _lib.ptr(iv), _lib.ptr(self._ref), _lib.ptr(self._ref_t), fe.num_quads,
-                _lib.ptr(self.plan.corner_pos), _lib.ptr(self._Ke) if jac else None, _lib.ptr(self._Re), _lib.stream_ptr()))
+                _lib.ptr(self._hex27_affine), _lib.ptr(self._hex27_list), _lib.ptr(self.plan.corner_pos), _lib.ptr(self._Ke) if jac else None, _lib.ptr(self._Re), _lib.stream_ptr()))
         elif tiles:
             post = (_lib.ctypes.c_double * 3)()
             _lib.check(lib.fem_element_tiles(

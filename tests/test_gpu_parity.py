@@ -334,6 +334,57 @@ def test_hex27_dmma_element_assembly_and_solve(order):
     assert relmax(usol, osol) <= SOL_TOL
 
 
+@pytest.mark.parametrize("mesh_kind", ["sheared", "mixed"])
+@pytest.mark.parametrize("law_kind", ["elastic", "simp_cell", "simp_graded"])
+def test_hex27_affine_cell_pass_matches_oracle(mesh_kind, law_kind):
+    """The HEX27 affine-cell pass (K_e = E detJ J^-T Ghat J^-1, R_e = K_e u_e) against the oracle's quadrature: a sheared box
+    (every cell affine), a mesh with curved cells on one side only (both kernels in one call), cell-constant SIMP density (affine
+    pass) and a density that varies inside the cells (listed for the general kernel); the list says which kernel ran."""
+    import jax_fem_b200 as jf
+    from jax_fem_b200 import laws
+    m = jf.box_mesh_hex27(4, 2, 2, 2.0, 1.0, 0.8)
+    pts, cells = m.points.copy(), m.cells_dict['hexahedron27']
+    rng = np.random.default_rng(11)
+    pts = pts @ np.array([[1.0, 0.2, 0.1], [0.05, 0.9, 0.3], [0.0, 0.1, 1.2]]).T + 0.3
+    curved = np.zeros(len(cells), dtype=bool)
+    if mesh_kind == "mixed":
+        move = pts[:, 0] > np.median(pts[:, 0])
+        pts[move] += 0.01 * rng.uniform(-1, 1, (int(move.sum()), 3))
+        curved = move[cells].any(axis=1)
+        assert curved.any() and not curved.all()
+    nq = 216
+    iv = None
+    if law_kind != "elastic":
+        iv = np.repeat(rng.uniform(0.2, 1.0, (len(cells), 1)), nq, axis=1)
+        if law_kind == "simp_graded":
+            iv[::2] += 0.05 * rng.uniform(0, 1, (len(iv[::2]), nq))
+    law = laws.LinearElasticity(70e3, 0.3) if law_kind == "elastic" else laws.SIMP(70e3, 70.0, 0.3, 3.0)
+    olaw = olaws.LinearElastic(70e3, 0.3) if law_kind == "elastic" else olaws.SIMP(70e3, 70.0, 0.3, 3.0)
+    P = type("P27", (jf.Problem,), {"get_tensor_map": lambda self: law})
+    kw = {} if iv is None else {"internal_vars": [iv]}
+    prob = P(jf.Mesh(pts, cells), vec=3, dim=3, ele_type='HEX27')
+    if iv is not None:
+        prob.internal_vars = [torch.from_numpy(iv).cuda()]
+    opb = fem.Problem(fem.Mesh(pts, cells), 3, 3, ele_type='HEX27', law=olaw, **kw)
+    sol = 1e-3 * rng.standard_normal((len(pts), 3))
+    res = prob.newton_update([torch.from_numpy(sol).cuda()])[0]
+    ores = opb.newton_update(sol)
+    left = host(prob._hex27_list)
+    flags = np.zeros(len(cells), dtype=bool)
+    flags[left[1:1 + left[0]]] = True
+    expect = curved.copy()
+    if law_kind == "simp_graded":
+        expect[::2] = True
+    assert np.array_equal(flags, expect)
+    assert relmax(host(prob.element_tangents()), opb.cell_jacobians(sol)) <= VAL_TOL
+    assert relmax(host(res), ores) <= VAL_TOL
+    data = host(jf.get_A(prob).getValuesCSR()[2])
+    assert relmax(data, fem.get_A(opb).data) <= VAL_TOL
+    # residual-only call (no tangent) goes through the same pass
+    res2 = prob.compute_residual([torch.from_numpy(sol).cuda()])[0]
+    assert relmax(host(res2), ores) <= VAL_TOL
+
+
 def test_cuda_core_element_path_for_elasticity_in_subprocess():
     """The HEX8 elasticity tangent has two kernels (FP64 tensor-core tiles by default, CUDA cores with
     FEM_ELEMENT_PATH=dfma); the choice is read once per process, so the second one is checked in a child process."""

@@ -457,3 +457,40 @@ def test_mesh_files_round_trip_through_the_three_readers(tmp_path):
         assert all(np.array_equal(a.point_data[k], pd2[k]) for k in pd2)
     with pytest.raises(NotImplementedError):
         read_mesh("mesh.xdmf")
+
+
+def test_hex27_affine_tables_reproduce_the_quadrature_on_affine_cells():
+    """The tables Problem hands to the HEX27 affine-cell pass (dN at the reference nodes, reference Gram tables) and the
+    formula the kernel evaluates with them, restated in numpy against the oracle's 216-point quadrature on a sheared box."""
+    import jax_fem_b200 as jf
+    from jax_fem_b200 import basis
+    from oracle import fem, laws as olaws
+    m = jf.box_mesh_hex27(2, 1, 1, 1.5, 1.0, 0.8)
+    pts, cells = m.points.copy(), m.cells_dict['hexahedron27']
+    pts = pts @ np.array([[1.0, 0.2, 0.1], [0.05, 0.9, 0.3], [0.0, 0.1, 1.2]]).T + 0.3
+    E, nu = 70e3, 0.3
+    opb = fem.Problem(fem.Mesh(pts, cells), 3, 3, ele_type='HEX27', law=olaws.LinearElastic(E, nu))
+    sol = 1e-3 * np.random.default_rng(0).standard_normal((len(pts), 3))
+    Kref = opb.cell_jacobians(sol)
+    _, dN, w = basis.get_shape_vals_and_grads('HEX27')
+    xi = basis.get_elements('HEX27')[3] / 2.0
+    corner = [int(np.flatnonzero((xi == t).all(axis=1))[0]) for t in ([0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1])]
+    gram = np.einsum('q,qae,qbf->efab', w, dN, dN)
+    mu1, lam1 = 1 / (2 * (1 + nu)), nu / ((1 + nu) * (1 - 2 * nu))
+
+    def affine_map(X):
+        J = np.stack([X[corner[e + 1]] - X[corner[0]] for e in range(3)], axis=1)
+        return J, np.abs(X - (X[corner[0]] + xi @ J.T)).max() / np.abs(J).max()
+
+    for c in range(len(cells)):
+        J, dev = affine_map(pts[cells[c]])
+        assert dev <= 1e-13                                                      # the kernel's affinity test
+        inv, det = np.linalg.inv(J), np.linalg.det(J)
+        G = E * det * np.einsum('ei,efab,fk->abik', inv, gram, inv)
+        K = lam1 * G + mu1 * G.transpose(0, 1, 3, 2) + mu1 * np.einsum('abii->ab', G)[:, :, None, None] * np.eye(3)
+        K = K.transpose(0, 2, 1, 3).reshape(81, 81)
+        assert np.abs(K - Kref[c].reshape(81, 81)).max() <= 1e-13 * np.abs(Kref[c]).max()
+    # a curved cell fails the test
+    pts2 = pts.copy()
+    pts2[cells[0][20]] += 0.01
+    assert affine_map(pts2[cells[0]])[1] > 1e-3
