@@ -109,18 +109,19 @@ int fem_element_residual_jacobian(int ele_type, int vec, int law_id, const doubl
 /* HEX27 (jax_fem/basis.py:58-65; 81x81 element tangents on FP64 DMMA tiles), isotropic elasticity (linear, SIMP).
  * ref_tables: [n_quad*27*3] dN then [n_quad] weights; ref_tables_t: the same dN as [27*3][n_quad] (point index fastest:
  * coalesced reads in the per-point phase) or NULL; internal_var (n_cells, n_quad) or NULL.
- * affine_tables (optional, with cell_list): [27][3] reference coordinates xi_n of the 27 nodes (unit cube) followed by
+ * affine_tables (optional, with affine_work): [27][3] reference coordinates xi_n of the 27 nodes (unit cube) followed by
  * [3][3][27][27] Ghat[e][f][a][b] = sum_q w_q dN_a^e(q) dN_b^f(q).  When given, a first pass tests every cell for an affine
  * geometry map (X_n = X_0 + J xi_n for all 27 nodes, J from the corners xi = 0, e_1, e_2, e_3) and a cell-constant internal
  * variable, and forms K_e = E detJ J^-T Ghat J^-1 and R_e = K_e u_e for those cells (exact up to rounding; 15x fewer FLOPs);
- * cell_list (n_cells + 1 int32, workspace) receives the number and the ids of the remaining cells, which the general DMMA
- * kernel then processes.  Both NULL: general kernel for every cell.
+ * the remaining cells are listed for the general DMMA kernel.  affine_work: device workspace of at least
+ * 100 * n_cells + 16 bytes, 16-byte aligned ([n_cells][12] doubles of per-cell records, then int32 count + cell ids of the
+ * list).  Both NULL: general kernel for every cell.
  * Ke: (n_cells*27, 244): row block of corner (c,a) = 27 blocks of 3x3 (+1 pad double) at corner_pos[c*27+a];
  * NULL = residual only.  Re: (n_cells, 81).                                                                    */
 int fem_hex27_residual_jacobian(int law_id, const double* law_params_host, const double* points,
                                 const int32_t* cells, int64_t n_cells, const double* sol,
                                 const double* internal_var, const double* ref_tables, const double* ref_tables_t,
-                                int n_quad, const double* affine_tables, int32_t* cell_list,
+                                int n_quad, const double* affine_tables, void* affine_work,
                                 const int32_t* corner_pos, double* Ke, double* Re, void* stream);
 
 /* ---- (1)+(2) fused: compute_newton_vars (jax_fem/problem.py:447-460) + _PetscTangentCache.update / get_A

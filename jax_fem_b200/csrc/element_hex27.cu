@@ -41,6 +41,7 @@ struct Hex27Args {
   const double* ref_t;       // [27*3][nq] the same dN with the point index fastest (coalesced reads when thread = point) or nullptr
   const int32_t* corner_pos;
   const double* affine;      // [27][3] reference node coordinates, then [3][3][27][27] reference Gram tables; or nullptr
+  double* rec;               // per cell: J^-1, E detJ, affine flag (written by the affine pass's first kernel) or nullptr
   int32_t* list;             // [0] = number of cells left to the general kernel, [1..] their ids (written by the affine pass) or nullptr
   double* Ke;                // (C*27, 244)
   double* Re;                // (C, 81)
@@ -305,131 +306,204 @@ __global__ void __launch_bounds__(H27_THREADS, 2) hex27_kernel(const Hex27Args A
 // X_n = X_0 + J xi_n with J = [X_1 - X_0, X_2 - X_0, X_3 - X_0]; with SIMP the density must also be constant over the cell's
 // points.  Everything else (curved cells, graded density) is listed for hex27_kernel.  The stress is linear in grad u for the
 // registered laws, so the element residual is K_e u_e (problem.py:204-210 with a constant tangent).
-constexpr int H27A_THREADS = 256;
+constexpr int H27A_WARPS = 9, H27A_THREADS = 32 * (H27A_WARPS + 1);   // compute warp w owns the row blocks a = w, w + 9, w + 18 (lane = column node b); warp 9 feeds them
 constexpr int H27A_NODE_TAB = H27_ND;                        // xi_n [27][3]
 constexpr int H27A_GRAM = 9 * H27_NN * H27_NN;               // Ghat[e][f][a][b]
+constexpr int H27A_GRAM6 = 6 * H27_NN * H27_NN;              // ... of which the kernel keeps e <= f
 constexpr int H27A_ROW = 244;
 
+constexpr int H27A_REC = 12;                                 // per cell: J^-1 (9), E detJ, affine flag, pad
+
+// Pass 1, one warp per cell (lane n = node n): the affinity test, J^-1, E detJ -> the cell's record; cells that fail are listed.
+__global__ void __launch_bounds__(256) hex27_affine_prep_kernel(const Hex27Args A) {
+  const int l = threadIdx.x & 31;
+  const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= A.C) return;                                      // warp-uniform
+  const bool in = l < H27_NN;
+  double xi[3] = {0, 0, 0}, x[3] = {0, 0, 0};
+  if (in) {
+    const int64_t node = A.cells[c * H27_NN + l];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      xi[d] = A.affine[l * 3 + d];
+      x[d] = A.points[node * 3 + d];
+    }
+  }
+  // which lanes hold the corners xi = 0, e_1, e_2, e_3
+  const double sum = xi[0] + xi[1] + xi[2];
+  int corner[4];
+  corner[0] = __ffs(__ballot_sync(0xffffffffu, in && sum == 0.0)) - 1;
+#pragma unroll
+  for (int e = 0; e < 3; ++e) corner[e + 1] = __ffs(__ballot_sync(0xffffffffu, in && xi[e] == 1.0 && sum == 1.0)) - 1;
+  double J[3][3], x0[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) x0[d] = __shfl_sync(0xffffffffu, x[d], corner[0]);
+#pragma unroll
+  for (int e = 0; e < 3; ++e)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) J[d][e] = __shfl_sync(0xffffffffu, x[d], corner[e + 1]) - x0[d];
+  double scale = 0.0, dev = 0.0;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double pred = x0[d] + J[d][0] * xi[0] + J[d][1] * xi[1] + J[d][2] * xi[2];
+    dev = fmax(dev, fabs(x[d] - pred));
+    scale = fmax(scale, fmax(fabs(J[d][0]), fmax(fabs(J[d][1]), fabs(J[d][2]))));
+  }
+  bool ok = !in || dev <= 1e-13 * scale;
+  double E = A.p[0];
+  if (A.law == FEM_LAW_SIMP) {
+    const double* iv = A.iv + c * A.nq;
+    const double r0 = iv[0];
+    for (int q = l; q < A.nq; q += 32) ok = ok && iv[q] == r0;
+    E = A.p[1] + (A.p[0] - A.p[1]) * pow(r0, A.p[3]);
+  }
+  double inv[3][3];
+  const double det = det_inv3(J, inv);
+  ok = __all_sync(0xffffffffu, ok) && det > 0.0;             // inverted cell: let the general kernel reproduce the reference
+  if (l == 0) {
+    double* rec = A.rec + c * H27A_REC;
+#pragma unroll
+    for (int e = 0; e < 3; ++e)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) rec[e * 3 + d] = inv[e][d];
+    rec[9] = E * det;
+    rec[10] = ok ? 1.0 : 0.0;
+    rec[11] = 0.0;
+    if (!ok) A.list[1 + atomicAdd(A.list, 1)] = (int)c;
+  }
+}
+
+// Pass 2, persistent CTAs of 9 warps; warp w owns the row blocks a = w, w + 9, w + 18 of the cell, lane = column node b.
 __global__ void __launch_bounds__(H27A_THREADS, 2) hex27_affine_kernel(const Hex27Args A) {
   extern __shared__ __align__(16) double sm[];
-  double* gram = sm;                                         // 6561 (+1)
-  double* out = gram + H27A_GRAM + 1;                        // [27][244] row blocks of the cell
-  double* X = out + H27_NN * H27A_ROW;                       // [27][3]
-  double* U = X + H27_ND;                                    // [27][3]
-  double* XI = U + H27_ND;                                   // [27][3] (+1)
-  double* part = XI + H27_ND + 1;                            // [81][3] residual partial sums (+1)
-  __shared__ int pos[H27_NN];
-  __shared__ int corner[4];
-  __shared__ double Ecell;
-  const int tid = threadIdx.x;
-  const int nq = A.nq;
+  double* gram = sm;                                         // the 6 tables e <= f ([e][f][a][b] = [f][e][b][a]): 4374 doubles
+  double* out = gram + H27A_GRAM6;                           // [27][244] row blocks of the cell
+  double* Y = out + H27_NN * H27A_ROW;                       // [27][27][3]: K_ab u_b, summed over b into the residual
+  double* U = Y + H27_NN * H27_ND + 1;                       // 2 x [27][3] (double-buffered by cell parity)
+  double* JI = U + 2 * H27_ND;                               // 2 x the cell's record
+  __shared__ int pos[2][H27_NN];
+  const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
   const double nu = A.law == FEM_LAW_SIMP ? A.p[2] : A.p[1];
   const double mu1 = 1.0 / (2.0 * (1.0 + nu)), lam1 = nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
-  for (int i = tid; i < H27A_GRAM; i += H27A_THREADS) gram[i] = A.affine[H27A_NODE_TAB + i];
-  if (tid < H27_NN) {
-    const double x = A.affine[tid * 3], y = A.affine[tid * 3 + 1], z = A.affine[tid * 3 + 2];
-    XI[tid * 3] = x; XI[tid * 3 + 1] = y; XI[tid * 3 + 2] = z;
-    if (x + y + z == 0.0) corner[0] = tid;
-    if (x == 1.0 && y + z == 0.0) corner[1] = tid;
-    if (y == 1.0 && x + z == 0.0) corner[2] = tid;
-    if (z == 1.0 && x + y == 0.0) corner[3] = tid;
+  for (int i = tid; i < H27A_GRAM6; i += H27A_THREADS) {
+    const int t = i / (H27_NN * H27_NN), e = t < 3 ? 0 : (t < 5 ? 1 : 2), f = t < 3 ? t : (t < 5 ? t - 2 : 2);
+    gram[i] = A.affine[H27A_NODE_TAB + (e * 3 + f) * (H27_NN * H27_NN) + i % (H27_NN * H27_NN)];
   }
 
-  for (int64_t c = blockIdx.x; c < A.C; c += gridDim.x) {
-    if (tid < H27_NN) {
-      const int64_t node = A.cells[c * H27_NN + tid];
+  // Warp 9 is the producer: while the nine compute warps work on cell c it stages the solution / row positions / record of the
+  // CTA's next cell in the other half of the double buffers and has the loads of the cell after that (and the node ids of one
+  // further) in flight, so that no global-load latency sits between the barriers of the compute warps.
+  const int64_t stride = gridDim.x;
+  int node_next = 0, ppos = 0;
+  double pu[3] = {0, 0, 0}, prec = 0.0;
+  auto load_node = [&](int64_t c) { return (c < A.C && l < H27_NN) ? A.cells[c * H27_NN + l] : 0; };
+  auto load_data = [&](int64_t c, int node) {
+    if (c >= A.C) return;
+    if (l < H27_NN) {
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        X[tid * 3 + d] = A.points[node * 3 + d];
-        U[tid * 3 + d] = A.sol[node * 3 + d];
-      }
-      pos[tid] = A.corner_pos ? A.corner_pos[c * H27_NN + tid] : (int)(c * H27_NN + tid);
+      for (int d = 0; d < 3; ++d) pu[d] = A.sol[(int64_t)node * 3 + d];
+      ppos = A.corner_pos ? A.corner_pos[c * H27_NN + l] : (int)(c * H27_NN + l);
     }
-    __syncthreads();
-    // J[d][e] = (X_corner(e+1) - X_corner(0))[d]: every thread forms it (and later its inverse) from shared memory
-    double J[3][3];
-    {
-      const double* x0 = X + corner[0] * 3;
+    if (l < H27A_REC) prec = A.rec[c * H27A_REC + l];
+  };
+  auto stage = [&](int half) {
+    if (l < H27_NN) {
 #pragma unroll
-      for (int e = 0; e < 3; ++e) {
-        const double* xe = X + corner[e + 1] * 3;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) J[d][e] = xe[d] - x0[d];
-      }
+      for (int d = 0; d < 3; ++d) U[half * H27_ND + l * 3 + d] = pu[d];
+      pos[half][l] = ppos;
     }
-    int ok = 1;
-    if (tid < H27_NN) {
-      const double* x0 = X + corner[0] * 3;
-      double scale = 0.0, dev = 0.0;
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const double pred = x0[d] + J[d][0] * XI[tid * 3] + J[d][1] * XI[tid * 3 + 1] + J[d][2] * XI[tid * 3 + 2];
-        dev = fmax(dev, fabs(X[tid * 3 + d] - pred));
-        scale = fmax(scale, fmax(fabs(J[d][0]), fmax(fabs(J[d][1]), fabs(J[d][2]))));
-      }
-      if (!(dev <= 1e-13 * scale)) ok = 0;
-    } else if (tid == 32) {
-      double E = A.p[0];
-      if (A.law == FEM_LAW_SIMP) E = A.p[1] + (A.p[0] - A.p[1]) * pow(A.iv[c * nq], A.p[3]);
-      Ecell = E;
-    } else if (tid >= 64 && A.law == FEM_LAW_SIMP) {
-      const double r0 = A.iv[c * nq];
-      for (int q = tid - 64; q < nq; q += H27A_THREADS - 64)
-        if (A.iv[c * nq + q] != r0) ok = 0;
-    }
+    if (l < H27A_REC) JI[half * H27A_REC + l] = prec;
+  };
+  if (warp == H27A_WARPS) {
+    load_data(blockIdx.x, load_node(blockIdx.x));
+    stage(0);
+    load_data(blockIdx.x + stride, load_node(blockIdx.x + stride));
+    node_next = load_node(blockIdx.x + 2 * stride);
+  }
+  __syncthreads();
+
+  int par = 0;
+  for (int64_t c = blockIdx.x; c < A.C; c += stride, par ^= 1) {
+    const bool affine = JI[par * H27A_REC + 10] != 0.0;      // block-uniform; otherwise the cell is listed for hex27_kernel
+    if (warp == H27A_WARPS) {
+      if (c + stride < A.C) stage(par ^ 1);
+      load_data(c + 2 * stride, node_next);
+      node_next = load_node(c + 3 * stride);
+    } else if (affine) {
     double inv[3][3];
-    const double det = det_inv3(J, inv);
-    if (!(det > 0.0)) ok = 0;                                // inverted cell: let the general kernel reproduce the reference
-    ok = __syncthreads_and(ok);
-    if (!ok) {                                               // block-uniform
-      if (tid == 0) A.list[1 + atomicAdd(A.list, 1)] = (int)c;
-      continue;
+#pragma unroll
+    for (int e = 0; e < 3; ++e)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) inv[e][d] = JI[par * H27A_REC + e * 3 + d];
+    const double cdet = JI[par * H27A_REC + 9];
+    double ub[3] = {0, 0, 0};
+    if (l < H27_NN) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) ub[d] = U[par * H27_ND + l * 3 + d];
     }
-    const double cdet = Ecell * det;
-    for (int j = tid; j < H27_NN * H27_NN; j += H27A_THREADS) {
-      const int a = j / H27_NN, b = j % H27_NN;
-      double T[3][3], G[3][3];
 #pragma unroll
-      for (int e = 0; e < 3; ++e) {
-        const double g0 = gram[(e * 3 + 0) * (H27_NN * H27_NN) + j], g1 = gram[(e * 3 + 1) * (H27_NN * H27_NN) + j],
-                     g2 = gram[(e * 3 + 2) * (H27_NN * H27_NN) + j];
+    for (int ai = 0; ai < H27_NN / H27A_WARPS; ++ai) {       // three independent items per lane: instruction-level parallelism
+      const int a = warp + ai * H27A_WARPS;
+      if (l < H27_NN) {
+        const int j = a * H27_NN + l, jt = l * H27_NN + a;
+        constexpr int S = H27_NN * H27_NN;
+        // Ghat_ab[e][f]: upper tables directly, lower ones from the transposed entry of the mirrored table
+        const double g00 = gram[j], g01 = gram[S + j], g02 = gram[2 * S + j], g11 = gram[3 * S + j], g12 = gram[4 * S + j],
+                     g22 = gram[5 * S + j], g10 = gram[S + jt], g20 = gram[2 * S + jt], g21 = gram[4 * S + jt];
+        const double gh[3][3] = {{g00, g01, g02}, {g10, g11, g12}, {g20, g21, g22}};
+        double T[3][3], G[3][3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) T[e][k] = g0 * inv[0][k] + g1 * inv[1][k] + g2 * inv[2][k];
+        for (int e = 0; e < 3; ++e)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) T[e][k] = gh[e][0] * inv[0][k] + gh[e][1] * inv[1][k] + gh[e][2] * inv[2][k];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) G[i][k] = cdet * (inv[0][i] * T[0][k] + inv[1][i] * T[1][k] + inv[2][i] * T[2][k]);
+        const double tr = G[0][0] + G[1][1] + G[2][2];
+        double* o = out + a * H27A_ROW + l * 9;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          double y = 0.0;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const double v = lam1 * G[i][k] + mu1 * G[k][i] + (i == k ? mu1 * tr : 0.0);
+            o[i * 3 + k] = v;
+            y = fma(v, ub[k], y);
+          }
+          Y[j * 3 + i] = y;
+        }
+      } else if (l == 31) {
+        out[a * H27A_ROW + 243] = 0.0;
       }
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) G[i][k] = cdet * (inv[0][i] * T[0][k] + inv[1][i] * T[1][k] + inv[2][i] * T[2][k]);
-      const double tr = G[0][0] + G[1][1] + G[2][2];
-      double* o = out + a * H27A_ROW + b * 9;
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) o[i * 3 + k] = lam1 * G[i][k] + mu1 * G[k][i] + (i == k ? mu1 * tr : 0.0);
     }
-    if (tid < H27_NN) out[tid * H27A_ROW + 243] = 0.0;
-    __syncthreads();
-    // residual row (a, i) in three parts of nine column nodes each
-    if (tid < 3 * H27_ND) {
-      const int r = tid / 3, p = tid % 3, a = r / 3, i = r % 3;
-      const double* o = out + a * H27A_ROW + i * 3;
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll
-      for (int b = 9 * p; b < 9 * p + 9; ++b) {
-        s0 = fma(o[b * 9], U[b * 3], s0);
-        s1 = fma(o[b * 9 + 1], U[b * 3 + 1], s1);
-        s2 = fma(o[b * 9 + 2], U[b * 3 + 2], s2);
-      }
-      part[tid] = (s0 + s1) + s2;
-    }
-    if (A.Ke) {
-      for (int j = tid; j < H27_NN * (H27A_ROW / 2); j += H27A_THREADS) {
-        const int a = j / (H27A_ROW / 2), w2 = j % (H27A_ROW / 2);
-        reinterpret_cast<double2*>(A.Ke + (int64_t)pos[a] * H27A_ROW)[w2] = reinterpret_cast<const double2*>(out + a * H27A_ROW)[w2];
-      }
+    fence_async_smem();
     }
     __syncthreads();
-    if (tid < H27_ND) A.Re[c * H27_ND + tid] = (part[3 * tid] + part[3 * tid + 1]) + part[3 * tid + 2];
+    if (affine) {
+      if (warp < 3) {
+        // residual row r = (a, i): sum of K_ab u_b over the column nodes in ascending b
+        const int r = tid;
+        if (r < H27_ND) {
+          const double* y = Y + (r / 3) * H27_ND + r % 3;
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+          for (int b = 0; b < H27_NN; b += 3) {
+            s0 += y[b * 3];
+            s1 += y[b * 3 + 3];
+            s2 += y[b * 3 + 6];
+          }
+          A.Re[c * H27_ND + r] = (s0 + s1) + s2;
+        }
+      } else if (warp == 3 && A.Ke && l < H27_NN) {
+        // the 27 row blocks go to their node-sorted positions as bulk copies (no LDS / STG instructions); the next cell may
+        // overwrite them once they have been read
+        bulk_s2g(A.Ke + (int64_t)pos[par][l] * H27A_ROW, out + l * H27A_ROW, H27A_ROW * sizeof(double));
+        bulk_commit();
+        bulk_wait_read<0>();
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -442,7 +516,7 @@ extern "C" int fem_hex27_residual_jacobian(int law_id, const double* law_params_
                                            const int32_t* cells, int64_t n_cells, const double* sol,
                                            const double* internal_var, const double* ref_tables,
                                            const double* ref_tables_t, int n_quad, const double* affine_tables,
-                                           int32_t* cell_list, const int32_t* corner_pos, double* Ke, double* Re,
+                                           void* affine_work, const int32_t* corner_pos, double* Ke, double* Re,
                                            void* stream) {
   if (int e = check_device()) return e;
   FEM_REQUIRE(points && cells && sol && ref_tables && Re && law_params_host, "null pointer");
@@ -450,13 +524,16 @@ extern "C" int fem_hex27_residual_jacobian(int law_id, const double* law_params_
               "HEX27 is registered for isotropic elasticity (linear, SIMP) only");
   FEM_REQUIRE(!(law_id == FEM_LAW_SIMP && !internal_var), "SIMP needs the per-quadrature-point density");
   FEM_REQUIRE(n_quad > 0 && n_quad <= 512, "unsupported number of quadrature points");
-  FEM_REQUIRE(!affine_tables == !cell_list, "the affine pass needs both its tables and the cell-list workspace");
+  FEM_REQUIRE(!affine_tables == !affine_work, "the affine pass needs both its tables and its workspace");
+  FEM_REQUIRE((reinterpret_cast<uintptr_t>(affine_work) & 15) == 0, "affine_work must be 16-byte aligned");
   if (n_cells == 0) return FEM_OK;
   Hex27Args A{};
   A.points = points; A.cells = cells; A.sol = sol; A.iv = internal_var; A.ref = ref_tables; A.ref_t = ref_tables_t;
   A.corner_pos = corner_pos; A.Ke = Ke; A.Re = Re; A.C = n_cells; A.nq = n_quad; A.law = law_id;
   for (int i = 0; i < 8; ++i) A.p[i] = law_params_host[i];
-  A.affine = affine_tables; A.list = cell_list;
+  A.affine = affine_tables;
+  A.rec = static_cast<double*>(affine_work);                                 // [n_cells][12] doubles, then the int32 list
+  A.list = affine_work ? reinterpret_cast<int32_t*>(A.rec + n_cells * H27A_REC) : nullptr;
   static int grid_of[64] = {0};
   int dev = 0;
   FEM_CUDA_CHECK(cudaGetDevice(&dev));
@@ -465,7 +542,7 @@ extern "C" int fem_hex27_residual_jacobian(int law_id, const double* law_params_
   const size_t work = (size_t)nq_pad * H27_QP + (nq_pad * H27_QP) % 2 + 2 * H27_QC * H27_GS;
   const size_t gsz = (size_t)88 * H27_GSS;
   const size_t smem = sizeof(double) * (3 * H27_ND + 1 + (work > gsz ? work : gsz));
-  const size_t asmem = sizeof(double) * (H27A_GRAM + 1 + H27_NN * H27A_ROW + 3 * H27_ND + 1 + 3 * H27_ND + 1);
+  const size_t asmem = sizeof(double) * (H27A_GRAM6 + H27_NN * H27A_ROW + H27_NN * H27_ND + 1 + 2 * H27_ND + 2 * H27A_REC);
   if (grid_of[dev] == 0) {
     int sms = 0;
     FEM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -476,7 +553,9 @@ extern "C" int fem_hex27_residual_jacobian(int law_id, const double* law_params_
   FEM_REQUIRE(smem <= 200 * 1024, "quadrature rule too large for the HEX27 kernel's shared memory");
   const unsigned grid = (unsigned)(n_cells < grid_of[dev] ? n_cells : grid_of[dev]);
   if (affine_tables) {
-    FEM_CUDA_CHECK(cudaMemsetAsync(cell_list, 0, sizeof(int32_t), (cudaStream_t)stream));
+    FEM_CUDA_CHECK(cudaMemsetAsync(A.list, 0, sizeof(int32_t), (cudaStream_t)stream));
+    hex27_affine_prep_kernel<<<(unsigned)((n_cells + 7) / 8), 256, 0, (cudaStream_t)stream>>>(A);
+    FEM_LAUNCH_CHECK();
     hex27_affine_kernel<<<grid, H27A_THREADS, asmem, (cudaStream_t)stream>>>(A);
     FEM_LAUNCH_CHECK();
   }

@@ -111,7 +111,8 @@ class Problem:
             xi = basis.get_elements('HEX27')[3] / 2.0
             gram = np.einsum('q,qae,qbf->efab', fe.quad_weights, fe.shape_grads_ref, fe.shape_grads_ref)
             self._hex27_affine = torch.from_numpy(np.concatenate([xi.reshape(-1), gram.reshape(-1)])).to(dev)
-            self._hex27_list = torch.zeros(fe.num_cells + 1, dtype=torch.int32, device=dev)
+            # workspace: [num_cells][12] doubles of per-cell records, then the int32 list (count, ids) of the non-affine cells
+            self._hex27_list = torch.zeros(100 * fe.num_cells + 16, dtype=torch.uint8, device=dev)
         # the plan is built by the library (fem_plan_create, csrc/plan.cu); FEM_PLAN=torch selects the torch construction
         # of plan.py (the one the CPU tests exercise), both give identical tables
         builder = build_plan if os.environ.get('FEM_PLAN', 'native') == 'torch' else build_plan_native
@@ -267,6 +268,13 @@ class Problem:
         return self._bc_cache[5]
 
     # ---- the hot path -----------------------------------------------------------------------------------
+    def hex27_general_cells(self):
+        """Ids of the cells the last HEX27 element call left to the general DMMA kernel (not affine / graded density)."""
+        if self._hex27_list is None:
+            return np.arange(self.num_cells)
+        left = self._hex27_list[96 * self.num_cells:].view(torch.int32).cpu().numpy()
+        return np.sort(left[1:1 + left[0]])
+
     def _internal_var(self):
         law = self._law
         iv = list(self.internal_vars)
