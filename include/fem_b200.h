@@ -225,6 +225,18 @@ int fem_gather_csr_tiles(int64_t n_blocks, const int32_t* gdesc, const int32_t* 
 int fem_gather_residual(int vec, int nn, int64_t n_nodes, const int32_t* nc_ptr, const int32_t* nc,
                         const double* Re, const double* f_ext, double* res, void* stream);
 
+/* ---- (1c) solution-dependent mass maps: get_mass_kernel (jax_fem/problem.py:216-236) and its share of value_and_jacfwd
+ *      (problem.py:262-266) for the registered mass law m_i(u) = a u_i + b_i with a = coef or coef_field (n_cells, n_quad)
+ *      and b = const_host[vec] or const_field (n_cells, n_quad, vec): backward-Euler heat capacity, phase-field driving term,
+ *      elastic foundation.  Runs between the element kernel and the gathers and ADDS, in place, to the element residuals Re
+ *      (n_cells, nn*vec) and to the staged row blocks Ke in the REFERENCE block layout of fem_element_residual_jacobian (not
+ *      the tile-major rows of fem_element_tiles); Ke == NULL: residual only.  shape_vals: [n_quad][nn] (basis.py:141-175).
+ *      HEX8 (vec 1, 3) and QUAD4 (vec 1, 2); one thread per (cell, node) owns its row block: deterministic, no atomics. */
+int fem_mass_term(int ele_type, int vec, const double* points, const int32_t* cells, int64_t n_cells, const double* sol,
+                  const double* ref_tables, const double* shape_vals, int n_quad, double coef, const double* coef_field,
+                  const double* const_host, const double* const_field, const int32_t* corner_pos, double* Ke, double* Re,
+                  void* stream);
+
 /* ---- (1b) solution-dependent surface maps: get_surface_kernel (jax_fem/problem.py:238-259) and its tangent
  *      (problem.py:289-325) for the registered surface law val_i(u) = coef_i (u_i - uref_i)^power (Robin / convection / spring
  *      foundation; applications/robin_bc/example.py:59-67 is coef 5, power 2).  law_host[7] = coef[3], uref[3], power.

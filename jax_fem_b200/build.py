@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfem_b200.so")
-SOURCES = ["element.cu", "element_hex27.cu", "fused.cu", "staged.cu", "plan_host.cpp", "sparse.cu", "krylov.cu", "dist.cu", "plan.cu", "faces.cu"]
+SOURCES = ["element.cu", "element_hex27.cu", "fused.cu", "staged.cu", "plan_host.cpp", "sparse.cu", "krylov.cu", "dist.cu", "plan.cu", "faces.cu", "mass.cu"]
 OBJDIR = os.path.join(LIBDIR, "obj")
 COMPILE_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 LINK_FLAGS = ["-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]

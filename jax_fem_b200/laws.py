@@ -123,6 +123,56 @@ class RobinPower(SurfaceLaw):
         return self.coef * (u - self.u_ref) ** self.power
 
 
+class MassLaw:
+    """A solution-dependent mass map with a hand-written kernel (csrc/mass.cu).  The reference accepts any callable
+    ``mass_map(u, x, *internal_vars)`` and differentiates it (problem.py:216-236, 262-266); here a u-dependent map must be one
+    of the registered objects below -- plain callables stay supported as long as they do not depend on u."""
+
+
+class LinearMass(MassLaw):
+    """m_i(u) = coef * u_i + const_i at every quadrature point.  ``coef``: a number or a (num_cells, num_quads) field;
+    ``const``: None, a number / vec numbers, or a (num_cells, num_quads[, vec]) field.  Both are read at every assembly, so a
+    time stepper updates them in place between solves: backward-Euler heat capacity ``rho Cp (T - T_old) / dt`` is
+    ``coef = rho Cp / dt, const = -coef * T_old(q)`` (applications/thermal_mechanical/example.py:40-43), the phase-field
+    driving term ``(G_c / l + 2 H) d - 2 H`` is ``coef = G_c / l + 2 H(q), const = -2 H(q)``
+    (applications/phase_field_fracture/example.py:54-57)."""
+
+    def __init__(self, coef, const=None):
+        self.coef = coef
+        self.const = const
+
+    def fields(self, num_cells, num_quads, vec, device):
+        """-> (coef scalar, coef field or None, const host vector (3,), const field (C, Q, vec) or None)."""
+        import numpy as np
+        import torch
+
+        def as_field(v, shape):
+            t = v if isinstance(v, torch.Tensor) else torch.as_tensor(np.asarray(v, dtype=np.float64))
+            t = t.detach().to(device=device, dtype=torch.float64)
+            if t.ndim == 2 and len(shape) == 3:                  # one field for every component
+                t = t.unsqueeze(-1).expand(*t.shape, vec)
+            if tuple(t.shape) != tuple(shape):
+                raise ValueError(f"LinearMass: field of shape {tuple(t.shape)}, expected {tuple(shape)}")
+            return t.contiguous()
+
+        ndim = lambda v: v.ndim if hasattr(v, 'ndim') else np.ndim(v)
+        size = lambda v: v.numel() if isinstance(v, torch.Tensor) else np.size(v)
+        coef, coef_f = 0.0, None
+        if ndim(self.coef) == 0:
+            coef = float(self.coef)
+        else:
+            coef_f = as_field(self.coef, (num_cells, num_quads))
+        cst, cst_f = np.zeros(3), None
+        if self.const is None:
+            pass
+        elif ndim(self.const) <= 1 and size(self.const) in (1, vec):
+            host = self.const.detach().cpu().numpy() if isinstance(self.const, torch.Tensor) else self.const
+            cst[:vec] = np.broadcast_to(np.asarray(host, dtype=np.float64).reshape(-1), (vec,))
+        else:
+            cst_f = as_field(self.const, (num_cells, num_quads, vec))
+        return coef, coef_f, cst, cst_f
+
+
 REGISTERED = {
     ('HEX8', 1, Poisson), ('HEX8', 3, LinearElasticity), ('HEX8', 3, NeoHookean), ('HEX8', 3, SIMP),
     ('QUAD4', 1, Poisson), ('QUAD4', 2, LinearElasticity), ('QUAD4', 2, SIMP),

@@ -161,10 +161,17 @@ class Problem:
         fe = self.fes[0]
         f = np.zeros((fe.num_total_nodes, fe.vec))
         used = False
-        if hasattr(self, 'get_mass_map'):
+        self._mass_law = None
+        mass_map = self.get_mass_map() if hasattr(self, 'get_mass_map') else None
+        if isinstance(mass_map, laws.MassLaw):                                     # u-dependent: device kernel (csrc/mass.cu)
+            if self.ele_type == 'HEX27':
+                raise NotImplementedError("solution-dependent mass maps are registered for HEX8 and QUAD4")
+            self._mass_law = mass_map
+            self._shape_vals = torch.from_numpy(np.ascontiguousarray(fe.shape_vals)).to(self.device)
+        elif mass_map is not None:
             x = fe.get_physical_quad_points()                                      # (C,Q,dim)
             JxW = fe.get_JxW()
-            val = _eval_load_map(self.get_mass_map(), None, x.reshape(-1, self.dim), fe.vec).reshape(*x.shape[:2], fe.vec)
+            val = _eval_load_map(mass_map, None, x.reshape(-1, self.dim), fe.vec).reshape(*x.shape[:2], fe.vec)
             contrib = np.einsum('cqv,qn,cq->cnv', val, fe.shape_vals, JxW)
             for i in range(fe.vec):
                 f[:, i] += np.bincount(fe.cells.reshape(-1), weights=contrib[:, :, i].reshape(-1), minlength=fe.num_total_nodes)
@@ -308,7 +315,7 @@ class Problem:
            'fused'  : owner-computes patches (csrc/fused.cu; measured slower).
         FEM_ASSEMBLY in the environment selects the mode; every mode is parity-tested."""
         import os
-        eligible = (self.ele_type == 'HEX8' and self.fes[0].vec == 3
+        eligible = (self.ele_type == 'HEX8' and self.fes[0].vec == 3 and self._mass_law is None
                     and self._law.law_id in (laws.LinearElasticity.law_id, laws.SIMP.law_id))
         mode = os.environ.get('FEM_ASSEMBLY', 'staged')
         if mode not in ('ring', 'staged', 'fused'):
@@ -413,6 +420,7 @@ class Problem:
         kernels instead (A/B measurements; all paths are parity-tested)."""
         import os
         return (os.environ.get('FEM_ELEMENT_PATH', 'tiles') == 'tiles' and self.ele_type == 'HEX8' and self.fes[0].vec == 3
+                and self._mass_law is None      # the mass kernel adds to row blocks in the reference layout
                 and self._law.law_id in (laws.LinearElasticity.law_id, laws.SIMP.law_id, laws.NeoHookean.law_id))
 
     def _run_element_kernel(self, sol, jac, tiles=None):
@@ -443,6 +451,13 @@ class Problem:
             self._launch_element(lib, fe, sol, iv, jac)
         if jac:
             self._Ke_tiles = tiles
+        if self._mass_law is not None:
+            coef, coef_f, cst, cst_f = self._mass_law.fields(self.num_cells, fe.num_quads, fe.vec, self.device)
+            _lib.check(lib.fem_mass_term(
+                _lib.ELE[self.ele_type], fe.vec, _lib.ptr(self._points), _lib.ptr(self._cells), self.num_cells, _lib.ptr(sol),
+                _lib.ptr(self._ref), _lib.ptr(self._shape_vals), fe.num_quads, coef, _lib.ptr(coef_f), _lib.host_doubles(cst),
+                _lib.ptr(cst_f), _lib.ptr(self.plan.corner_pos), _lib.ptr(self._Ke) if jac else None, _lib.ptr(self._Re),
+                _lib.stream_ptr()))
         res = torch.empty((fe.num_total_nodes, fe.vec), dtype=torch.float64, device=self.device)
         p = self.plan
         _lib.check(lib.fem_gather_residual(fe.vec, fe.num_nodes, fe.num_total_nodes, _lib.ptr(p.nc_ptr), _lib.ptr(p.nc),

@@ -183,12 +183,14 @@ class Problem:
     """
 
     def __init__(self, mesh, vec, dim, ele_type='HEX8', quadrature_order=None, dirichlet_bc_info=None,
-                 location_fns=None, law=None, mass_map=None, surface_maps=None, internal_vars=(), surface_map_jacs=None):
+                 location_fns=None, law=None, mass_map=None, surface_maps=None, internal_vars=(), surface_map_jacs=None,
+                 mass_map_jac=None):
         self.fe = FiniteElement(mesh, vec, dim, ele_type, quadrature_order, dirichlet_bc_info)
         self.fes = [self.fe]
         fe = self.fe
         self.vec, self.dim, self.law = vec, dim, law
         self.mass_map, self.surface_maps = mass_map, surface_maps or []
+        self.mass_map_jac = mass_map_jac      # vectorised d mass_map / d u -> (..., vec, vec); None: the map does not depend on u
         # d(surface_map)/du (..., vec, vec) per boundary set, or None for a u-independent map (the reference gets it from jacfwd
         # of the surface kernel, problem.py:299-301)
         self.surface_map_jacs = surface_map_jacs or [None] * len(self.surface_maps)
@@ -250,7 +252,13 @@ class Problem:
         with _blas_single_thread():      # tiny GEMMs: BLAS thread hand-offs dominate on many-core hosts
             AB = np.matmul(A.reshape(C, Q, v * d, v * d) * self.JxW[sl][:, :, None, None], B)
             K = np.matmul(B.transpose(0, 1, 3, 2), AB).sum(axis=1)
-        return K.reshape(K.shape[0], self.ndof, self.ndof)
+        K = K.reshape(K.shape[0], self.ndof, self.ndof)
+        if self.mass_map_jac is not None:                                               # problem.py:216-236 differentiated
+            u = np.einsum('cnv,qn->cqv', sol[self.cells[sl]], self.fe.shape_vals)
+            dm = np.broadcast_to(self.mass_map_jac(u, self.physical_quad_points[sl]), u.shape + (v,))
+            M = np.einsum('cqik,qa,qb,cq->caibk', dm, self.fe.shape_vals, self.fe.shape_vals, self.JxW[sl])
+            K = K + M.reshape(K.shape)
+        return K
 
     def face_residuals(self, sol, k):
         """surface kernel, problem.py:238-259 -> (S,N,vec)."""

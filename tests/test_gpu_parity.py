@@ -662,6 +662,76 @@ def test_solution_dependent_surface_maps_match_oracle(case, mode, monkeypatch):
     assert relmax(host(x), fem.solver(opb)) <= SOL_TOL
 
 
+@pytest.mark.parametrize("case", ["heat_step_hex8", "heat_step_quad4", "phase_field_hex8", "foundation_hex8", "foundation_quad4"])
+def test_solution_dependent_mass_maps_match_oracle(case):
+    """registered u-dependent mass maps (laws.LinearMass, csrc/mass.cu): the backward-Euler heat capacity
+    rho Cp (T - T_old) / dt of applications/thermal_mechanical (constant coefficient, per-point T_old), the phase-field driving
+    term (G_c / l + 2 H) d - 2 H (per-point coefficient and constant), and an elastic foundation k u with a body force on
+    vec 3 / vec 2 elasticity.  Residual, CSR values, problem.V and the solution of the step must equal the oracle's; the fields
+    are then changed in place (next time step) and the same objects must follow."""
+    import jax_fem_b200 as jf
+    from jax_fem_b200 import laws
+    rng = np.random.default_rng(21)
+    quad = case.endswith("quad4")
+    if quad:
+        m = jf.rectangle_mesh(8, 6, 1., 1.)
+        pts, cells, ele, dim = m.points + 0.01 * rng.uniform(-1, 1, m.points.shape), m.cells_dict['quad'], 'QUAD4', 2
+    else:
+        pts, cells = perturbed_box(5, seed=4)
+        ele, dim = 'HEX8', 3
+    nq = 4 if quad else 8
+    C = len(cells)
+    lo = lambda p: p[0] < 0.02
+    hi = lambda p: p[0] > 0.98
+    if case.startswith("foundation"):
+        vec = dim
+        kf, body = 2.5e3, np.array([0., -40., 15.])[:vec]
+        law, olaw = laws.LinearElasticity(70e3, 0.3), olaws.LinearElastic(70e3, 0.3)
+        mass = laws.LinearMass(kf, body)
+        fields = lambda: (kf * np.ones((C, nq)), np.broadcast_to(body, (C, nq, vec)))
+        bc = [[lo] * vec, list(range(vec)), [lambda p: 0.] * vec]
+    else:
+        vec = 1
+        law, olaw = laws.Poisson(2.0), olaws.Poisson(2.0)
+        bc = [[lo], [0], [lambda p: 0.4]]
+        if case.startswith("heat"):
+            coef = 7.0 / 0.05                                                  # rho Cp / dt
+            T_old = 0.5 + 0.2 * rng.standard_normal((C, nq))
+            mass = laws.LinearMass(coef, -coef * T_old)
+            fields = lambda: (coef * np.ones((C, nq)), np.asarray(mass.const)[..., None])
+        else:
+            H = rng.uniform(0., 3., (C, nq))
+            mass = laws.LinearMass(torch.from_numpy(1.5 + 2 * H).cuda(), torch.from_numpy(-2 * H).cuda())
+            fields = lambda: (host(mass.coef), host(mass.const)[..., None])
+    P = type("MassProblem", (jf.Problem,), {"get_tensor_map": lambda self: law, "get_mass_map": lambda self: mass,
+                                            "get_surface_maps": lambda self: [lambda u, x: np.full(vec, 3.0)]})
+    prob = P(jf.Mesh(pts, cells), vec=vec, dim=dim, ele_type=ele, dirichlet_bc_info=bc, location_fns=[hi])
+    opb = fem.Problem(fem.Mesh(pts, cells), vec, dim, ele_type=ele, dirichlet_bc_info=bc, location_fns=[hi], law=olaw,
+                      mass_map=lambda u, x: fields()[0][..., None] * u + fields()[1],
+                      mass_map_jac=lambda u, x: fields()[0][..., None, None] * np.eye(vec),
+                      surface_maps=[lambda u, x: 3.0 + 0. * u])
+    assert prob.assembly_mode() == 'staged' and not prob.tiles_enabled()
+    sol = 0.3 + 0.1 * rng.standard_normal((len(pts), vec))
+    for step in range(2):
+        res = prob.newton_update([torch.from_numpy(sol).cuda()])[0]
+        A = jf.get_A(prob)
+        ores = opb.newton_update(sol)
+        oA = fem.get_A(opb)
+        assert np.array_equal(host(A.getValuesCSR()[1]), oA.indices)
+        assert relmax(host(A.data), oA.data) <= VAL_TOL and relmax(host(res), ores) <= VAL_TOL
+        assert relmax(host(prob.V), opb.coo_values()) <= VAL_TOL
+        assert relmax(host(prob.compute_residual([torch.from_numpy(sol).cuda()])[0]), ores) <= VAL_TOL    # residual-only call
+        x = host(jf.solver(prob, {'jax_solver': {}})[0])
+        assert relmax(x, fem.solver(opb)) <= SOL_TOL
+        if case.startswith("heat"):                                            # next time step: T_old <- T at the points
+            T_q = np.einsum('cn,qn->cq', x[cells, 0], prob.fes[0].shape_vals)
+            mass.const = -coef * T_q
+        elif case.startswith("phase"):
+            mass.coef.mul_(1.1)
+        else:
+            break
+
+
 def test_csr_diagonal_beyond_2_30_nonzeros():
     """The Jacobi preconditioner of the 200^3 mesh (nnz = 1.95e9): row offsets above 2^30 must not overflow the binary search
     for the diagonal entry (lo + hi in int32 did: the first 200^3 solve on one GPU hung).  Synthetic banded matrix with

@@ -175,3 +175,27 @@ def test_oracle_face_tangent_is_the_derivative_of_the_face_residual():
             e[j] = h
             col = (pb.compute_residual(sol + e.reshape(sol.shape)) - pb.compute_residual(sol - e.reshape(sol.shape))).reshape(-1) / (2 * h)
             assert np.abs(col - A[:, j]).max() <= 1e-6 * max(np.abs(A[:, j]).max(), 1.0)
+
+
+def test_oracle_mass_map_jacobian_matches_finite_differences():
+    """oracle.fem.Problem.cell_jacobians with a u-dependent mass map (the checker of csrc/mass.cu) against central
+    differences of cell_residuals."""
+    import jax_fem_b200 as jf
+    from oracle import fem, laws as olaws
+    rng = np.random.default_rng(3)
+    m = jf.box_mesh(2, 2, 1, 1., 1., 0.5)
+    pts = m.points + 0.03 * rng.uniform(-1, 1, m.points.shape)
+    cells = m.cells_dict['hexahedron']
+    a = rng.uniform(1, 3, (len(cells), 8))
+    b = rng.standard_normal((len(cells), 8, 1))
+    pb = fem.Problem(fem.Mesh(pts, cells), 1, 3, law=olaws.Poisson(2.0), mass_map=lambda u, x: a[..., None] * u + b,
+                     mass_map_jac=lambda u, x: a[..., None, None] * np.ones((1, 1)))
+    sol = rng.standard_normal((len(pts), 1))
+    K = pb.cell_jacobians(sol)
+    h = 1e-6
+    for c in (0, 3):
+        for j in range(8):
+            e = np.zeros_like(sol)
+            e[cells[c, j]] = h
+            col = (pb.cell_residuals(sol + e)[c] - pb.cell_residuals(sol - e)[c]).reshape(-1) / (2 * h)
+            assert np.abs(col - K[c][:, j]).max() <= 1e-7 * np.abs(K[c]).max()
