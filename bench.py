@@ -281,6 +281,7 @@ def main():
     ap.add_argument("--no-solve", action="store_true", help="skip the Jacobi-CG solve (it is part of every default run)")
     ap.add_argument("--ref-size", type=int, default=64,
                     help="edge length of the CPU sample (cells per direction): 64^3 is about 10-20 s of host work")
+    ap.add_argument("--bicgstab-iters", type=int, default=0, help="also time this many Jacobi-BiCGSTAB iterations (cg_solve.bicgstab)")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--newton", action="store_true",
@@ -477,6 +478,32 @@ def main():
                  "solution_l1": float(chk[0]), "solution_l2": float(chk[1].sqrt()),
                  "halo_bytes_per_rank_per_exchange": sharded.halo.bytes_per_exchange if sharded else 0,
                  "effective_spmv_gbs": world * b_spmv / (cg_ms * 1e-3 / its) / 1e9}
+        # optional: K iterations of Jacobi-BiCGSTAB (the reference's default solver and its adjoint solver) on the same system
+        if args.bicgstab_iters > 0:
+            if sharded:
+                from jax_fem_b200.distributed import distributed_bicgstab
+                run_bi = lambda k: distributed_bicgstab(A0, -r0, torch.zeros_like(dofs), sharded.part, sharded.halo, comm, 3, maxiter=k)
+            else:
+                run_bi = lambda k: jax_solve(A0, -r0, torch.zeros_like(dofs), True, method='bicgstab', return_info=True, maxiter=k)
+
+            def guarded(k):
+                try:
+                    return run_bi(k)[1]
+                except AssertionError:                # a capped run does not meet the reference's err < 0.1 post-check
+                    return {"iterations": k}
+            guarded(5)
+            barrier()
+            c0.record()
+            binfo = guarded(args.bicgstab_iters)
+            c1.record()
+            barrier()
+            t_bi = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_bi, op=dist.ReduceOp.MAX)
+            kb = max(int(binfo.get('iterations', args.bicgstab_iters)), 1)
+            solve["bicgstab"] = {"iterations_timed": kb, "ms_per_iteration": float(t_bi.item()) / kb,
+                                 "note": "capped run (2 SpMV, 2 halo exchanges and 4 all-reduces per iteration), includes the final true-residual check"}
+            log(f"bicgstab: {solve['bicgstab']}")
         del A0, r0, xs, dofs
     newton = None
     if args.newton:

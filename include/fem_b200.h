@@ -336,6 +336,13 @@ int fem_halo_create(void* nccl_comm, int vec, int n_neighbours, const int32_t* p
                     const int64_t* recv_count_host, double* sendbuf, void** halo_out);
 int fem_halo_destroy(void* halo);
 int fem_halo_exchange(void* halo, double* x, void* stream);
+
+/* Owned nodes [node_lo, node_hi) of the rank have no ghost neighbour: fem_dist_pcg / fem_dist_pbicgstab multiply their rows
+ * while the halo exchange of the product's input is in flight on the plan's own stream (pack -> event -> ncclSend/ncclRecv on
+ * that stream -> event), and the remaining rows once the ghosts have arrived; the rank-local dot of the product is completed
+ * by the second launch.  Used when more than half of the owned nodes are in the range and the matrix has its node-block
+ * structure (vec 2 or 3); an empty range (the default) keeps exchange and product in sequence.                          */
+int fem_halo_set_interior(void* halo, int64_t node_lo, int64_t node_hi);
 int fem_allreduce_sum(void* halo, double* buf, int count, void* stream);
 /* Distributed Jacobi-CG / BiCGSTAB on the rank's owned rows (CSR rows 0..n_owned-1 complete, columns index the local
  * vector of n_local entries).  Same recurrences, stopping rule and info_host as fem_pcg / fem_pbicgstab; per iteration

@@ -62,9 +62,8 @@ __global__ void halo_pack_kernel(int64_t n, const int32_t* __restrict__ idx, con
 }
 }  // namespace
 
-int halo_exchange(const HaloPlan* h, double* x, cudaStream_t st) {
-  const NcclApi* nc = nccl_api();
-  if (!nc) return FEM_ECUDA;
+namespace {
+int halo_pack(const HaloPlan* h, const double* x, cudaStream_t st) {
   const int64_t n_send = h->send_ptr[h->n_nb];
   if (n_send > 0) {
     const unsigned grid = (unsigned)((n_send + 255) / 256);
@@ -73,7 +72,12 @@ int halo_exchange(const HaloPlan* h, double* x, cudaStream_t st) {
     else halo_pack_kernel<3><<<grid, 256, 0, st>>>(n_send, h->send_idx, x, h->sendbuf);
     FEM_LAUNCH_CHECK();
   }
-  if (h->n_nb == 0) return FEM_OK;
+  return FEM_OK;
+}
+
+int halo_transfer(const HaloPlan* h, double* x, cudaStream_t st) {
+  const NcclApi* nc = nccl_api();
+  if (!nc) return FEM_ECUDA;
   FEM_NCCL_CHECK(nc->GroupStart());
   for (int k = 0; k < h->n_nb; ++k) {
     const int64_t ns = h->send_ptr[k + 1] - h->send_ptr[k];
@@ -83,6 +87,30 @@ int halo_exchange(const HaloPlan* h, double* x, cudaStream_t st) {
       FEM_NCCL_CHECK(nc->Recv(x + h->recv_start[k] * h->vec, (size_t)h->recv_count[k] * h->vec, ncclDouble, h->peer[k], h->comm, st));
   }
   FEM_NCCL_CHECK(nc->GroupEnd());
+  return FEM_OK;
+}
+}  // namespace
+
+int halo_exchange(const HaloPlan* h, double* x, cudaStream_t st) {
+  if (int e = halo_pack(h, x, st)) return e;
+  if (h->n_nb == 0) return FEM_OK;
+  return halo_transfer(h, x, st);
+}
+
+int halo_begin(const HaloPlan* h, double* x, cudaStream_t st) {
+  if (int e = halo_pack(h, x, st)) return e;
+  if (h->n_nb == 0) return FEM_OK;
+  // everything queued on `st` so far (the producer of x, the previous readers of its ghosts) precedes the transfer
+  FEM_CUDA_CHECK(cudaEventRecord(h->ev_packed, st));
+  FEM_CUDA_CHECK(cudaStreamWaitEvent(h->comm_stream, h->ev_packed, 0));
+  if (int e = halo_transfer(h, x, h->comm_stream)) return e;
+  FEM_CUDA_CHECK(cudaEventRecord(h->ev_arrived, h->comm_stream));
+  return FEM_OK;
+}
+
+int halo_end(const HaloPlan* h, cudaStream_t st) {
+  if (h->n_nb == 0) return FEM_OK;
+  FEM_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_arrived, 0));
   return FEM_OK;
 }
 
@@ -152,12 +180,39 @@ extern "C" int fem_halo_create(void* nccl_comm, int vec, int n_neighbours, const
     set_error("invalid argument: send_idx / sendbuf missing");
     return FEM_EINVAL;
   }
+  h->int_lo = h->int_hi = 0;
+  h->comm_stream = nullptr;
+  h->ev_packed = h->ev_arrived = nullptr;
+  if (n_neighbours > 0) {
+    cudaError_t e = cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_packed, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_arrived, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+      set_error("fem_halo_create: %s", cudaGetErrorString(e));
+      delete h;
+      return FEM_ECUDA;
+    }
+  }
   *halo_out = h;
   return FEM_OK;
 }
 
 extern "C" int fem_halo_destroy(void* halo) {
-  delete reinterpret_cast<HaloPlan*>(halo);
+  HaloPlan* h = reinterpret_cast<HaloPlan*>(halo);
+  if (h) {
+    if (h->ev_packed) cudaEventDestroy(h->ev_packed);
+    if (h->ev_arrived) cudaEventDestroy(h->ev_arrived);
+    if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  }
+  delete h;
+  return FEM_OK;
+}
+
+extern "C" int fem_halo_set_interior(void* halo, int64_t node_lo, int64_t node_hi) {
+  FEM_REQUIRE(halo && node_lo >= 0 && node_hi >= node_lo, "bad interior range");
+  HaloPlan* h = reinterpret_cast<HaloPlan*>(halo);
+  h->int_lo = node_lo;
+  h->int_hi = node_hi;
   return FEM_OK;
 }
 

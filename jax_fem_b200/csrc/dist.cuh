@@ -41,9 +41,18 @@ struct HaloPlan {
   int64_t recv_count[16];
   const int32_t* send_idx;  // device: local ids of the owned nodes to pack, all neighbours concatenated
   double* sendbuf;          // device: vec * send_ptr[n_nb] doubles
+  // overlap of the exchange with the rows that need no ghost value (fem_halo_set_interior): owned nodes [int_lo, int_hi) have
+  // no ghost neighbour; the sends / receives run on comm_stream between the two events
+  int64_t int_lo, int_hi;
+  cudaStream_t comm_stream;
+  cudaEvent_t ev_packed, ev_arrived;
 };
 
 int halo_exchange(const HaloPlan* h, double* x, cudaStream_t st);
+// split form: halo_begin packs on `st` and issues the sends / receives on the plan's own stream; work queued on `st` after
+// it runs concurrently with the transfer and must not touch the ghost entries of x; halo_end makes `st` wait for the arrival.
+int halo_begin(const HaloPlan* h, double* x, cudaStream_t st);
+int halo_end(const HaloPlan* h, cudaStream_t st);
 int allreduce_sum(const HaloPlan* h, double* buf, int count, cudaStream_t st);
 
 }  // namespace femb200

@@ -68,18 +68,30 @@ inline Ws carve(double* w, int64_t n) {
 }
 
 // Block partials -> global; the last block to arrive sums them in index order and runs `fin`.
+// A product may be split over two launches (rows that need no ghost value first, the others after the halo has arrived):
+// the launches write their partials side by side (`poff`, `ptotal` slots per dot) and only the last one (`finalize`) takes
+// tickets and sums all of them -- stream order guarantees that the earlier launch has completed.
+struct RowSplit {
+  int64_t a0, a_cnt, b0, b_cnt;   // node ranges [a0, a0 + a_cnt) then [b0, b0 + b_cnt)
+  int poff, ptotal, finalize;
+};
+
 template <int NV, class Fin>
 __device__ __forceinline__ void reduce_and_finalize(double (&v)[NV], double* __restrict__ S,
-                                                    double* __restrict__ partial, Fin fin) {
+                                                    double* __restrict__ partial, Fin fin, int poff, int ptotal,
+                                                    bool finalize) {
   __shared__ double red[NV * (kThreads / 32)];
   __shared__ bool is_last;
   block_sum<NV, kThreads>(v, red);
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 0; k < NV; ++k) partial[(int64_t)k * gridDim.x + blockIdx.x] = v[k];
-    __threadfence();
-    const unsigned t = atomicAdd(reinterpret_cast<unsigned*>(S + S_TICKET), 1u);
-    is_last = (t == gridDim.x - 1);
+    for (int k = 0; k < NV; ++k) partial[(int64_t)k * ptotal + poff + blockIdx.x] = v[k];
+    is_last = false;
+    if (finalize) {
+      __threadfence();
+      const unsigned t = atomicAdd(reinterpret_cast<unsigned*>(S + S_TICKET), 1u);
+      is_last = (t == gridDim.x - 1);
+    }
   }
   __syncthreads();
   if (!is_last) return;
@@ -88,7 +100,7 @@ __device__ __forceinline__ void reduce_and_finalize(double (&v)[NV], double* __r
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     double a = 0.0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) a += __ldcg(partial + (int64_t)k * gridDim.x + i);
+    for (int i = threadIdx.x; i < ptotal; i += kThreads) a += __ldcg(partial + (int64_t)k * ptotal + i);
     tot[k] = a;
   }
   __syncthreads();
@@ -98,6 +110,12 @@ __device__ __forceinline__ void reduce_and_finalize(double (&v)[NV], double* __r
     fin(tot);
     __threadfence();
   }
+}
+
+template <int NV, class Fin>
+__device__ __forceinline__ void reduce_and_finalize(double (&v)[NV], double* __restrict__ S,
+                                                    double* __restrict__ partial, Fin fin) {
+  reduce_and_finalize<NV>(v, S, partial, fin, 0, (int)gridDim.x, true);
 }
 
 __device__ __forceinline__ bool solver_done(const double* S) { return __ldcg(S + S_DONE) != 0.0; }
@@ -170,7 +188,7 @@ __global__ void __launch_bounds__(kThreads) spmv_fused_kernel(int64_t n, const i
 // column index per VEC x VEC block (4/9 instead of 4 index bytes per nonzero for VEC = 3), gather VEC consecutive
 // entries of x and stream the VEC row segments at full width.  `indices` is not read at all.
 template <int VEC, int LPN, int MODE>
-__global__ void __launch_bounds__(kThreads) spmv_block_fused_kernel(int64_t n_nodes, const int32_t* __restrict__ brow_ptr,
+__global__ void __launch_bounds__(kThreads) spmv_block_fused_kernel(const RowSplit R, const int32_t* __restrict__ brow_ptr,
                                                                     const int32_t* __restrict__ bcol,
                                                                     const double* __restrict__ data,
                                                                     const double* __restrict__ x, double* __restrict__ y,
@@ -180,10 +198,13 @@ __global__ void __launch_bounds__(kThreads) spmv_block_fused_kernel(int64_t n_no
   constexpr int NPB = kThreads / LPN;
   constexpr int VV = VEC * VEC;
   const int sub = threadIdx.x % LPN;
+  const int64_t n_nodes = R.a_cnt + R.b_cnt;
+  const int ptotal = R.ptotal ? R.ptotal : (int)gridDim.x;
   double dots[2] = {0.0, 0.0};
   for (int64_t base = (int64_t)blockIdx.x * NPB; base < n_nodes; base += (int64_t)gridDim.x * NPB) {
-    const int64_t nd = base + threadIdx.x / LPN;
-    const bool valid = nd < n_nodes;
+    const int64_t li = base + threadIdx.x / LPN;
+    const bool valid = li < n_nodes;
+    const int64_t nd = li < R.a_cnt ? R.a0 + li : R.b0 + (li - R.a_cnt);
     double acc[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) acc[i] = 0.0;
@@ -224,17 +245,17 @@ __global__ void __launch_bounds__(kThreads) spmv_block_fused_kernel(int64_t n_no
   }
   if constexpr (MODE == 1) {
     double v[1] = {dots[0]};
-    reduce_and_finalize<1>(v, S, partial, [&](double (&t)[1]) { S[S_ALPHA] = S[S_GAMMA] / t[0]; });
+    reduce_and_finalize<1>(v, S, partial, [&](double (&t)[1]) { S[S_ALPHA] = S[S_GAMMA] / t[0]; }, R.poff, ptotal, R.finalize);
   } else if constexpr (MODE == 2) {
     double v[1] = {dots[0]};
-    reduce_and_finalize<1>(v, S, partial, [&](double (&t)[1]) { S[S_ALPHA] = S[S_RHO_NEW] / t[0]; });
+    reduce_and_finalize<1>(v, S, partial, [&](double (&t)[1]) { S[S_ALPHA] = S[S_RHO_NEW] / t[0]; }, R.poff, ptotal, R.finalize);
   } else if constexpr (MODE == 3) {
-    reduce_and_finalize<2>(dots, S, partial, [&](double (&t)[2]) { S[S_OMEGA] = t[0] / t[1]; });
+    reduce_and_finalize<2>(dots, S, partial, [&](double (&t)[2]) { S[S_OMEGA] = t[0] / t[1]; }, R.poff, ptotal, R.finalize);
   } else if constexpr (MODE == 4) {
     double v[1] = {dots[0]};
-    reduce_and_finalize<1>(v, S, partial, [&](double (&t)[1]) { S[S_SUM0] = t[0]; });
+    reduce_and_finalize<1>(v, S, partial, [&](double (&t)[1]) { S[S_SUM0] = t[0]; }, R.poff, ptotal, R.finalize);
   } else if constexpr (MODE == 5) {
-    reduce_and_finalize<2>(dots, S, partial, [&](double (&t)[2]) { S[S_SUM2] = t[0]; S[S_SUM3] = t[1]; });
+    reduce_and_finalize<2>(dots, S, partial, [&](double (&t)[2]) { S[S_SUM2] = t[0]; S[S_SUM3] = t[1]; }, R.poff, ptotal, R.finalize);
   }
 }
 
@@ -627,19 +648,52 @@ struct Mat {
   const int32_t* bcol;
 };
 
+inline RowSplit whole_rows(int64_t n_nodes) { return RowSplit{0, n_nodes, 0, 0, 0, 0, 1}; }
+
 template <int MODE>
 void spmv_fused(const Mat& A, const double* x, double* y, const double* d1, const Ws& w, cudaStream_t st) {
   constexpr int LPN = 8;
   if (A.brow_ptr && A.bcol && A.vec == 3) {
     spmv_block_fused_kernel<3, LPN, MODE><<<FEM_PGRID((spmv_block_fused_kernel<3, LPN, MODE>))>>>(
-        A.n / 3, A.brow_ptr, A.bcol, A.data, x, y, d1, w.s, w.partial);
+        whole_rows(A.n / 3), A.brow_ptr, A.bcol, A.data, x, y, d1, w.s, w.partial);
   } else if (A.brow_ptr && A.bcol && A.vec == 2) {
     spmv_block_fused_kernel<2, LPN, MODE><<<FEM_PGRID((spmv_block_fused_kernel<2, LPN, MODE>))>>>(
-        A.n / 2, A.brow_ptr, A.bcol, A.data, x, y, d1, w.s, w.partial);
+        whole_rows(A.n / 2), A.brow_ptr, A.bcol, A.data, x, y, d1, w.s, w.partial);
   } else {
     spmv_fused_kernel<kLPR, MODE><<<FEM_PGRID((spmv_fused_kernel<kLPR, MODE>))>>>(A.n, A.indptr, A.indices, A.data, x, y,
                                                                                  d1, w.s, w.partial);
   }
+}
+
+// y[owned] = (A x)[owned] with x's ghosts refreshed first.  When the plan knows a range of owned nodes without ghost
+// neighbours (fem_halo_set_interior) and the matrix has its node-block structure, those rows are multiplied while the sends
+// and receives are in flight on the plan's stream; the remaining rows follow once the ghosts have arrived.
+template <int MODE, int VEC>
+int dist_spmv_split(const HaloPlan* h, const Mat& A, double* x, double* y, const double* d1, const Ws& w, cudaStream_t st) {
+  constexpr int LPN = 8, NPB = kThreads / LPN;
+  auto k = spmv_block_fused_kernel<VEC, LPN, MODE>;
+  const int64_t n_nodes = A.n / VEC, lo = h->int_lo, hi = h->int_hi;
+  const int cap = persistent_grid(k);
+  auto blocks = [&](int64_t cnt) { return (int)std::max<int64_t>(1, std::min<int64_t>(cap, (cnt + NPB - 1) / NPB)); };
+  const int g1 = blocks(hi - lo), g2 = blocks(n_nodes - (hi - lo));
+  if (int e = halo_begin(h, x, st)) return e;
+  k<<<g1, kThreads, 0, st>>>(RowSplit{lo, hi - lo, 0, 0, 0, g1 + g2, 0}, A.brow_ptr, A.bcol, A.data, x, y, d1, w.s, w.partial);
+  if (int e = halo_end(h, st)) return e;
+  k<<<g2, kThreads, 0, st>>>(RowSplit{0, lo, hi, n_nodes - hi, g1, g1 + g2, 1}, A.brow_ptr, A.bcol, A.data, x, y, d1, w.s, w.partial);
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
+}
+
+template <int MODE>
+int dist_spmv(const HaloPlan* h, const Mat& A, double* x, double* y, const double* d1, const Ws& w, cudaStream_t st) {
+  const int64_t n_nodes = A.vec > 0 ? A.n / A.vec : 0;
+  const bool split = h->n_nb > 0 && A.brow_ptr && A.bcol && h->int_hi > h->int_lo && h->int_hi <= n_nodes &&
+                     (h->int_hi - h->int_lo) * 2 > n_nodes;          // worth two launches only if most rows are interior
+  if (split && A.vec == 3) return dist_spmv_split<MODE, 3>(h, A, x, y, d1, w, st);
+  if (split && A.vec == 2) return dist_spmv_split<MODE, 2>(h, A, x, y, d1, w, st);
+  if (int e = halo_exchange(h, x, st)) return e;
+  spmv_fused<MODE>(A, x, y, d1, w, st);
+  return FEM_OK;
 }
 
 int init_scalars(const Ws& w, double tol, double atol, int maxiter, cudaStream_t st) {
@@ -688,9 +742,9 @@ int launch_spmv_block(int64_t n, int vec, const int32_t* brow_ptr, const int32_t
   const int64_t n_nodes = n / vec;
   const unsigned grid = (unsigned)((n_nodes * LPN + kThreads - 1) / kThreads);
   if (vec == 3)
-    spmv_block_fused_kernel<3, LPN, 0><<<grid, kThreads, 0, st>>>(n_nodes, brow_ptr, bcol, data, x, y, nullptr, nullptr, nullptr);
+    spmv_block_fused_kernel<3, LPN, 0><<<grid, kThreads, 0, st>>>(whole_rows(n_nodes), brow_ptr, bcol, data, x, y, nullptr, nullptr, nullptr);
   else
-    spmv_block_fused_kernel<2, LPN, 0><<<grid, kThreads, 0, st>>>(n_nodes, brow_ptr, bcol, data, x, y, nullptr, nullptr, nullptr);
+    spmv_block_fused_kernel<2, LPN, 0><<<grid, kThreads, 0, st>>>(whole_rows(n_nodes), brow_ptr, bcol, data, x, y, nullptr, nullptr, nullptr);
   FEM_LAUNCH_CHECK();
   return FEM_OK;
 }
@@ -877,8 +931,7 @@ extern "C" int fem_dist_pcg(void* halo, int64_t n_owned, int64_t n_local, const 
   if (int e = poll_done(w, &done, st)) return e;
   for (int it = 0; !done && it < maxiter; it += check_every) {
     for (int j = 0; j < check_every; ++j) {
-      if (int e = halo_exchange(h, p, st)) return e;
-      spmv_fused<4>(A, p, q, p, w, st);                                        // q = A p ; rank-local p.Ap
+      if (int e = dist_spmv<4>(h, A, p, q, p, w, st)) return e;                // ghosts of p ; q = A p ; rank-local p.Ap
       if (int e = allreduce_sum(h, w.s + S_SUM0, 1, st)) return e;
       dcg_update_kernel<<<FEM_PGRID(dcg_update_kernel)>>>(n_owned, diag, p, q, x, r, w.s, w.partial);
       if (int e = allreduce_sum(h, w.s + S_SUM1, 2, st)) return e;
@@ -918,13 +971,11 @@ extern "C" int fem_dist_pbicgstab(void* halo, int64_t n_owned, int64_t n_local, 
   for (int it = 0; !done && it < maxiter; it += check_every) {
     for (int j = 0; j < check_every; ++j) {
       bicg_p_kernel<<<FEM_PGRID(bicg_p_kernel)>>>(n_owned, diag, r, q, p, phat, w.s);
-      if (int e = halo_exchange(h, phat, st)) return e;
-      spmv_fused<4>(A, phat, q, rhat, w, st);                                  // q = A phat ; rank-local rhat.q
+      if (int e = dist_spmv<4>(h, A, phat, q, rhat, w, st)) return e;          // ghosts of phat ; q = A phat ; rank-local rhat.q
       if (int e = allreduce_sum(h, w.s + S_SUM0, 1, st)) return e;
       dbicg_s_kernel<<<FEM_PGRID(dbicg_s_kernel)>>>(n_owned, diag, r, q, s, shat, w.s, w.partial);
       if (int e = allreduce_sum(h, w.s + S_SUM1, 1, st)) return e;
-      if (int e = halo_exchange(h, shat, st)) return e;
-      spmv_fused<5>(A, shat, t, s, w, st);                                     // t = A shat ; rank-local t.s, t.t
+      if (int e = dist_spmv<5>(h, A, shat, t, s, w, st)) return e;             // ghosts of shat ; t = A shat ; rank-local t.s, t.t
       if (int e = allreduce_sum(h, w.s + S_SUM2, 2, st)) return e;
       dbicg_x_kernel<<<FEM_PGRID(dbicg_x_kernel)>>>(n_owned, phat, shat, s, t, rhat, x, r, w.s, w.partial);
       if (int e = allreduce_sum(h, w.s + S_SUM4, 2, st)) return e;

@@ -224,6 +224,19 @@ class ThreadComm:
         self.sh.barrier.wait()
 
 
+def interior_node_range(part):
+    """Longest run [lo, hi) of owned local nodes none of whose cells holds a ghost node: their matrix rows read no ghost value."""
+    cl = np.asarray(part.cells_local)
+    touch = np.zeros(part.n_local, dtype=bool)
+    touch[cl[(cl >= part.n_owned).any(axis=1)].reshape(-1)] = True
+    edges = np.flatnonzero(np.diff(np.concatenate([[1], touch[:part.n_owned].astype(np.int8), [1]])))
+    if len(edges) < 2:
+        return (0, 0)
+    starts, ends = edges[0::2], edges[1::2]                      # runs of non-touching nodes
+    k = int(np.argmax(ends - starts))
+    return (int(starts[k]), int(ends[k]))
+
+
 class Halo:
     """Ghost update of a (n_local_nodes, vec) field: owners -> ghosts, neighbour ranks only.  With the library's NCCL
     communicator the pack kernel and the grouped ncclSend / ncclRecv are issued from C (fem_halo_exchange)."""
@@ -250,6 +263,13 @@ class Halo:
             as_p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
             _lib.check(_lib.load().fem_halo_create(comm.handle, vec, n, as_p(peer), as_p(send_ptr), _lib.ptr(self._idx),
                                                    as_p(recv_start), as_p(recv_count), _lib.ptr(self._buf), ctypes.byref(self.handle)))
+            # owned nodes without a ghost neighbour (no cell of theirs holds a ghost): the longest run of them is multiplied
+            # while the exchange is in flight (fem_halo_set_interior; FEM_HALO_OVERLAP=0 keeps exchange and SpMV in sequence)
+            import os
+            self.interior = (0, 0)
+            if n and os.environ.get('FEM_HALO_OVERLAP', '1') != '0':
+                self.interior = interior_node_range(part)
+                _lib.check(_lib.load().fem_halo_set_interior(self.handle, self.interior[0], self.interior[1]))
 
     def update(self, x):
         """x: flat (n_local*vec,) or (n_local, vec) tensor, updated in place."""

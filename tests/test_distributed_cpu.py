@@ -157,3 +157,23 @@ def test_send_lists_from_local_cells_equal_the_other_ranks_ghost_lists():
                     _, g_s, o_s = _rank_view(conn, ranges, s)
                     mine = g_s[o_s == rank] - ranges[rank]
                     assert np.array_equal(part.send.get(s, np.zeros(0, np.int64)), mine)
+
+
+def test_interior_node_range_reads_no_ghosts():
+    """The run of owned nodes whose rows are multiplied while the halo exchange is in flight (fem_halo_set_interior) must not
+    touch a ghost column and must be maximal."""
+    import jax_fem_b200 as jf
+    from jax_fem_b200.distributed import partition_mesh, interior_node_range
+    m = jf.box_mesh(12, 5, 4, 3., 1., 1.)
+    cells = m.cells_dict['hexahedron']
+    for world in (2, 3, 4):
+        for rank in range(world):
+            part = partition_mesh(cells, len(m.points), rank, world)
+            lo, hi = interior_node_range(part)
+            assert 0 <= lo < hi <= part.n_owned
+            cl = part.cells_local
+            neigh_max = np.zeros(part.n_local, dtype=np.int64)
+            np.maximum.at(neigh_max, cl.reshape(-1), np.repeat(cl.max(axis=1), cl.shape[1]))
+            assert (neigh_max[lo:hi] < part.n_owned).all()                      # no ghost neighbour inside the run
+            assert lo == 0 or neigh_max[lo - 1] >= part.n_owned                 # maximal on both sides
+            assert hi == part.n_owned or neigh_max[hi] >= part.n_owned
