@@ -377,37 +377,62 @@ def main():
 
     # ---- e2e: public API from pinned host buffers -------------------------------------------------------
     # Every step copies its input from pinned host memory and its result (the residual with Dirichlet rows) back.
-    # The copies run on a second stream: the D2H of step k overlaps get_A of step k, the H2D of step k+1 is issued
-    # as soon as step k's element kernel has consumed the other input buffer.  All of it is inside the timed region.
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    main_s, copy_s = torch.cuda.current_stream(), torch.cuda.Stream()
+    # The copies run on two more streams, one per direction (PCIe is full duplex), and are software-pipelined against the
+    # compute: the H2D of step k+1 goes into the other input buffer as soon as step k-1 has consumed it (so it overlaps the
+    # whole of step k), the D2H of step k overlaps get_A of step k and the start of step k+1.  All of it is inside the timed
+    # region; a step is only as fast as the slower of its kernels and its 8 B/DOF in each direction over PCIe.
+    main_s, h2d_s, d2h_s = torch.cuda.current_stream(), torch.cuda.Stream(), torch.cuda.Stream()
     sol_bufs = [torch.empty_like(sol), torch.empty_like(sol)]
-    h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
-    res_ready, d2h_done = torch.cuda.Event(), torch.cuda.Event()
-    barrier()
-    e0.record()
-    copy_s.wait_stream(main_s)
-    with torch.cuda.stream(copy_s):
+
+    def e2e_pass(n_steps):
+        """-> (ms per step, last result, last matrix)"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        res_ready, d2h_done = torch.cuda.Event(), torch.cuda.Event()
+        barrier()
+        e0.record()
+        h2d_s.wait_stream(main_s)
+        d2h_s.wait_stream(main_s)
+        with torch.cuda.stream(h2d_s):
+            sol_bufs[0].copy_(sol_host, non_blocking=True)
+            h2d_done[0].record(h2d_s)
+        for k in range(n_steps):
+            if k + 1 < n_steps:
+                with torch.cuda.stream(h2d_s):
+                    if k >= 1:
+                        h2d_s.wait_event(consumed[(k + 1) % 2])       # step k-1 was the last reader of that buffer
+                    sol_bufs[(k + 1) % 2].copy_(sol_host, non_blocking=True)
+                    h2d_done[(k + 1) % 2].record(h2d_s)
+            main_s.wait_event(h2d_done[k % 2])
+            res = prob.newton_update([sol_bufs[k % 2]])[0]
+            res_vec = jf.apply_bc_vec(res.reshape(-1), sol_bufs[k % 2].reshape(-1), prob)
+            consumed[k % 2].record(main_s)
+            res_ready.record(main_s)
+            res_vec.record_stream(d2h_s)
+            with torch.cuda.stream(d2h_s):
+                d2h_s.wait_event(res_ready)
+                res_host.copy_(res_vec, non_blocking=True)
+                d2h_done.record(d2h_s)
+            A = jf.get_A(prob)
+        main_s.wait_event(d2h_done)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / n_steps, res_vec, A
+
+    e2e_pass(max(args.warmup, 3))            # untimed: the caching allocator settles on the blocks the pipelined copies need
+    e2e_ms, res_vec, A = e2e_pass(args.steps)
+    # the PCIe rates these copies get on this box (outside the timed region): with ~8 B/DOF each way they bound e2e
+    p0, p1, p2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    p0.record()
+    for _ in range(3):
         sol_bufs[0].copy_(sol_host, non_blocking=True)
-        h2d_done[0].record(copy_s)
-    for k in range(args.steps):
-        main_s.wait_event(h2d_done[k % 2])
-        res = prob.newton_update([sol_bufs[k % 2]])[0]
-        res_vec = jf.apply_bc_vec(res.reshape(-1), sol_bufs[k % 2].reshape(-1), prob)
-        res_ready.record(main_s)
-        res_vec.record_stream(copy_s)
-        with torch.cuda.stream(copy_s):
-            copy_s.wait_event(res_ready)
-            if k + 1 < args.steps:
-                sol_bufs[(k + 1) % 2].copy_(sol_host, non_blocking=True)
-                h2d_done[(k + 1) % 2].record(copy_s)
-            res_host.copy_(res_vec, non_blocking=True)
-            d2h_done.record(copy_s)
-        A = jf.get_A(prob)
-    main_s.wait_event(d2h_done)
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1) / args.steps
+    p1.record()
+    for _ in range(3):
+        res_host.copy_(res_vec, non_blocking=True)
+    p2.record()
+    torch.cuda.synchronize()
+    pcie = {"h2d_gbs": 3 * n_local * 8 / (p0.elapsed_time(p1) * 1e6), "d2h_gbs": 3 * n_local * 8 / (p1.elapsed_time(p2) * 1e6)}
     del sol_bufs
     log(f"assembly {ms_step:.3f} ms/step (element {t_elem:.3f}, bc {t_bc:.3f}, gather {t_gather:.3f}); e2e {e2e_ms:.3f} ms")
 
@@ -642,7 +667,9 @@ def main():
                               "note": "algorithmic bytes are those of scalar CSR (12 B/nnz, SURVEY 8d); the kernel reads 8.44 B/nnz, "
                                       "so `frac` can exceed 1; `frac_of_kernel_bytes` is the fraction on the kernel's own traffic"},
             "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": "DOF/s", "h2d_bytes_per_step": n_local * 8,
-                    "d2h_bytes_per_step": n_local * 8, "ms_per_step": e2e_ms},
+                    "d2h_bytes_per_step": n_local * 8, "ms_per_step": e2e_ms,
+                    "pcie_gbs_this_box": pcie,
+                    "pcie_bound_ms": max(n_local * 8 / (pcie["h2d_gbs"] * 1e6), n_local * 8 / (pcie["d2h_gbs"] * 1e6))},
             "gpu_launches": args.steps * 4 * world, "clocks": clocks, "setup_s": setup_s,
         }
         if solve:
