@@ -6,7 +6,8 @@
 // 262-266) and FiniteElement.get_shape_grads (jax_fem/fe.py:112-141).  The reference would materialise
 // shape_grads (C,216,27,3) = 30 GB at 60^3; here geometry is recomputed per cell.
 //
-// One CTA (10 warps) per cell:
+// General kernel (hex27_kernel): persistent CTAs of 10 warps, one cell at a time per CTA (all cells, or the list the affine-cell
+// pass at the end of this file leaves):
 //   phase 1  thread = quadrature point: J, J^-1, JxW, grad u, stress  ->  shared {J^-1, E w, S = sigma JxW}
 //   phase 2  for chunks of 32 quadrature points:
 //              all threads: g[q][n][:] = dN[q][n] J^-1(q)                     -> shared Gq[q][3n+d]
