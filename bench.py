@@ -602,7 +602,7 @@ def main():
     # ---- cfg 2 itself (BASELINE.json configs[1], 100^3) on one GPU, for continuity with round 1 --------------------------
     cfg2 = None
     if world == 1 and args.cfg2_size and args.cfg2_size != args.size and args.workload == "elasticity":
-        del A, res_vec, res, sol, prob
+        del A, res_vec, sol, prob
         torch.cuda.empty_cache()
         p2, _ = build_problem(args.cfg2_size)
         f2 = p2.fes[0]
