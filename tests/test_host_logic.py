@@ -494,3 +494,80 @@ def test_hex27_affine_tables_reproduce_the_quadrature_on_affine_cells():
     pts2 = pts.copy()
     pts2[cells[0][20]] += 0.01
     assert affine_map(pts2[cells[0]])[1] > 1e-3
+
+
+def _undefined_names(path):
+    """Names a function reads or deletes that are bound nowhere it can see (its own scope, an enclosing function, the module,
+    builtins).  A small stand-in for pyflakes, which this image does not have: bench.py runs unattended on the GPU box."""
+    import ast
+    import builtins
+    tree = ast.parse(open(path).read(), path)
+    problems = []
+
+    def bound_in(node):
+        names = set()
+        args = getattr(node, 'args', None)
+        if isinstance(args, ast.arguments):
+            for a in args.posonlyargs + args.args + args.kwonlyargs + [args.vararg, args.kwarg]:
+                if a is not None:
+                    names.add(a.arg)
+
+        def visit(n):
+            for child in ast.iter_child_nodes(n):
+                if isinstance(child, (ast.FunctionDef, ast.AsyncFunctionDef, ast.ClassDef)):
+                    names.add(child.name)
+                    continue                      # own scope
+                if isinstance(child, ast.Lambda):
+                    continue
+                if isinstance(child, ast.Name) and isinstance(child.ctx, ast.Store):
+                    names.add(child.id)
+                elif isinstance(child, (ast.Import, ast.ImportFrom)):
+                    for al in child.names:
+                        names.add((al.asname or al.name).split('.')[0])
+                elif isinstance(child, ast.ExceptHandler) and child.name:
+                    names.add(child.name)
+                elif isinstance(child, (ast.Global, ast.Nonlocal)):
+                    names.update(child.names)
+                elif isinstance(child, (ast.ListComp, ast.SetComp, ast.DictComp, ast.GeneratorExp)):
+                    for g in child.generators:
+                        for t in ast.walk(g.target):
+                            if isinstance(t, ast.Name):
+                                names.add(t.id)
+                elif isinstance(child, ast.NamedExpr):
+                    names.add(child.target.id)
+                visit(child)
+        visit(node)
+        return names
+
+    def check(node, visible):
+        scope = visible | bound_in(node)
+        for child in ast.iter_child_nodes(node):
+            walk(child, scope)
+
+    def walk(n, scope):
+        if isinstance(n, (ast.FunctionDef, ast.AsyncFunctionDef, ast.Lambda)):
+            for d in getattr(n, 'decorator_list', []):
+                walk(d, scope)
+            check(n, scope)
+            return
+        if isinstance(n, ast.ClassDef):
+            check(n, scope)
+            return
+        if isinstance(n, ast.Name) and isinstance(n.ctx, (ast.Load, ast.Del)) and n.id not in scope:
+            problems.append(f"{path}:{n.lineno}: {n.id}")
+        for child in ast.iter_child_nodes(n):
+            walk(child, scope)
+
+    check(tree, set(dir(builtins)) | {'__file__', '__name__', '__doc__'})
+    return problems
+
+
+def test_scripts_and_package_have_no_undefined_names():
+    import glob
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [os.path.join(root, f) for f in ("bench.py", "__graft_entry__.py")]
+    files += sorted(glob.glob(os.path.join(root, "jax_fem_b200", "*.py"))) + sorted(glob.glob(os.path.join(root, "examples", "*.py")))
+    files += sorted(glob.glob(os.path.join(root, "tests", "*.py"))) + sorted(glob.glob(os.path.join(root, "oracle", "*.py")))
+    problems = [p for f in files for p in _undefined_names(f)]
+    assert not problems, "\n".join(problems)
