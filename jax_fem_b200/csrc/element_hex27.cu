@@ -195,20 +195,26 @@ __device__ __forceinline__ void hex27_cell(const Hex27Args& A, const int64_t c, 
   // g[q][n][:] = dN[q][n] J^-1(q) of one chunk -> Gq buffer; done by the warps with the fewest tiles (3..9: the three warps that
   // own 9 tiles each are the critical path of the DMMA step and get none of it)
   constexpr int G_FIRST = 96, G_THREADS = H27_THREADS - G_FIRST;
+  constexpr int G_ITEMS = (H27_QC * H27_NN + G_THREADS - 1) / G_THREADS;   // 4 (point, node) pairs per thread
   auto fill_chunk = [&](int q0, double* Gb) {
     if (tid < G_FIRST) return;
-    for (int j = tid - G_FIRST; j < H27_QC * H27_NN; j += G_THREADS) {
-      const int ql = j / H27_NN, n = j % H27_NN, q = q0 + ql;
-      double g[3] = {0.0, 0.0, 0.0};
-      if (q < nq) {
-        const double* dN = A.ref + ((int64_t)q * H27_NN + n) * 3;
-        const double d0 = __ldg(dN), d1 = __ldg(dN + 1), d2 = __ldg(dN + 2);
-        const double* inv = QP + q * H27_QP;
+    // all loads of the thread's pairs are issued before the first use: one L2 round trip per chunk instead of four
+    double d[G_ITEMS][3];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) g[d] = d0 * inv[d] + d1 * inv[3 + d] + d2 * inv[6 + d];
-      }
+    for (int k = 0; k < G_ITEMS; ++k) {
+      const int j = tid - G_FIRST + k * G_THREADS, ql = j / H27_NN, n = j % H27_NN, q = q0 + ql;
+      const bool on = j < H27_QC * H27_NN && q < nq;
+      const double* dN = A.ref + ((int64_t)(on ? q : 0) * H27_NN + (on ? n : 0)) * 3;
 #pragma unroll
-      for (int d = 0; d < 3; ++d) Gb[ql * H27_GS + n * 3 + d] = g[d];
+      for (int e = 0; e < 3; ++e) d[k][e] = on ? __ldg(dN + e) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < G_ITEMS; ++k) {
+      const int j = tid - G_FIRST + k * G_THREADS, ql = j / H27_NN, n = j % H27_NN, q = q0 + ql;
+      if (j >= H27_QC * H27_NN) break;
+      const double* inv = QP + (q < nq ? q : 0) * H27_QP;
+#pragma unroll
+      for (int e = 0; e < 3; ++e) Gb[ql * H27_GS + n * 3 + e] = d[k][0] * inv[e] + d[k][1] * inv[3 + e] + d[k][2] * inv[6 + e];
     }
   };
   // Two Gq buffers: while the slower warps still multiply chunk k, the others already fill chunk k+1 -- ONE barrier per chunk.
@@ -231,11 +237,17 @@ __device__ __forceinline__ void hex27_cell(const Hex27Args& A, const int64_t c, 
     // gradients (dependent global loads: 38.4 -> 43.7 ms); 4 lanes per row with 11 warps x 6 tiles (more fragment loads: 40.8 ms)
     if (rt >= 0 && rt < H27_ND) {
       const int a = rt / 3, i = rt % 3;
-      for (int ql = 0; ql < H27_QC; ++ql) {
-        const double* S = QP + (q0 + ql) * H27_QP + 10 + i * 3;
-        const double* g = Gc + ql * H27_GS + a * 3;
-        racc = fma(S[0], g[0], fma(S[1], g[1], fma(S[2], g[2], racc)));                   // problem.py:210
+      double r4[4] = {0.0, 0.0, 0.0, 0.0};                 // four independent chains instead of one of 96 dependent FMAs
+#pragma unroll 2
+      for (int ql = 0; ql < H27_QC; ql += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double* S = QP + (q0 + ql + u) * H27_QP + 10 + i * 3;
+          const double* g = Gc + (ql + u) * H27_GS + a * 3;
+          r4[u] = fma(S[0], g[0], fma(S[1], g[1], fma(S[2], g[2], r4[u])));                 // problem.py:210
+        }
       }
+      racc += (r4[0] + r4[1]) + (r4[2] + r4[3]);
     }
     if (q0 + H27_QC < nq_pad) fill_chunk(q0 + H27_QC, Gq + ((kc + 1) & 1) * (H27_QC * H27_GS));
     __syncthreads();
