@@ -732,6 +732,50 @@ def test_solution_dependent_mass_maps_match_oracle(case):
             break
 
 
+def test_c_abi_empty_inputs_and_argument_errors():
+    """Edge cases straight at the C ABI: empty meshes / boundary sets are no-ops that return FEM_OK, missing pointers and
+    unregistered combinations return FEM_EINVAL with a message in fem_last_error (never a crash, never a silent fallback)."""
+    from jax_fem_b200 import _lib
+    lib, P = _lib.load(), _lib.ptr
+    dev = 'cuda'
+    d = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=dev)
+    i32 = lambda *shape: torch.zeros(shape, dtype=torch.int32, device=dev)
+    pts, cells, sol, ref, Re = d(8, 3), i32(1, 8), d(8, 3), d(8 * 8 * 3 + 8), d(1, 24)
+    params = _lib.host_doubles([70e3, 0.3])
+    ok = lambda rc: rc == 0
+    einval = lambda rc, text: rc == -1 and text in lib.fem_last_error().decode()
+    # zero cells / zero boundary nodes / zero blocks: nothing is launched
+    assert ok(lib.fem_element_residual_jacobian(0, 3, 1, params, P(pts), P(cells), 0, P(sol), None, P(ref), None, None, P(Re), None))
+    assert ok(lib.fem_element_tiles(1, params, P(pts), P(cells), 0, P(sol), None, P(ref), None, P(d(72)), P(Re),
+                                    (_lib.ctypes.c_double * 3)(), None))
+    assert ok(lib.fem_hex27_residual_jacobian(1, params, P(pts), P(cells), 0, P(sol), None, P(ref), None, 27, None, None, None,
+                                              None, P(Re), None))
+    assert ok(lib.fem_mass_term(0, 1, P(pts), P(cells), 0, P(sol), P(ref), P(d(64)), 8, 1.0, None, _lib.host_doubles([0.]), None,
+                                None, None, P(Re), None))
+    assert ok(lib.fem_gather_csr(3, 8, 0, P(i32(4)), P(i32(4)), P(i32(4)), P(d(72)), P(d(9)), None))
+    assert ok(lib.fem_apply_bc_vec(0, None, None, 1.0, P(d(3)), P(d(3)), None))
+    # missing pointers
+    assert einval(lib.fem_element_residual_jacobian(0, 3, 1, params, None, P(cells), 1, P(sol), None, P(ref), None, None, P(Re), None),
+                  "null pointer")
+    assert einval(lib.fem_mass_term(0, 1, P(pts), P(cells), 1, P(sol), P(ref), None, 8, 1.0, None, _lib.host_doubles([0.]), None,
+                                    None, None, P(Re), None), "null pointer")
+    # unregistered combinations
+    assert einval(lib.fem_element_residual_jacobian(0, 2, 1, params, P(pts), P(cells), 1, P(sol), None, P(ref), None, None, P(Re), None), "")
+    assert einval(lib.fem_mass_term(2, 3, P(pts), P(cells), 1, P(sol), P(ref), P(d(64)), 8, 1.0, None, _lib.host_doubles([0.] * 3),
+                                    None, None, None, P(Re), None), "unregistered")
+    assert einval(lib.fem_mass_term(0, 1, P(pts), P(cells), 1, P(sol), P(ref), P(d(64)), 64, 1.0, None, _lib.host_doubles([0.]), None,
+                                    None, None, P(Re), None), "quadrature")
+    assert einval(lib.fem_hex27_residual_jacobian(2, params, P(pts), P(cells), 1, P(sol), None, P(ref), None, 27, None, None, None,
+                                                  None, P(Re), None), "HEX27")
+    # the affine pass needs both its tables and its workspace
+    assert einval(lib.fem_hex27_residual_jacobian(1, params, P(pts), P(cells), 1, P(sol), None, P(ref), None, 27, P(d(8)), None, None,
+                                                  None, P(Re), None), "affine")
+    # SIMP without its density field
+    assert einval(lib.fem_hex27_residual_jacobian(3, params, P(pts), P(cells), 1, P(sol), None, P(ref), None, 27, None, None, None,
+                                                  None, P(Re), None), "density")
+    torch.cuda.synchronize()
+
+
 def test_csr_diagonal_beyond_2_30_nonzeros():
     """The Jacobi preconditioner of the 200^3 mesh (nnz = 1.95e9): row offsets above 2^30 must not overflow the binary search
     for the diagonal entry (lo + hi in int32 did: the first 200^3 solve on one GPU hung).  Synthetic banded matrix with
