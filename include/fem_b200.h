@@ -343,6 +343,23 @@ int fem_halo_exchange(void* halo, double* x, void* stream);
  * by the second launch.  Used when more than half of the owned nodes are in the range and the matrix has its node-block
  * structure (vec 2 or 3); an empty range (the default) keeps exchange and product in sequence.                          */
 int fem_halo_set_interior(void* halo, int64_t node_lo, int64_t node_hi);
+
+/* Peer-memory halo exchange for the distributed Krylov loops (ranks on one node, NVLink / NVSwitch): instead of ncclSend /
+ * ncclRecv the pack kernel stores every interface value straight into the neighbour's mailbox and the last block raises a flag
+ * there (st.release.sys); the receiver's unpack kernel waits for its flags (bounded spin: an error, never a hang) and copies
+ * the ghost blocks into the vector.  The all-reduce that follows every product in CG / BiCGSTAB orders consecutive exchanges,
+ * and the two receive buffers alternate.  Setup, once per halo plan:
+ *   fem_halo_p2p_alloc    every rank: mailbox of 256 + 2 * n_ghost_nodes * vec * 8 bytes (cudaMalloc) and its 64-byte CUDA IPC
+ *                         handle, to be handed to the neighbours by any host-side means;
+ *   fem_halo_p2p_connect  per neighbour k: map its mailbox (cudaIpcOpenMemHandle); peer_ghost_offset_nodes = where this rank's
+ *                         block starts inside the neighbour's ghost range, my_slot_in_peer = this rank's index in the
+ *                         neighbour's peer list (its flag word);
+ *   fem_halo_p2p_enable   after a barrier, on every rank or on none.
+ * fem_halo_exchange itself keeps using NCCL (no ordering guarantee between two stand-alone exchanges).                    */
+int fem_halo_p2p_alloc(void* halo, int64_t n_owned_nodes, int64_t n_ghost_nodes, void* ipc_handle64_out);
+int fem_halo_p2p_connect(void* halo, int k, const void* peer_ipc_handle64, int64_t peer_n_ghost_nodes,
+                         int64_t peer_ghost_offset_nodes, int my_slot_in_peer);
+int fem_halo_p2p_enable(void* halo, int on);
 int fem_allreduce_sum(void* halo, double* buf, int count, void* stream);
 /* Distributed Jacobi-CG / BiCGSTAB on the rank's owned rows (CSR rows 0..n_owned-1 complete, columns index the local
  * vector of n_local entries).  Same recurrences, stopping rule and info_host as fem_pcg / fem_pbicgstab; per iteration

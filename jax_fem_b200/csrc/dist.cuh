@@ -46,13 +46,30 @@ struct HaloPlan {
   int64_t int_lo, int_hi;
   cudaStream_t comm_stream;
   cudaEvent_t ev_packed, ev_arrived;
+  // peer-memory exchange (fem_halo_p2p_*): the pack kernel stores the interface values straight into the neighbours' mailboxes
+  // over NVLink and raises a flag there; the receiver's unpack kernel waits for its flags and copies the ghosts into x.
+  // mailbox (cudaMalloc, exported with cudaIpcGetMemHandle): 16 flag words, an error word, a ticket, then two receive buffers
+  // of n_ghost * vec doubles (alternating with the exchange counter).
+  unsigned long long* mailbox;
+  int64_t n_ghost, n_owned_nodes;        // ghost / owned nodes of this rank
+  double* peer_buf[16];                  // mapped: start of my block in neighbour k's receive buffer 0
+  int64_t peer_stride[16];               // doubles between neighbour k's two receive buffers
+  unsigned long long* peer_flag[16];     // mapped: my flag word in neighbour k's mailbox
+  void* peer_base[16];                   // what cudaIpcOpenMemHandle returned (closed in fem_halo_destroy)
+  int p2p_ready;
+  mutable unsigned long long p2p_seq;    // exchanges so far; identical on every rank
 };
+constexpr int kMailboxHeaderWords = 32;  // 16 flags, error, ticket, padding: 256 bytes
 
 int halo_exchange(const HaloPlan* h, double* x, cudaStream_t st);
 // split form: halo_begin packs on `st` and issues the sends / receives on the plan's own stream; work queued on `st` after
 // it runs concurrently with the transfer and must not touch the ghost entries of x; halo_end makes `st` wait for the arrival.
 int halo_begin(const HaloPlan* h, double* x, cudaStream_t st);
 int halo_end(const HaloPlan* h, cudaStream_t st);
+// peer-memory form of the same pair (valid when h->p2p_ready): no NCCL call, no second stream
+int halo_p2p_send(const HaloPlan* h, const double* x, cudaStream_t st);
+int halo_p2p_receive(const HaloPlan* h, double* x, cudaStream_t st);
+int halo_p2p_status(const HaloPlan* h, cudaStream_t st);      // FEM_ECUDA if a receive ever gave up waiting
 int allreduce_sum(const HaloPlan* h, double* buf, int count, cudaStream_t st);
 
 }  // namespace femb200

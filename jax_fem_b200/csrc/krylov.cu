@@ -676,9 +676,11 @@ int dist_spmv_split(const HaloPlan* h, const Mat& A, double* x, double* y, const
   const int cap = persistent_grid(k);
   auto blocks = [&](int64_t cnt) { return (int)std::max<int64_t>(1, std::min<int64_t>(cap, (cnt + NPB - 1) / NPB)); };
   const int g1 = blocks(hi - lo), g2 = blocks(n_nodes - (hi - lo));
-  if (int e = halo_begin(h, x, st)) return e;
+  // peer-memory exchange when the plan has it (stores into the neighbours' mailboxes, flags, wait + unpack: no NCCL call, one
+  // stream); otherwise ncclSend / ncclRecv on the plan's second stream
+  if (int e = h->p2p_ready ? halo_p2p_send(h, x, st) : halo_begin(h, x, st)) return e;
   k<<<g1, kThreads, 0, st>>>(RowSplit{lo, hi - lo, 0, 0, 0, g1 + g2, 0}, A.brow_ptr, A.bcol, A.data, x, y, d1, w.s, w.partial);
-  if (int e = halo_end(h, st)) return e;
+  if (int e = h->p2p_ready ? halo_p2p_receive(h, x, st) : halo_end(h, st)) return e;
   k<<<g2, kThreads, 0, st>>>(RowSplit{0, lo, hi, n_nodes - hi, g1, g1 + g2, 1}, A.brow_ptr, A.bcol, A.data, x, y, d1, w.s, w.partial);
   FEM_LAUNCH_CHECK();
   return FEM_OK;
@@ -691,7 +693,12 @@ int dist_spmv(const HaloPlan* h, const Mat& A, double* x, double* y, const doubl
                      (h->int_hi - h->int_lo) * 2 > n_nodes;          // worth two launches only if most rows are interior
   if (split && A.vec == 3) return dist_spmv_split<MODE, 3>(h, A, x, y, d1, w, st);
   if (split && A.vec == 2) return dist_spmv_split<MODE, 2>(h, A, x, y, d1, w, st);
-  if (int e = halo_exchange(h, x, st)) return e;
+  if (h->p2p_ready) {
+    if (int e = halo_p2p_send(h, x, st)) return e;
+    if (int e = halo_p2p_receive(h, x, st)) return e;
+  } else if (int e = halo_exchange(h, x, st)) {
+    return e;
+  }
   spmv_fused<MODE>(A, x, y, d1, w, st);
   return FEM_OK;
 }
@@ -894,6 +901,7 @@ int dist_finish(const HaloPlan* h, const Mat& A, const double* b, double* x, con
   FEM_CUDA_CHECK(cudaStreamSynchronize(st));
   info_host[0] = hs[S_K];
   info_host[1] = hs[S_RR];
+  if (int e = halo_p2p_status(h, st)) return e;
   if (int e = halo_exchange(h, x, st)) return e;                 // the caller gets up-to-date ghosts
   spmv_fused<0>(A, x, scratch, nullptr, w, st);
   dresnorm_kernel<<<FEM_PGRID(dresnorm_kernel)>>>(A.n, scratch, b, w.s, w.partial);

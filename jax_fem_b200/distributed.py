@@ -270,6 +270,44 @@ class Halo:
             if n and os.environ.get('FEM_HALO_OVERLAP', '1') != '0':
                 self.interior = interior_node_range(part)
                 _lib.check(_lib.load().fem_halo_set_interior(self.handle, self.interior[0], self.interior[1]))
+            self.p2p = False
+            if os.environ.get('FEM_HALO_P2P', '0') == '1' and comm.world > 1:       # opt-in: measured on par with NCCL
+                self.p2p = self._connect_peer_memory(part, comm, peers)
+
+    def _connect_peer_memory(self, part, comm, peers):
+        """Peer-memory halo exchange for the library's Krylov loops (csrc/dist.cu): every rank allocates a mailbox, the ranks
+        swap its CUDA IPC handle and their ghost layouts through torch.distributed, map their neighbours' mailboxes and switch
+        the plan over -- on all ranks or on none (e.g. ranks on different nodes, IPC not permitted): then ncclSend / ncclRecv
+        stay in use."""
+        import ctypes
+        import socket
+        lib = _lib.load()
+        n_ghost = part.n_local - part.n_owned
+        hbuf = (ctypes.c_char * 64)()
+        ok = lib.fem_halo_p2p_alloc(self.handle, part.n_owned, n_ghost, hbuf) == 0
+        mine = {"ok": ok, "handle": bytes(hbuf), "peers": list(peers), "n_owned": part.n_owned, "n_ghost": n_ghost,
+                "recv": {int(s): (int(a), int(b)) for s, (a, b) in part.recv.items()}, "host": socket.gethostname()}
+        everyone = [None] * comm.world
+        comm.dist.all_gather_object(everyone, mine, group=comm.group)
+        ok = all(e["ok"] and e["host"] == mine["host"] for e in everyone)
+        if ok:
+            for k, s in enumerate(peers):
+                theirs = everyone[s]
+                start = theirs["recv"].get(comm.rank, (theirs["n_owned"], theirs["n_owned"]))[0]
+                rc = lib.fem_halo_p2p_connect(self.handle, k, theirs["handle"], theirs["n_ghost"], start - theirs["n_owned"],
+                                              theirs["peers"].index(comm.rank))
+                ok = ok and rc == 0
+        verdicts = [None] * comm.world
+        comm.dist.all_gather_object(verdicts, bool(ok), group=comm.group)
+        ok = all(verdicts)
+        if ok:
+            _lib.check(lib.fem_halo_p2p_enable(self.handle, 1))
+        elif comm.rank == 0:
+            import warnings
+            warnings.warn("peer-memory halo exchange unavailable (" + lib.fem_last_error().decode() + "): using ncclSend / ncclRecv")
+        torch.cuda.synchronize()
+        comm.dist.barrier(group=comm.group)
+        return ok
 
     def update(self, x):
         """x: flat (n_local*vec,) or (n_local, vec) tensor, updated in place."""

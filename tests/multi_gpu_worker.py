@@ -63,6 +63,20 @@ def main():
     assert e1b <= TOL, f"sharded BiCGSTAB solve differs: {e1b}"
     report["bicgstab"] = {"err": e1b, "iterations": sp.last_info["iterations"]}
 
+    # ---- 1b. the same solves with the peer-memory halo exchange (stores into the neighbours' mailboxes instead of ncclSend /
+    #          ncclRecv): the arithmetic is untouched, so iterates and solutions must be bit-identical --------------------------
+    os.environ["FEM_HALO_P2P"] = "1"
+    sp2 = ShardedProblem(Elasticity, pts, cells, comm, vec=3, dim=3, **kw)
+    os.environ.pop("FEM_HALO_P2P")
+    assert sp2.halo.p2p, "peer-memory exchange did not come up on this node"
+    sol2 = sp2.solve_linear().cpu().numpy()
+    it2 = sp2.last_info["iterations"]
+    assert np.array_equal(sol2, sol) and it2 == report["cg"]["iterations"], "peer-memory CG differs from the NCCL one"
+    sol2b = sp2.solve_linear(method='bicgstab').cpu().numpy()
+    assert np.array_equal(sol2b, sol_b), "peer-memory BiCGSTAB differs from the NCCL one"
+    report["p2p"] = {"cg_iterations": it2, "bit_identical": True}
+    del sp2
+
     # ---- 2. Neo-Hookean Newton with per-iteration re-assembly ---------------------------------------------------------------
     class Hyper(jf.Problem):
         def get_tensor_map(self):
