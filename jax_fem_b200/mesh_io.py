@@ -7,8 +7,11 @@ parsed here with the standard library.  ``read_mesh`` returns the same meshio-li
 generate_mesh.py (``.points``, ``.cells_dict`` keyed by meshio cell names, ``.point_data``), so reference code such as
 ``Mesh(m.points, m.cells_dict['hexahedron'])`` runs unchanged.
 
-First-order cells only (hexahedron / quad / tetra / triangle: their node order is the same in Gmsh, Abaqus, VTK and
-meshio); anything else raises -- a silently permuted higher-order cell would corrupt every element matrix.
+First-order cells (hexahedron / quad / tetra / triangle: their node order is the same in Gmsh, Abaqus, VTK and meshio) and
+the 27-node hexahedron of the path's HEX27 element: VTK type 29 is already in the meshio / VTK order the kernels use, Gmsh
+type 12 numbers its edge and face nodes differently and is permuted (the permutation is derived from the two documented
+edge / face tables below, not typed in).  Anything else raises -- a silently permuted higher-order cell would corrupt every
+element matrix.
 """
 import os
 import xml.etree.ElementTree as ET
@@ -28,7 +31,27 @@ _GMSH = {1: ('line', 2), 2: ('triangle', 3), 3: ('quad', 4), 4: ('tetra', 4), 5:
 _VTK = {3: ('line', 2), 5: ('triangle', 3), 9: ('quad', 4), 10: ('tetra', 4), 12: ('hexahedron', 8), 72: ('hexahedron', 8)}
 _ABAQUS = {'C3D8': 'hexahedron', 'C3D8R': 'hexahedron', 'C3D4': 'tetra', 'CPS4': 'quad', 'CPE4': 'quad', 'CPS4R': 'quad',
            'CPE4R': 'quad', 'S4': 'quad', 'S4R': 'quad', 'CPS3': 'triangle', 'CPE3': 'triangle', 'S3': 'triangle'}
-_NODES = {'hexahedron': 8, 'tetra': 4, 'quad': 4, 'triangle': 3, 'line': 2, 'vertex': 1}
+_NODES = {'hexahedron': 8, 'tetra': 4, 'quad': 4, 'triangle': 3, 'line': 2, 'vertex': 1, 'hexahedron27': 27}
+_GMSH[12] = ('hexahedron27', 27)
+_VTK[29] = ('hexahedron27', 27)
+
+
+def _hex27_gmsh_to_vtk():
+    """perm such that vtk_cell = gmsh_cell[perm].  Both formats number the 8 vertices alike, then the 12 edge midpoints, the 6
+    face centres and the cell centre; only the order of the edges and faces differs (Gmsh reference manual, "Node ordering";
+    VTK_TRIQUADRATIC_HEXAHEDRON)."""
+    corner = [(0, 0, 0), (2, 0, 0), (2, 2, 0), (0, 2, 0), (0, 0, 2), (2, 0, 2), (2, 2, 2), (0, 2, 2)]
+    centre = lambda vs: tuple(sum(corner[v][d] for v in vs) // len(vs) for d in range(3))
+    gmsh_edges = [(0, 1), (0, 3), (0, 4), (1, 2), (1, 5), (2, 3), (2, 6), (3, 7), (4, 5), (4, 7), (5, 6), (6, 7)]
+    gmsh_faces = [(0, 3, 2, 1), (0, 1, 5, 4), (0, 4, 7, 3), (1, 2, 6, 5), (2, 3, 7, 6), (4, 5, 6, 7)]
+    vtk_edges = [(0, 1), (1, 2), (2, 3), (3, 0), (4, 5), (5, 6), (6, 7), (7, 4), (0, 4), (1, 5), (2, 6), (3, 7)]
+    vtk_faces = [(0, 4, 7, 3), (1, 2, 6, 5), (0, 1, 5, 4), (2, 3, 7, 6), (0, 1, 2, 3), (4, 5, 6, 7)]
+    where = lambda edges, faces: corner + [centre(e) for e in edges] + [centre(f) for f in faces] + [(1, 1, 1)]
+    gmsh = where(gmsh_edges, gmsh_faces)
+    return np.array([gmsh.index(p) for p in where(vtk_edges, vtk_faces)])
+
+
+_HEX27_GMSH_TO_VTK = _hex27_gmsh_to_vtk()
 
 
 def _stack(groups):
@@ -58,8 +81,8 @@ def read_msh(path):
                 f = l.split()
                 etype, ntags = int(f[1]), int(f[2])
                 if etype not in _GMSH:
-                    raise NotImplementedError(f"{path}: Gmsh element type {etype} is not a first-order cell; higher-order node "
-                                              "orders differ between Gmsh and VTK and are not converted here")
+                    raise NotImplementedError(f"{path}: Gmsh element type {etype} is not registered (first-order cells and the "
+                                              "27-node hexahedron are); other higher-order node orders are not converted here")
                 name, per = _GMSH[etype]
                 groups.setdefault(name, []).append([int(v) for v in f[3 + ntags:3 + ntags + per]])
             i += n + 3
@@ -69,7 +92,10 @@ def read_msh(path):
         raise ValueError(f"{path}: no $Nodes section")
     lookup = np.full(int(ids.max()) + 1, -1, dtype=np.int64)
     lookup[ids] = np.arange(len(ids))
-    return MeshFile(points, {k: lookup[v] for k, v in _stack(groups).items()})
+    cells = {k: lookup[v] for k, v in _stack(groups).items()}
+    if 'hexahedron27' in cells:
+        cells['hexahedron27'] = cells['hexahedron27'][:, _HEX27_GMSH_TO_VTK]
+    return MeshFile(points, cells)
 
 
 def read_inp(path):
@@ -124,7 +150,7 @@ def read_vtu(path):
     groups = {}
     for t in np.unique(types):
         if int(t) not in _VTK:
-            raise NotImplementedError(f"{path}: VTK cell type {int(t)} is not a registered first-order cell")
+            raise NotImplementedError(f"{path}: VTK cell type {int(t)} is not registered (first-order cells and type 29)")
         name, per = _VTK[int(t)]
         sel = np.flatnonzero(types == t)
         if not np.all(offs[sel] - starts[sel] == per):

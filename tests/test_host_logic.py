@@ -571,3 +571,45 @@ def test_scripts_and_package_have_no_undefined_names():
     files += sorted(glob.glob(os.path.join(root, "tests", "*.py"))) + sorted(glob.glob(os.path.join(root, "oracle", "*.py")))
     problems = [p for f in files for p in _undefined_names(f)]
     assert not problems, "\n".join(problems)
+
+
+def test_hex27_meshes_through_the_readers(tmp_path):
+    """The 27-node hexahedron of cfg 4 through the file formats: save_sol writes VTK type 29 in the kernels' own node order
+    and read_mesh reads it back unchanged; a Gmsh MSH 2.2 file (element type 12) numbers edge and face nodes differently and
+    must come back in the kernels' order -- checked geometrically: every node of every cell must sit at the reference
+    position the element's lattice gives it."""
+    import numpy as np
+    import jax_fem_b200 as jf
+    from jax_fem_b200 import basis, mesh_io
+    from jax_fem_b200.mesh_io import read_mesh
+    m = jf.box_mesh_hex27(2, 2, 1, 2.0, 1.0, 0.5)
+    pts, cells = m.points, m.cells_dict['hexahedron27']
+    fe = jf.FiniteElement(jf.Mesh(pts, cells), vec=3, dim=3, ele_type='HEX27', quadrature_order=4)
+    jf.save_sol(fe, np.zeros((len(pts), 3)), str(tmp_path / "h27.vtu"))
+    got = read_mesh(str(tmp_path / "h27.vtu"))
+    assert np.array_equal(got.cells_dict['hexahedron27'], cells) and np.allclose(got.points, pts)
+    # the derivation's VTK table is the element's lattice
+    lattice = basis.get_elements('HEX27')[3]
+    perm = mesh_io._HEX27_GMSH_TO_VTK
+    assert sorted(perm.tolist()) == list(range(27)) and perm[:8].tolist() == list(range(8))
+    # Gmsh file: gmsh_cell[perm] = vtk_cell  <=>  gmsh_cell = vtk_cell[inverse]
+    inv = np.argsort(perm)
+    with open(tmp_path / "h27.msh", "w") as f:
+        f.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n%d\n" % len(pts))
+        f.write("".join("%d %.17g %.17g %.17g\n" % (i + 1, *p) for i, p in enumerate(pts)))
+        f.write("$EndNodes\n$Elements\n%d\n" % len(cells))
+        f.write("".join("%d 12 2 0 1 %s\n" % (k + 1, " ".join(str(n + 1) for n in c[inv])) for k, c in enumerate(cells)))
+        f.write("$EndElements\n")
+    got = read_mesh(str(tmp_path / "h27.msh"))
+    c2 = got.cells_dict['hexahedron27']
+    assert np.array_equal(c2, cells)
+    # independent geometric check of the Gmsh convention itself: in a Gmsh cell, node 9 is the midpoint of vertices 0 and 3,
+    # node 20 the centre of face (0, 3, 2, 1), node 26 the cell centre (Gmsh reference manual, hexahedron27)
+    g = cells[0][inv]
+    P = got.points
+    assert np.allclose(P[g[9]], 0.5 * (P[g[0]] + P[g[3]])) and np.allclose(P[g[11]], 0.5 * (P[g[1]] + P[g[2]]))
+    assert np.allclose(P[g[20]], 0.25 * (P[g[0]] + P[g[3]] + P[g[2]] + P[g[1]])) and np.allclose(P[g[26]], P[g[:8]].mean(axis=0))
+    # and of the result: every node where the lattice says
+    X = P[c2[0]]
+    lo, ext = X[:8].min(axis=0), X[:8].max(axis=0) - X[:8].min(axis=0)
+    assert np.allclose((X - lo) / ext, lattice / 2.0)
