@@ -375,6 +375,30 @@ def main():
     ms_step, t_elem, t_bc, t_gather = time_assembly(prob, sol, args.steps, jf, torch, barrier)
     res_vec, A = step(sol)
 
+    # HEX27: the default element step takes the exact affine-cell pass wherever a cell's geometry map is affine (every cell of
+    # this box mesh); the same assembly with the pass switched off (FEM_HEX27_AFFINE=0: FP64 tensor-core kernel for every cell,
+    # what a mesh of curved cells costs) is timed beside it so that the line carries both
+    hex27_info = None
+    if args.workload == "hex27" and world == 1:
+        n_general = int(len(prob.hex27_general_cells()))
+        os.environ["FEM_HEX27_AFFINE"] = "0"
+        try:
+            pg, _ = build_problem(args.size, workload="hex27")
+        finally:
+            os.environ.pop("FEM_HEX27_AFFINE")
+        for _ in range(args.warmup):
+            pg.newton_update([sol])
+            jf.get_A(pg)
+        g_ms = time_assembly(pg, sol, max(2, args.steps // 2), jf, torch, barrier)[0]
+        del pg
+        torch.cuda.empty_cache()
+        hex27_info = {"cells": int(prob.num_cells), "cells_on_the_affine_pass": int(prob.num_cells) - n_general,
+                      "cells_on_the_general_dmma_kernel": n_general, "ms_per_step": ms_step,
+                      "ms_per_step_general_kernel_for_every_cell": g_ms,
+                      "note": "affine pass: K_e = E detJ J^-T Ghat J^-1 from reference Gram tables, exact up to rounding, chosen per cell "
+                              "on every call by an exact affinity test (DESIGN.md 4.1)"}
+        log(f"hex27: {hex27_info}")
+
     # ---- e2e: public API from pinned host buffers -------------------------------------------------------
     # Every step copies its input from pinned host memory and its result (the residual with Dirichlet rows) back.
     # The copies run on two more streams, one per direction (PCIe is full duplex), and are software-pipelined against the
@@ -670,10 +694,12 @@ def main():
                     "d2h_bytes_per_step": n_local * 8, "ms_per_step": e2e_ms,
                     "pcie_gbs_this_box": pcie,
                     "pcie_bound_ms": max(n_local * 8 / (pcie["h2d_gbs"] * 1e6), n_local * 8 / (pcie["d2h_gbs"] * 1e6))},
-            "gpu_launches": args.steps * 4 * world, "clocks": clocks, "setup_s": setup_s,
+            "gpu_launches": args.steps * world * (6 if args.workload == "hex27" and os.environ.get("FEM_HEX27_AFFINE", "1") != "0" else 4), "clocks": clocks, "setup_s": setup_s,
         }
         if solve:
             line["cg_solve"] = solve
+        if hex27_info:
+            line["hex27"] = hex27_info
         if newton:
             line["newton_solve"] = newton
         if adjoint:
