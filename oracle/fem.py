@@ -177,7 +177,7 @@ class Problem:
     """problem.py:46-128 for ONE variable (the hot path's scope).
 
     law          : oracle.laws.* object (tensor map + closed-form tangent)
-    mass_map     : vectorised f(u (...,vec), x (...,dim)) -> (...,vec), u-independent, or None
+    mass_map     : vectorised f(u (...,vec), x (...,dim)) -> (...,vec) or None; if it depends on u, mass_map_jac gives d f / d u
     surface_maps : list of such functions, one per location_fn
     internal_vars: list of (C,Q,...) arrays forwarded to the law
     """

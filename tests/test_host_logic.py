@@ -613,3 +613,26 @@ def test_hex27_meshes_through_the_readers(tmp_path):
     X = P[c2[0]]
     lo, ext = X[:8].min(axis=0), X[:8].max(axis=0) - X[:8].min(axis=0)
     assert np.allclose((X - lo) / ext, lattice / 2.0)
+
+
+def test_linear_mass_law_field_shapes():
+    """laws.LinearMass.fields: scalars stay scalars (passed by value to fem_mass_term), per-point fields are validated and
+    broadcast to (cells, quads, vec); a field of the wrong shape is refused."""
+    import numpy as np
+    import pytest
+    import torch
+    from jax_fem_b200 import laws
+    C, Q = 5, 8
+    coef, coef_f, cst, cst_f = laws.LinearMass(2.5).fields(C, Q, 1, 'cpu')
+    assert coef == 2.5 and coef_f is None and cst_f is None and np.array_equal(cst, np.zeros(3))
+    coef, coef_f, cst, cst_f = laws.LinearMass(1.0, [0., -40., 15.]).fields(C, Q, 3, 'cpu')
+    assert coef_f is None and cst_f is None and np.array_equal(cst, [0., -40., 15.])
+    a, b = np.arange(C * Q, dtype=np.float64).reshape(C, Q), np.ones((C, Q))
+    coef, coef_f, cst, cst_f = laws.LinearMass(a, torch.from_numpy(b)).fields(C, Q, 1, 'cpu')
+    assert coef_f.shape == (C, Q) and coef_f.is_contiguous() and cst_f.shape == (C, Q, 1) and torch.equal(coef_f, torch.from_numpy(a))
+    _, _, _, cst_f = laws.LinearMass(1.0, b).fields(C, Q, 3, 'cpu')              # one field for every component
+    assert cst_f.shape == (C, Q, 3) and cst_f.is_contiguous() and bool((cst_f == 1).all())
+    with pytest.raises(ValueError):
+        laws.LinearMass(np.ones((C, Q + 1))).fields(C, Q, 1, 'cpu')
+    with pytest.raises(ValueError):
+        laws.LinearMass(1.0, np.ones((C, Q, 2))).fields(C, Q, 3, 'cpu')
