@@ -383,6 +383,11 @@ int fem_adjoint_param_grad(int ele_type, int vec, int law_id, const double* law_
                            const double* sol, const double* internal_var, const double* lam,
                            const double* ref_tables, double* grad, void* stream);
 
+/* The same for HEX27 + SIMP (the 216- or 27-point rules of basis.py:58-65): grad (n_cells, n_quad). */
+int fem_hex27_adjoint_param_grad(int law_id, const double* law_params_host, const double* points, const int32_t* cells,
+                                 int64_t n_cells, const double* sol, const double* internal_var, const double* lam,
+                                 const double* ref_tables, int n_quad, double* grad, void* stream);
+
 /* small helpers used by the Newton loop */
 int fem_dot(int64_t n, const double* x, const double* y, double* result_host, double* workspace, void* stream);
 int fem_axpy(int64_t n, double alpha, const double* x, double* y, void* stream);

@@ -30,6 +30,7 @@ _SIGNATURES = {
     "fem_halo_p2p_alloc": (_i, [_vp, _i64, _i64, _vp]),
     "fem_halo_p2p_connect": (_i, [_vp, _i, _vp, _i64, _i64, _i]),
     "fem_halo_p2p_enable": (_i, [_vp, _i]),
+    "fem_hex27_adjoint_param_grad": (_i, [_i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "fem_mass_term": (_i, [_i, _i, _vp, _vp, _i64, _vp, _vp, _vp, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fem_hex27_residual_jacobian": (_i, [_i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fem_assemble_fused": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64] + [_vp] * 18 + [_i, _vp]),

@@ -520,6 +520,65 @@ __global__ void __launch_bounds__(H27A_THREADS, 2) hex27_affine_kernel(const Hex
   }
 }
 
+
+// ---- adjoint: -lambda^T dc/dtheta per quadrature point (SIMP), one CTA per cell, thread = point --------------------------
+// d r_a / d theta_q = dE/dtheta (lam' tr(eps) I + 2 mu' eps)(q) grad N_a(q) JxW_q, so the contraction with lambda is the double
+// dot of that stress derivative with grad(lambda)(q) = GL J^-1, GL = sum_n lambda_n (x) dN_n: no per-node gradient is formed
+// (solver.py:1362-1418 with problem.py:204-210 differentiated in the density).
+__global__ void __launch_bounds__(224) hex27_param_grad_kernel(const Hex27Args A, const double* __restrict__ lam,
+                                                               double* __restrict__ grad) {
+  __shared__ double X[H27_ND], U[H27_ND], L[H27_ND];
+  const int64_t c = blockIdx.x;
+  const int tid = threadIdx.x, nq = A.nq;
+  if (tid < H27_NN) {
+    const int64_t node = A.cells[c * H27_NN + tid];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      X[tid * 3 + d] = A.points[node * 3 + d];
+      U[tid * 3 + d] = A.sol[node * 3 + d];
+      L[tid * 3 + d] = lam[node * 3 + d];
+    }
+  }
+  __syncthreads();
+  const double nu = A.p[2], mu1 = 1.0 / (2.0 * (1.0 + nu)), lam1 = nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
+  for (int q = tid; q < nq; q += blockDim.x) {
+    const double* dN = A.ref + (int64_t)q * H27_ND;
+    double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, Gu[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}},
+           GL[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll 3
+    for (int n = 0; n < H27_NN; ++n) {
+      const double d0 = __ldg(dN + n * 3), d1 = __ldg(dN + n * 3 + 1), d2 = __ldg(dN + n * 3 + 2);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double x = X[n * 3 + i], u = U[n * 3 + i], l = L[n * 3 + i];
+        J[i][0] = fma(x, d0, J[i][0]);  J[i][1] = fma(x, d1, J[i][1]);  J[i][2] = fma(x, d2, J[i][2]);
+        Gu[i][0] = fma(u, d0, Gu[i][0]); Gu[i][1] = fma(u, d1, Gu[i][1]); Gu[i][2] = fma(u, d2, Gu[i][2]);
+        GL[i][0] = fma(l, d0, GL[i][0]); GL[i][1] = fma(l, d1, GL[i][1]); GL[i][2] = fma(l, d2, GL[i][2]);
+      }
+    }
+    double inv[3][3];
+    const double w = det_inv3(J, inv) * __ldg(A.ref + (int64_t)nq * H27_ND + q);
+    double ug[3][3], lg[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        ug[i][d] = Gu[i][0] * inv[0][d] + Gu[i][1] * inv[1][d] + Gu[i][2] * inv[2][d];
+        lg[i][d] = GL[i][0] * inv[0][d] + GL[i][1] * inv[1][d] + GL[i][2] * inv[2][d];
+      }
+    const double theta = A.iv[c * nq + q];
+    const double dE = (A.p[0] - A.p[1]) * A.p[3] * pow(theta, A.p[3] - 1.0);       // E = Emin + (Emax - Emin) theta^p
+    const double tr = ug[0][0] + ug[1][1] + ug[2][2];
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        acc = fma(dE * (mu1 * (ug[i][d] + ug[d][i]) + (i == d ? lam1 * tr : 0.0)), lg[i][d], acc);
+    grad[c * nq + q] = -acc * w;
+  }
+}
+
 }  // namespace
 }  // namespace femb200
 
@@ -573,6 +632,24 @@ extern "C" int fem_hex27_residual_jacobian(int law_id, const double* law_params_
     FEM_LAUNCH_CHECK();
   }
   hex27_kernel<<<grid, H27_THREADS, smem, (cudaStream_t)stream>>>(A);
+  FEM_LAUNCH_CHECK();
+  return FEM_OK;
+}
+
+extern "C" int fem_hex27_adjoint_param_grad(int law_id, const double* law_params_host, const double* points,
+                                            const int32_t* cells, int64_t n_cells, const double* sol,
+                                            const double* internal_var, const double* lam, const double* ref_tables,
+                                            int n_quad, double* grad, void* stream) {
+  if (int e = check_device()) return e;
+  FEM_REQUIRE(points && cells && sol && internal_var && lam && ref_tables && grad && law_params_host, "null pointer");
+  FEM_REQUIRE(law_id == FEM_LAW_SIMP, "the HEX27 parameter gradient is registered for SIMP (per-point density) only");
+  FEM_REQUIRE(n_quad > 0 && n_quad <= 512, "unsupported number of quadrature points");
+  if (n_cells == 0) return FEM_OK;
+  Hex27Args A{};
+  A.points = points; A.cells = cells; A.sol = sol; A.iv = internal_var; A.ref = ref_tables; A.C = n_cells; A.nq = n_quad;
+  A.law = law_id;
+  for (int i = 0; i < 8; ++i) A.p[i] = law_params_host[i];
+  hex27_param_grad_kernel<<<(unsigned)n_cells, 224, 0, (cudaStream_t)stream>>>(A, lam, grad);
   FEM_LAUNCH_CHECK();
   return FEM_OK;
 }

@@ -16,7 +16,7 @@ import time
 import numpy as np
 import torch
 
-from . import _lib, logger
+from . import _lib, laws, logger
 from .sparse import CSRMatrix
 
 ################################################################################
@@ -336,6 +336,12 @@ def implicit_vjp(problem, sol_list, params, v_list, adjoint_solver_options):
         raise ValueError("implicit_vjp needs a per-quadrature-point parameter in problem.internal_vars")
     grad = torch.empty_like(iv)
     law = problem._law
+    if problem.ele_type == 'HEX27':
+        _lib.check(_lib.load().fem_hex27_adjoint_param_grad(
+            law.law_id, _lib.host_doubles(law.params()), _lib.ptr(problem._points), _lib.ptr(problem._cells), problem.num_cells,
+            _lib.ptr(problem._as_sol(sol_list)), _lib.ptr(iv), _lib.ptr(lam), _lib.ptr(problem._ref), fe.num_quads,
+            _lib.ptr(grad), _lib.stream_ptr()))
+        return grad
     _lib.check(_lib.load().fem_adjoint_param_grad(
         _lib.ELE[problem.ele_type], fe.vec, law.law_id, _lib.host_doubles(law.params()), _lib.ptr(problem._points),
         _lib.ptr(problem._cells), problem.num_cells, _lib.ptr(problem._as_sol(sol_list)), _lib.ptr(iv), _lib.ptr(lam),
@@ -351,9 +357,8 @@ def ad_wrapper(problem, solver_options={}, adjoint_solver_options={}):
     autograd Function whose backward is the implicit adjoint, so ``objective(fwd_pred(params)).backward()``
     fills ``params.grad`` exactly as ``jax.grad`` does in the reference."""
 
-    if problem.ele_type == 'HEX27':
-        raise NotImplementedError("ad_wrapper: the parameter-gradient kernel is registered for HEX8 and QUAD4 only (HEX27 + SIMP "
-                                  "would fail in backward); it does not fall back")
+    if problem.ele_type == 'HEX27' and not isinstance(problem._law, laws.SIMP):
+        raise NotImplementedError("ad_wrapper on HEX27: the parameter-gradient kernel is registered for SIMP only; it does not fall back")
 
     class _Solve(torch.autograd.Function):
         @staticmethod
