@@ -182,6 +182,9 @@ class Problem:
                 if len(b) == 0:
                     continue
                 if isinstance(self.get_surface_maps()[k], laws.SurfaceLaw):       # u-dependent: device face kernels
+                    if self.ele_type == 'HEX27':
+                        raise NotImplementedError("solution-dependent surface maps are registered for HEX8 and QUAD4 "
+                                                  "(the face tangent kernel does not cover 9-node faces); nothing falls back")
                     self._face_sets.append(self._build_face_set(k, b, self.get_surface_maps()[k]))
                     continue
                 x = fe.get_physical_surface_quad_points(b)

@@ -720,6 +720,23 @@ def test_solution_dependent_surface_maps_match_oracle(case, mode, monkeypatch):
     assert relmax(host(x), fem.solver(opb)) <= SOL_TOL
 
 
+def test_solution_dependent_maps_on_hex27_are_refused():
+    """Registered u-dependent surface / mass laws cover HEX8 and QUAD4; on HEX27 they raise instead of assembling something
+    else (a first attempt at the 9-node faces differed from the oracle's tangent by 3e-3 and was withdrawn)."""
+    import jax_fem_b200 as jf
+    import gpu_problems as gp
+    from jax_fem_b200 import laws
+    m = jf.box_mesh_hex27(2, 1, 1, 1.0, 1.0, 1.0)
+    pts, cells = m.points, m.cells_dict['hexahedron27']
+    hi = lambda p: p[0] > 0.99
+    with pytest.raises(NotImplementedError):
+        gp.SpringFoundation(jf.Mesh(pts, cells), vec=3, dim=3, ele_type='HEX27', location_fns=[hi, hi])
+    P = type("M27", (jf.Problem,), {"get_tensor_map": lambda self: laws.LinearElasticity(70e3, 0.3),
+                                    "get_mass_map": lambda self: laws.LinearMass(1.0)})
+    with pytest.raises(NotImplementedError):
+        P(jf.Mesh(pts, cells), vec=3, dim=3, ele_type='HEX27')
+
+
 @pytest.mark.parametrize("case", ["heat_step_hex8", "heat_step_quad4", "phase_field_hex8", "foundation_hex8", "foundation_quad4"])
 def test_solution_dependent_mass_maps_match_oracle(case):
     """registered u-dependent mass maps (laws.LinearMass, csrc/mass.cu): the backward-Euler heat capacity
