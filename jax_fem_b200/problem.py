@@ -182,9 +182,6 @@ class Problem:
                 if len(b) == 0:
                     continue
                 if isinstance(self.get_surface_maps()[k], laws.SurfaceLaw):       # u-dependent: device face kernels
-                    if self.ele_type == 'HEX27':
-                        raise NotImplementedError("solution-dependent surface maps are registered for HEX8 and QUAD4 "
-                                                  "(the face tangent kernel does not cover 9-node faces); nothing falls back")
                     self._face_sets.append(self._build_face_set(k, b, self.get_surface_maps()[k]))
                     continue
                 x = fe.get_physical_surface_quad_points(b)
@@ -203,7 +200,11 @@ class Problem:
         scale x weight per face quadrature point, and for every boundary node its (face, local node) pairs."""
         fe, dev = self.fes[0], self.device
         _, nanson = fe.get_face_shape_grads(b)                                     # (F, FQ)
-        face_nodes = fe.face_inds[b[:, 1]]                                         # (F, V) local nodes of the cell on the face
+        # local nodes of the cell that live on each local face: those whose face shape values do not vanish (fe.face_inds only
+        # lists the face's VERTICES, which is all of them for HEX8 / QUAD4 but 4 of the 9 for HEX27)
+        support = [np.flatnonzero(np.abs(fe.face_shape_vals[l]).max(axis=0) > 1e-12) for l in range(len(fe.face_shape_vals))]
+        assert len({len(sup) for sup in support}) == 1
+        face_nodes = np.stack(support)[b[:, 1]]                                    # (F, V)
         glob = fe.cells[b[:, 0][:, None], face_nodes]                              # (F, V) global nodes
         fidx = np.repeat(np.arange(len(b)), face_nodes.shape[1])
         order = np.lexsort((fidx, glob.reshape(-1)))                               # by node, then ascending face

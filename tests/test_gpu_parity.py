@@ -720,17 +720,38 @@ def test_solution_dependent_surface_maps_match_oracle(case, mode, monkeypatch):
     assert relmax(host(x), fem.solver(opb)) <= SOL_TOL
 
 
-def test_solution_dependent_maps_on_hex27_are_refused():
-    """Registered u-dependent surface / mass laws cover HEX8 and QUAD4; on HEX27 they raise instead of assembling something
-    else (a first attempt at the 9-node faces differed from the oracle's tangent by 3e-3 and was withdrawn)."""
+def test_solution_dependent_surface_map_on_hex27():
+    """The registered Robin law on the 9-node faces of HEX27 cells (spring foundation + dead load), curved cells: residual, CSR
+    values and the Newton solution against the oracle.  (The face set must hold every cell node that lives on the face, not only
+    the four vertices fe.face_inds lists.)  Registered mass laws are refused on HEX27."""
     import jax_fem_b200 as jf
     import gpu_problems as gp
     from jax_fem_b200 import laws
-    m = jf.box_mesh_hex27(2, 1, 1, 1.0, 1.0, 1.0)
-    pts, cells = m.points, m.cells_dict['hexahedron27']
-    hi = lambda p: p[0] > 0.99
-    with pytest.raises(NotImplementedError):
-        gp.SpringFoundation(jf.Mesh(pts, cells), vec=3, dim=3, ele_type='HEX27', location_fns=[hi, hi])
+    m = jf.box_mesh_hex27(3, 2, 2, 1.5, 1.0, 0.8)
+    pts, cells = m.points.copy(), m.cells_dict['hexahedron27']
+    rng = np.random.default_rng(12)
+    inner = (pts[:, 0] > 0.03) & (pts[:, 0] < 1.47) & (pts[:, 1] < 0.97)
+    pts[inner] += 0.01 * rng.uniform(-1, 1, (int(inner.sum()), 3))
+    lo = lambda p: p[0] < 0.02
+    hi = lambda p: p[0] > 1.48
+    side = lambda p: p[1] > 0.98
+    bc = [[lo] * 3, [0, 1, 2], [lambda p: 0., lambda p: 0.01, lambda p: 0.]]
+    k = np.array([3e3, 5e3, 7e3])
+    prob = gp.SpringFoundation(jf.Mesh(pts, cells), vec=3, dim=3, ele_type='HEX27', quadrature_order=4, dirichlet_bc_info=bc,
+                               location_fns=[hi, side])
+    opb = fem.Problem(fem.Mesh(pts, cells), 3, 3, ele_type='HEX27', quadrature_order=4, dirichlet_bc_info=bc, location_fns=[hi, side],
+                      law=olaws.LinearElastic(70e3, 0.3),
+                      surface_maps=[lambda u, x: k * u, lambda u, x: np.array([0., 0., 100.]) + 0. * u],
+                      surface_map_jacs=[lambda u, x: np.broadcast_to(np.diag(k), u.shape + (3,)), None])
+    sol = 0.01 * rng.standard_normal((len(pts), 3))
+    res = prob.newton_update([torch.from_numpy(sol).cuda()])[0]
+    A = jf.get_A(prob)
+    ores = opb.newton_update(sol)
+    oA = fem.get_A(opb)
+    assert np.array_equal(host(A.getValuesCSR()[1]), oA.indices)
+    assert relmax(host(A.data), oA.data) <= VAL_TOL and relmax(host(res), ores) <= VAL_TOL
+    x = jf.solver(prob, {'jax_solver': {}})[0]
+    assert relmax(host(x), fem.solver(opb)) <= SOL_TOL
     P = type("M27", (jf.Problem,), {"get_tensor_map": lambda self: laws.LinearElasticity(70e3, 0.3),
                                     "get_mass_map": lambda self: laws.LinearMass(1.0)})
     with pytest.raises(NotImplementedError):
