@@ -231,7 +231,8 @@ int fem_gather_residual(int vec, int nn, int64_t n_nodes, const int32_t* nc_ptr,
  *      elastic foundation.  Runs between the element kernel and the gathers and ADDS, in place, to the element residuals Re
  *      (n_cells, nn*vec) and to the staged row blocks Ke in the REFERENCE block layout of fem_element_residual_jacobian (not
  *      the tile-major rows of fem_element_tiles); Ke == NULL: residual only.  shape_vals: [n_quad][nn] (basis.py:141-175).
- *      HEX8 (vec 1, 3) and QUAD4 (vec 1, 2); one thread per (cell, node) owns its row block: deterministic, no atomics. */
+ *      HEX8 (vec 1, 3), QUAD4 (vec 1, 2) and HEX27 (vec 3; up to 216 points); one thread per (cell, node) owns its row block:
+ *      deterministic, no atomics.                                                                                        */
 int fem_mass_term(int ele_type, int vec, const double* points, const int32_t* cells, int64_t n_cells, const double* sol,
                   const double* ref_tables, const double* shape_vals, int n_quad, double coef, const double* coef_field,
                   const double* const_host, const double* const_field, const int32_t* corner_pos, double* Ke, double* Re,

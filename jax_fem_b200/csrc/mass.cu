@@ -19,7 +19,8 @@
 namespace femb200 {
 namespace {
 
-constexpr int kMassMaxQ = 27;
+constexpr int kMassMaxQ = 27;      // HEX8 / QUAD4 (up to the 27-point rule)
+constexpr int kMassMaxQ27 = 216;   // HEX27 (basis.py:64: default degree 10 = 6 x 6 x 6 points)
 
 struct MassArgs {
   int64_t C;
@@ -37,10 +38,10 @@ struct MassArgs {
   int nq;
 };
 
-template <int NN, int DIM, int VEC, int CPB>
+template <int NN, int DIM, int VEC, int CPB, int MAXQ>
 __global__ void __launch_bounds__(CPB* NN) mass_term_kernel(const MassArgs A) {
   constexpr int VV = VEC * VEC, ROW = (NN * VV + 1) / 2 * 2;
-  __shared__ double X[CPB][NN * DIM], U[CPB][NN * VEC], AQ[CPB][kMassMaxQ], BQ[CPB][kMassMaxQ * VEC];
+  __shared__ double X[CPB][NN * DIM], U[CPB][NN * VEC], AQ[CPB][MAXQ], BQ[CPB][MAXQ * VEC];
   const int lc = threadIdx.x / NN, a = threadIdx.x % NN;
   const int64_t c = (int64_t)blockIdx.x * CPB + lc;
   const bool act = c < A.C;
@@ -108,8 +109,8 @@ __global__ void __launch_bounds__(CPB* NN) mass_term_kernel(const MassArgs A) {
 
 template <int NN, int DIM, int VEC>
 int launch_mass(const MassArgs& A, cudaStream_t st) {
-  constexpr int CPB = 128 / NN;
-  mass_term_kernel<NN, DIM, VEC, CPB><<<(unsigned)((A.C + CPB - 1) / CPB), CPB * NN, 0, st>>>(A);
+  constexpr int CPB = 128 / NN, MAXQ = NN == 27 ? kMassMaxQ27 : kMassMaxQ;
+  mass_term_kernel<NN, DIM, VEC, CPB, MAXQ><<<(unsigned)((A.C + CPB - 1) / CPB), CPB * NN, 0, st>>>(A);
   FEM_LAUNCH_CHECK();
   return FEM_OK;
 }
@@ -125,7 +126,7 @@ extern "C" int fem_mass_term(int ele_type, int vec, const double* points, const 
                              const int32_t* corner_pos, double* Ke, double* Re, void* stream) {
   if (int e = check_device()) return e;
   FEM_REQUIRE(points && cells && sol && ref_tables && shape_vals && const_host && Re, "null pointer");
-  FEM_REQUIRE(n_quad > 0 && n_quad <= kMassMaxQ, "unsupported number of quadrature points");
+  FEM_REQUIRE(n_quad > 0 && n_quad <= (ele_type == FEM_ELE_HEX27 ? kMassMaxQ27 : kMassMaxQ), "unsupported number of quadrature points");
   if (n_cells == 0) return FEM_OK;
   MassArgs A{};
   A.C = n_cells; A.cells = cells; A.points = points; A.sol = sol; A.ref = ref_tables; A.vals = shape_vals;
@@ -136,6 +137,7 @@ extern "C" int fem_mass_term(int ele_type, int vec, const double* points, const 
 #define FEM_M(E, NN, DIM, V) \
   if (ele_type == E && vec == V) return launch_mass<NN, DIM, V>(A, st);
   FEM_M(FEM_ELE_HEX8, 8, 3, 1) FEM_M(FEM_ELE_HEX8, 8, 3, 3) FEM_M(FEM_ELE_QUAD4, 4, 2, 1) FEM_M(FEM_ELE_QUAD4, 4, 2, 2)
+  FEM_M(FEM_ELE_HEX27, 27, 3, 3)
 #undef FEM_M
   set_error("fem_mass_term: unregistered (ele_type=%d, vec=%d)", ele_type, vec);
   return FEM_EINVAL;

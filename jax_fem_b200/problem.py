@@ -164,8 +164,6 @@ class Problem:
         self._mass_law = None
         mass_map = self.get_mass_map() if hasattr(self, 'get_mass_map') else None
         if isinstance(mass_map, laws.MassLaw):                                     # u-dependent: device kernel (csrc/mass.cu)
-            if self.ele_type == 'HEX27':
-                raise NotImplementedError("solution-dependent mass maps are registered for HEX8 and QUAD4")
             self._mass_law = mass_map
             self._shape_vals = torch.from_numpy(np.ascontiguousarray(fe.shape_vals)).to(self.device)
         elif mass_map is not None:

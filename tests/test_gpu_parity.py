@@ -723,7 +723,7 @@ def test_solution_dependent_surface_maps_match_oracle(case, mode, monkeypatch):
 def test_solution_dependent_surface_map_on_hex27():
     """The registered Robin law on the 9-node faces of HEX27 cells (spring foundation + dead load), curved cells: residual, CSR
     values and the Newton solution against the oracle.  (The face set must hold every cell node that lives on the face, not only
-    the four vertices fe.face_inds lists.)  Registered mass laws are refused on HEX27."""
+    the four vertices fe.face_inds lists.)"""
     import jax_fem_b200 as jf
     import gpu_problems as gp
     from jax_fem_b200 import laws
@@ -752,13 +752,10 @@ def test_solution_dependent_surface_map_on_hex27():
     assert relmax(host(A.data), oA.data) <= VAL_TOL and relmax(host(res), ores) <= VAL_TOL
     x = jf.solver(prob, {'jax_solver': {}})[0]
     assert relmax(host(x), fem.solver(opb)) <= SOL_TOL
-    P = type("M27", (jf.Problem,), {"get_tensor_map": lambda self: laws.LinearElasticity(70e3, 0.3),
-                                    "get_mass_map": lambda self: laws.LinearMass(1.0)})
-    with pytest.raises(NotImplementedError):
-        P(jf.Mesh(pts, cells), vec=3, dim=3, ele_type='HEX27')
 
 
-@pytest.mark.parametrize("case", ["heat_step_hex8", "heat_step_quad4", "phase_field_hex8", "foundation_hex8", "foundation_quad4"])
+@pytest.mark.parametrize("case", ["heat_step_hex8", "heat_step_quad4", "phase_field_hex8", "foundation_hex8", "foundation_quad4",
+                                  "foundation_hex27"])
 def test_solution_dependent_mass_maps_match_oracle(case):
     """registered u-dependent mass maps (laws.LinearMass, csrc/mass.cu): the backward-Euler heat capacity
     rho Cp (T - T_old) / dt of applications/thermal_mechanical (constant coefficient, per-point T_old), the phase-field driving
@@ -769,13 +766,20 @@ def test_solution_dependent_mass_maps_match_oracle(case):
     from jax_fem_b200 import laws
     rng = np.random.default_rng(21)
     quad = case.endswith("quad4")
+    extra = {}
     if quad:
         m = jf.rectangle_mesh(8, 6, 1., 1.)
         pts, cells, ele, dim = m.points + 0.01 * rng.uniform(-1, 1, m.points.shape), m.cells_dict['quad'], 'QUAD4', 2
+    elif case.endswith("hex27"):
+        m = jf.box_mesh_hex27(2, 2, 1, 1., 1., 0.5)
+        pts, cells, ele, dim = m.points.copy(), m.cells_dict['hexahedron27'], 'HEX27', 3
+        inner = (pts[:, 0] > 0.02) & (pts[:, 0] < 0.98)
+        pts[inner] += 0.01 * rng.uniform(-1, 1, (int(inner.sum()), 3))
+        extra = {"quadrature_order": 4}
     else:
         pts, cells = perturbed_box(5, seed=4)
         ele, dim = 'HEX8', 3
-    nq = 4 if quad else 8
+    nq = 4 if quad else (27 if ele == 'HEX27' else 8)
     C = len(cells)
     lo = lambda p: p[0] < 0.02
     hi = lambda p: p[0] > 0.98
@@ -801,8 +805,8 @@ def test_solution_dependent_mass_maps_match_oracle(case):
             fields = lambda: (host(mass.coef), host(mass.const)[..., None])
     P = type("MassProblem", (jf.Problem,), {"get_tensor_map": lambda self: law, "get_mass_map": lambda self: mass,
                                             "get_surface_maps": lambda self: [lambda u, x: np.full(vec, 3.0)]})
-    prob = P(jf.Mesh(pts, cells), vec=vec, dim=dim, ele_type=ele, dirichlet_bc_info=bc, location_fns=[hi])
-    opb = fem.Problem(fem.Mesh(pts, cells), vec, dim, ele_type=ele, dirichlet_bc_info=bc, location_fns=[hi], law=olaw,
+    prob = P(jf.Mesh(pts, cells), vec=vec, dim=dim, ele_type=ele, dirichlet_bc_info=bc, location_fns=[hi], **extra)
+    opb = fem.Problem(fem.Mesh(pts, cells), vec, dim, ele_type=ele, dirichlet_bc_info=bc, location_fns=[hi], law=olaw, **extra,
                       mass_map=lambda u, x: fields()[0][..., None] * u + fields()[1],
                       mass_map_jac=lambda u, x: fields()[0][..., None, None] * np.eye(vec),
                       surface_maps=[lambda u, x: 3.0 + 0. * u])
@@ -857,7 +861,7 @@ def test_c_abi_empty_inputs_and_argument_errors():
                                     None, None, P(Re), None), "null pointer")
     # unregistered combinations
     assert einval(lib.fem_element_residual_jacobian(0, 2, 1, params, P(pts), P(cells), 1, P(sol), None, P(ref), None, None, P(Re), None), "")
-    assert einval(lib.fem_mass_term(2, 3, P(pts), P(cells), 1, P(sol), P(ref), P(d(64)), 8, 1.0, None, _lib.host_doubles([0.] * 3),
+    assert einval(lib.fem_mass_term(2, 1, P(pts), P(cells), 1, P(sol), P(ref), P(d(64)), 8, 1.0, None, _lib.host_doubles([0.]),
                                     None, None, None, P(Re), None), "unregistered")
     assert einval(lib.fem_mass_term(0, 1, P(pts), P(cells), 1, P(sol), P(ref), P(d(64)), 64, 1.0, None, _lib.host_doubles([0.]), None,
                                     None, None, P(Re), None), "quadrature")
